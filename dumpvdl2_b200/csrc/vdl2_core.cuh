@@ -1,0 +1,613 @@
+/*
+ * vdl2_core.cuh — per-channel / per-burst device functions of libvdl2gpu.so.
+ *
+ * Everything here is __host__ __device__ so that tests/hostsim can compile the very same source with
+ * g++ (-ffp-contract=off) and step it on the CPU against the oracle BEFORE GPU time is spent.  The host
+ * instantiation is test-only; the product never runs it (no CPU fallback).
+ *
+ * Floating-point discipline: the reference source read strictly (no fast-math, no contraction).  Every
+ * float/double operation goes through an explicit round-to-nearest intrinsic so that nvcc can neither
+ * fuse (FMA) nor reassociate it; promotions to double happen exactly where C's usual arithmetic
+ * conversions put them in the reference (M_PI, M_PI_4 are double there).
+ * Reference citations are file:line under /root/reference.
+ */
+#ifndef VDL2_CORE_CUH
+#define VDL2_CORE_CUH
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include "vdl2_types.h"
+
+#if defined(__CUDACC__)
+#define VDL2_HD __host__ __device__ __forceinline__
+#else
+#define VDL2_HD static inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define F_MUL(a, b) __fmul_rn((a), (b))
+#define F_ADD(a, b) __fadd_rn((a), (b))
+#define F_SUB(a, b) __fsub_rn((a), (b))
+#define F_DIV(a, b) __fdiv_rn((a), (b))
+#define D_MUL(a, b) __dmul_rn((a), (b))
+#define D_ADD(a, b) __dadd_rn((a), (b))
+#define D_SUB(a, b) __dsub_rn((a), (b))
+#define D_DIV(a, b) __ddiv_rn((a), (b))
+#define D_SQRT(a) __dsqrt_rn((a))
+#define D_TO_F(a) __double2float_rn((a))
+#define VDL2_ATOMIC_ADD_U32(p, v) atomicAdd((unsigned int *)(p), (unsigned int)(v))
+#define VDL2_ATOMIC_ADD_I32(p, v) atomicAdd((int *)(p), (int)(v))
+#define VDL2_THREADFENCE() __threadfence()
+#else
+#define F_MUL(a, b) ((float)(a) * (float)(b))
+#define F_ADD(a, b) ((float)(a) + (float)(b))
+#define F_SUB(a, b) ((float)(a) - (float)(b))
+#define F_DIV(a, b) ((float)(a) / (float)(b))
+#define D_MUL(a, b) ((double)(a) * (double)(b))
+#define D_ADD(a, b) ((double)(a) + (double)(b))
+#define D_SUB(a, b) ((double)(a) - (double)(b))
+#define D_DIV(a, b) ((double)(a) / (double)(b))
+#define D_SQRT(a) sqrt((double)(a))
+#define D_TO_F(a) ((float)(a))
+static inline uint32_t vdl2_host_fetch_add_u32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline int32_t vdl2_host_fetch_add_i32(int32_t *p, int32_t v) { int32_t o = *p; *p = o + v; return o; }
+#define VDL2_ATOMIC_ADD_U32(p, v) vdl2_host_fetch_add_u32((uint32_t *)(p), (uint32_t)(v))
+#define VDL2_ATOMIC_ADD_I32(p, v) vdl2_host_fetch_add_i32((int32_t *)(p), (int32_t)(v))
+#define VDL2_THREADFENCE() do {} while (0)
+#endif
+
+#define VDL2_PI 3.14159265358979323846          /* M_PI */
+#define VDL2_TWO_PI 6.28318530717958647692      /* 2.0f * M_PI evaluated in double */
+#define VDL2_PI_4 0.78539816339744830962        /* M_PI_4 */
+/* smallest floats strictly greater than the double constants: `f > M_PI` (float promoted to double)
+ * is the same predicate as `f >= VDL2_PI_F_ABOVE` */
+#define VDL2_PI_F_ABOVE 3.14159274101257324f
+#define VDL2_TWO_PI_F_ABOVE 6.28318548202514648f
+
+/* ------------------------------------------------------------------------------------------------
+ * K2: demodulator + header decode, one decimated sample at a time      src/demod.c:205-286
+ * ---------------------------------------------------------------------------------------------- */
+struct vdl2_chan {
+	float prev_phi, prev_dphi, dphi, pherr0, pherr1, pherr2, ppm_error, mag_lp, mag_nf, frame_pwr;
+	int32_t ring_pos, sclk, nfcnt, frame_pwr_cnt;
+	uint32_t state;
+	uint64_t acc;                /* last 64 burst bits, newest in bit 0 */
+	uint32_t nbits, need_bits, datalen, syndrome;
+	int32_t slot;
+	uint32_t burst_seq;
+	uint64_t sync_dec_index;
+	uint32_t freq;
+	uint32_t cnt_sync, cnt_hdr_good;
+};
+
+struct vdl2_event_rec {          /* == vdl2gpu_event / vo_event */
+	uint32_t channel, kind;
+	uint64_t dec_index;
+	int32_t i[8];
+	float f[8];
+};
+
+struct vdl2_k2_env {
+	const float *pr_phase;       /* 16 */
+	const float *lr_X;           /* 16 */
+	float lr_denom;
+	float max_ppm;
+	uint32_t s27;                /* first 27 scrambler output bits, first bit in bit 26 */
+	vdl2_burst_slot *pool;
+	int32_t *free_list;
+	uint32_t *ready;
+	vdl2_queue_ctl *ctl;
+	vdl2_event_rec *events;
+	uint32_t event_cap;
+	uint32_t trace;
+	uint32_t *cnt_bursts;        /* per-channel counter plane */
+};
+
+VDL2_HD uint32_t vdl2_dec_state(const vdl2_chan &v) { return (v.state >> VDL2_DEC_SHIFT) & 3u; }
+VDL2_HD void vdl2_set_dec_state(vdl2_chan &v, uint32_t s) { v.state = (v.state & VDL2_ST_LOCKED) | (s << VDL2_DEC_SHIFT); }
+
+/* src/demod.c:205-220 */
+VDL2_HD void vdl2_demod_reset(vdl2_chan &v) {
+	v.state = (VDL2_DEC_HEADER << VDL2_DEC_SHIFT);      /* DM_INIT + DEC_HEADER */
+	v.need_bits = VDL2_HEADER_LEN;
+	v.nbits = 0;
+	v.acc = 0;
+	v.sclk = 0;
+	v.pherr1 = v.pherr2 = 1000.f;
+	v.frame_pwr = 0.f;
+	v.frame_pwr_cnt = 0;
+}
+
+/* src/demod.c:379-392 */
+VDL2_HD void vdl2_chan_init(vdl2_chan &v, uint32_t freq) {
+	memset(&v, 0, sizeof(v));
+	v.mag_nf = 2.0f;
+	v.freq = freq;
+	v.slot = -1;
+	vdl2_demod_reset(v);
+}
+
+VDL2_HD void vdl2_emit_event(const vdl2_k2_env &env, const vdl2_event_rec &e) {
+	uint32_t k = VDL2_ATOMIC_ADD_U32(&env.ctl->n_events, 1u);
+	if(k < env.event_cap) env.events[k] = e;
+}
+
+/* src/decode.c:55-61 */
+VDL2_HD uint32_t vdl2_header_syndrome(uint32_t word) {
+	const uint32_t rows[VDL2_HDRFECLEN] = { 0x001FFF0u, 0x07E1FE8u, 0x18E61E4u, 0x1B6A662u, 0x0D3CAA1u };
+	uint32_t syn = 0;
+#pragma unroll
+	for(int r = 0; r < VDL2_HDRFECLEN; r++) {
+		uint32_t x = word & rows[r];
+		x ^= x >> 16; x ^= x >> 8; x ^= x >> 4; x ^= x >> 2; x ^= x >> 1;
+		syn |= (x & 1u) << (VDL2_HDRFECLEN - 1 - r);
+	}
+	return syn;
+}
+
+/* error pattern per syndrome (src/decode.c:63-96): syndromes of single-bit errors map back to that bit,
+ * the seven remaining syndromes to the reference's chosen double-bit patterns. */
+VDL2_HD uint32_t vdl2_header_error_pattern(uint32_t syn) {
+	switch(syn) {
+		case 0: return 0;
+		case 3: return 0x0800004u; case 5: return 0x0800002u; case 13: return 0x1100000u;
+		case 18: return 0x0804000u; case 20: return 0x0808000u; case 23: return 0x1010000u;
+		default: break;
+	}
+	/* single-bit: find the column of the check matrix equal to syn */
+	const uint32_t rows[VDL2_HDRFECLEN] = { 0x001FFF0u, 0x07E1FE8u, 0x18E61E4u, 0x1B6A662u, 0x0D3CAA1u };
+	for(int bit = 0; bit < VDL2_HEADER_LEN; bit++) {
+		uint32_t col = 0;
+#pragma unroll
+		for(int r = 0; r < VDL2_HDRFECLEN; r++) col |= ((rows[r] >> bit) & 1u) << (VDL2_HDRFECLEN - 1 - r);
+		if(col == syn) return 1u << bit;
+	}
+	return 0;
+}
+
+VDL2_HD uint32_t vdl2_synd_weight(uint32_t syn) {          /* src/decode.c:98-100 */
+	if(syn == 0) return 0;
+	return (syn == 3 || syn == 5 || syn == 13 || syn == 18 || syn == 20 || syn == 23) ? 2u : 1u;
+}
+
+VDL2_HD int vdl2_fec_octets_for(uint32_t len) {             /* src/decode.c:124-133 */
+	return len < 3 ? 0 : len < 31 ? 2 : len < 68 ? 4 : 6;
+}
+
+VDL2_HD uint32_t vdl2_reverse17(uint32_t v) {               /* reverse(v, 17): src/bitstream.c:152-164 */
+	uint32_t r = 0;
+#pragma unroll
+	for(int b = 0; b < VDL2_TRLEN; b++) r |= ((v >> b) & 1u) << (VDL2_TRLEN - 1 - b);
+	return r;
+}
+
+/* src/demod.c:98-103 */
+VDL2_HD float vdl2_para_vertex(float x, float y1, float y2, float y3) {
+	const float d = 3.f, d2 = 6.f, denom = -54.f;   /* d = SYNC_SKIP, denom = (float)(d * 2*d * (-d)) */
+	float xd = F_SUB(x, d), x2d = F_SUB(x, d2);
+	float qa = F_DIV(F_ADD(F_ADD(F_MUL(x, F_SUB(y2, y1)), F_MUL(xd, F_SUB(y1, y3))), F_MUL(x2d, F_SUB(y3, y2))), denom);
+	float qb = F_DIV(F_ADD(F_ADD(F_MUL(F_MUL(x, x), F_SUB(y1, y2)), F_MUL(F_MUL(xd, xd), F_SUB(y3, y1))),
+				F_MUL(F_MUL(x2d, x2d), F_SUB(y2, y3))), denom);
+	return F_DIV(-qb, F_MUL(2.f, qa));
+}
+
+/* src/demod.c:105-198.  `ring` points at this channel's column, consecutive phases `rs` floats apart. */
+VDL2_HD int vdl2_preamble_metric(vdl2_chan &v, const float *ring, int rs, const vdl2_k2_env &env,
+		uint32_t chan_idx, uint64_t dec_index) {
+	float err[VDL2_PREAMBLE_SYMS];
+	int idx = v.ring_pos + VDL2_SPS;
+	if(idx >= VDL2_SYNC_BUFLEN) idx -= VDL2_SYNC_BUFLEN;
+	float unwrap = 0.f;
+	float prev = F_SUB(ring[idx * rs], env.pr_phase[0]);
+	float mean = prev;
+	err[0] = prev;
+#pragma unroll
+	for(int i = 1; i < VDL2_PREAMBLE_SYMS; i++) {
+		idx += VDL2_SPS;
+		if(idx >= VDL2_SYNC_BUFLEN) idx -= VDL2_SYNC_BUFLEN;
+		float cur = F_SUB(ring[idx * rs], env.pr_phase[i]);
+		float step = F_SUB(cur, prev);
+		prev = cur;
+		if(step >= VDL2_PI_F_ABOVE) unwrap = D_TO_F(D_SUB((double)unwrap, VDL2_TWO_PI));
+		else if(step <= -VDL2_PI_F_ABOVE) unwrap = D_TO_F(D_ADD((double)unwrap, VDL2_TWO_PI));
+		err[i] = F_ADD(cur, unwrap);
+		mean = F_ADD(mean, err[i]);
+	}
+	mean = F_MUL(mean, 0.0625f);               /* /= 16: exact power-of-two scaling */
+	float slope = 0.f;
+#pragma unroll
+	for(int i = 0; i < VDL2_PREAMBLE_SYMS; i++) {
+		err[i] = F_SUB(err[i], mean);
+		slope = F_ADD(slope, F_MUL(env.lr_X[i], err[i]));
+	}
+	slope = F_DIV(slope, env.lr_denom);
+	float p0 = 0.f;
+#pragma unroll
+	for(int i = 0; i < VDL2_PREAMBLE_SYMS; i++) {
+		float e = F_SUB(err[i], F_MUL(slope, env.lr_X[i]));
+		p0 = F_ADD(p0, F_MUL(e, e));
+	}
+	v.pherr0 = p0;
+	if(v.pherr1 < 4.f && p0 > v.pherr1) {
+		float vertex = vdl2_para_vertex((float)v.sclk, v.pherr2, v.pherr1, p0);
+		float neg = -roundf(vertex);
+		/* reachable metric triples give vertex in [-4.5,-1.5]; the guard only keeps the
+		 * conversion defined for inputs the reference itself would mis-handle */
+		v.sclk = (neg > -1.0e6f && neg < 1.0e6f) ? (int)neg : 0;
+		int sp = v.ring_pos - v.sclk;
+		if(sp < 0) sp += VDL2_SYNC_BUFLEN;
+		sp = ((sp % VDL2_SYNC_BUFLEN) + VDL2_SYNC_BUFLEN) % VDL2_SYNC_BUFLEN;
+		v.prev_phi = ring[sp * rs];
+		v.dphi = v.prev_dphi;
+		v.ppm_error = D_TO_F(D_MUL(D_DIV((double)F_MUL((float)VDL2_SYMBOL_RATE, v.dphi),
+						D_MUL(VDL2_TWO_PI, (double)v.freq)), 1e+6));
+		int accepted = !(env.max_ppm != 0.f && fabsf(v.ppm_error) > env.max_ppm);
+		if(env.trace) {
+			vdl2_event_rec e;
+			memset(&e, 0, sizeof(e));
+			e.channel = chan_idx; e.kind = 1; e.dec_index = dec_index;
+			e.i[0] = v.sclk; e.i[1] = v.ring_pos; e.i[2] = sp; e.i[3] = accepted;
+			e.f[0] = v.pherr2; e.f[1] = v.pherr1; e.f[2] = p0; e.f[3] = vertex;
+			e.f[4] = v.prev_phi; e.f[5] = v.dphi; e.f[6] = v.ppm_error;
+			vdl2_emit_event(env, e);
+		}
+		v.pherr1 = v.pherr2 = 1000.f;
+		return accepted;
+	}
+	v.pherr2 = v.pherr1;
+	v.pherr1 = p0;
+	v.prev_dphi = slope;
+	return 0;
+}
+
+/* DEC_HEADER branch of decode_vdl2_burst: src/decode.c:198-258 */
+VDL2_HD void vdl2_header_step(vdl2_chan &v, const vdl2_k2_env &env, uint32_t chan_idx, uint64_t dec_index) {
+	/* nbits == 27 here: 9 symbols; descramble all of them, the header is the first 25 */
+	uint32_t raw27 = (uint32_t)(v.acc & 0x7FFFFFFu) ^ env.s27;
+	uint32_t word = raw27 >> 2;
+	uint32_t raw25 = word;
+	word &= (1u << (VDL2_TRLEN + VDL2_HDRFECLEN)) - 1u;
+	uint32_t syn = vdl2_header_syndrome(word);
+	word ^= vdl2_header_error_pattern(syn);
+	v.syndrome = syn;
+	if(syn == 0) v.cnt_hdr_good++;
+	int status = VDL2_BURST_OK;
+	uint32_t datalen = 0, octets = 0, fec = 0;
+	if((word & ((1u << (VDL2_TRLEN + VDL2_HDRFECLEN)) - 1u)) != word) {
+		status = VDL2_ERR_CRC_BAD;
+	} else {
+		datalen = vdl2_reverse17((word >> VDL2_HDRFECLEN) & 0x1FFFFu);
+		if((syn != 0 && datalen > VDL2_MAX_FRAME_LENGTH_CORRECTED) || datalen > VDL2_MAX_FRAME_LENGTH)
+			status = VDL2_ERR_TOO_LONG;
+	}
+	if(status == VDL2_BURST_OK) {
+		octets = datalen / 8 + ((datalen % 8) != 0);
+		fec = (octets / VDL2_RS_K) * (VDL2_RS_N - VDL2_RS_K) + (uint32_t)vdl2_fec_octets_for(octets % VDL2_RS_K);
+		if(fec == 0) status = VDL2_ERR_NO_FEC;
+	}
+	if(status == VDL2_BURST_OK) {
+		v.datalen = datalen;
+		v.need_bits = VDL2_HEADER_LEN + 8 * (octets + fec);
+		vdl2_set_dec_state(v, VDL2_DEC_DATA);
+		/* take a burst slot from the pool (K3 returns it) */
+		int32_t top = VDL2_ATOMIC_ADD_I32(&env.ctl->free_top, -1) - 1;
+		if(top >= 0) {
+			v.slot = env.free_list[top];
+		} else {
+			VDL2_ATOMIC_ADD_I32(&env.ctl->free_top, 1);
+			VDL2_ATOMIC_ADD_U32(&env.ctl->pool_overflows, 1u);
+			v.slot = -1;
+		}
+	} else {
+		vdl2_set_dec_state(v, VDL2_DEC_IDLE);
+	}
+	if(env.trace) {
+		vdl2_event_rec e;
+		memset(&e, 0, sizeof(e));
+		e.channel = chan_idx; e.kind = 2; e.dec_index = dec_index;
+		e.i[0] = (int32_t)raw25; e.i[1] = (int32_t)syn; e.i[2] = (int32_t)datalen; e.i[3] = status;
+		e.i[4] = (int32_t)(status == VDL2_BURST_OK ? v.need_bits - VDL2_HEADER_LEN : VDL2_HEADER_LEN);
+		vdl2_emit_event(env, e);
+	}
+}
+
+/* all requested bits are in: hand the burst to K3 (the data part of decode_vdl2_burst runs there) */
+VDL2_HD void vdl2_burst_complete(vdl2_chan &v, const vdl2_k2_env &env, uint32_t chan_idx) {
+	if(v.slot >= 0) {
+		vdl2_burst_slot *s = &env.pool[v.slot];
+		if(v.nbits & 31u) s->words[v.nbits >> 5] = (uint32_t)(v.acc << (32u - (v.nbits & 31u)));
+		s->channel = chan_idx;
+		s->burst_seq = v.burst_seq;
+		s->datalen_bits = v.datalen;
+		s->syndrome = v.syndrome;
+		s->nbits = v.nbits;
+		s->frame_pwr = v.frame_pwr;
+		s->mag_nf = v.mag_nf;
+		s->ppm_error = v.ppm_error;
+		s->sync_lo = (uint32_t)v.sync_dec_index;
+		s->sync_hi = (uint32_t)(v.sync_dec_index >> 32);
+		s->freq = v.freq;
+		uint32_t k = VDL2_ATOMIC_ADD_U32(&env.ctl->n_ready, 1u);
+		env.ready[k] = (uint32_t)v.slot;
+		v.slot = -1;
+	}
+	v.burst_seq++;
+	vdl2_set_dec_state(v, VDL2_DEC_IDLE);
+}
+
+/* src/demod.c:222-286 — one decimated sample of one channel */
+VDL2_HD void vdl2_demod_step(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env,
+		uint32_t chan_idx, uint64_t dec_index, float re, float im) {
+	if(vdl2_dec_state(v) == VDL2_DEC_IDLE) vdl2_demod_reset(v);
+	if(!(v.state & VDL2_ST_LOCKED)) {
+		v.ring_pos = (v.ring_pos + 1 == VDL2_SYNC_BUFLEN) ? 0 : v.ring_pos + 1;
+		ring[v.ring_pos * rs] = D_TO_F(atan2((double)im, (double)re));
+		if(++v.sclk < VDL2_SYNC_SKIP) return;
+		v.sclk = 0;
+		/* hypotf(re, im): glibc evaluates sqrt(x*x + y*y) in double and narrows (checked in tests) */
+		float mag = D_TO_F(D_SQRT(D_ADD(D_MUL((double)re, (double)re), D_MUL((double)im, (double)im))));
+		const float one_minus_mag_lp = 1.0f - 0.9f, one_minus_nf_lp = 1.0f - 0.85f;
+		v.mag_lp = F_ADD(F_MUL(v.mag_lp, 0.9f), F_MUL(mag, one_minus_mag_lp));
+		if(++v.nfcnt == 1000) {
+			v.nfcnt = 0;
+			v.mag_nf = F_ADD(F_ADD(F_MUL(0.85f, v.mag_nf), F_MUL(one_minus_nf_lp, fminf(v.mag_lp, v.mag_nf))), 0.0001f);
+		}
+		if(vdl2_preamble_metric(v, ring, rs, env, chan_idx, dec_index)) {
+			v.cnt_sync++;
+			v.sync_dec_index = dec_index;
+			v.state |= VDL2_ST_LOCKED;
+		}
+		return;
+	}
+	if(++v.sclk < VDL2_SPS) return;
+	v.sclk = 0;
+	float phi = D_TO_F(atan2((double)im, (double)re));
+	float dphi = F_SUB(F_SUB(phi, v.prev_phi), v.dphi);
+	if(dphi < 0.f) dphi = D_TO_F(D_ADD((double)dphi, VDL2_TWO_PI));
+	else if(dphi >= VDL2_TWO_PI_F_ABOVE) dphi = D_TO_F(D_SUB((double)dphi, VDL2_TWO_PI));
+	dphi = D_TO_F(D_DIV((double)dphi, VDL2_PI_4));
+	int sym = (int)roundf(dphi) % 8;
+	if(sym < 0) sym += 8;
+	float p = F_ADD(F_MUL(re, re), F_MUL(im, im));
+	v.frame_pwr = F_DIV(F_ADD(F_MUL(v.frame_pwr, (float)v.frame_pwr_cnt), p), (float)(v.frame_pwr_cnt + 1));
+	v.frame_pwr_cnt++;
+	v.prev_phi = phi;
+	/* Gray map {0,1,3,2,6,7,5,4} (src/demod.c:223), three bits MSB first (src/bitstream.c:46-56) */
+	uint32_t bits = (uint32_t)(sym ^ (sym >> 1));
+	uint32_t before = v.nbits;
+	v.acc = (v.acc << 3) | bits;
+	v.nbits = before + 3;
+	if((before >> 5) != (v.nbits >> 5) && v.slot >= 0)
+		env.pool[v.slot].words[before >> 5] = (uint32_t)(v.acc >> (v.nbits & 31u));
+	if(v.nbits >= v.need_bits) {
+		if(vdl2_dec_state(v) == VDL2_DEC_HEADER) vdl2_header_step(v, env, chan_idx, dec_index);
+		else if(vdl2_dec_state(v) == VDL2_DEC_DATA) vdl2_burst_complete(v, env, chan_idx);
+	}
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K3: data part of decode_vdl2_burst        src/decode.c:259-380
+ * ---------------------------------------------------------------------------------------------- */
+struct vdl2_burst_work {
+	uint32_t datalen_bits, datalen_octets, num_blocks, last_len, last_fec, fec_octets;
+	int32_t status;
+	int32_t fec_corr;
+	uint32_t n_frames, frame_bytes;
+	int32_t rs_ret[VDL2_MAX_BLOCKS + 3];
+	uint8_t tab[VDL2_MAX_BLOCKS][256];       /* RS blocks, row = block, 255 used */
+	uint8_t frames[2064];
+	uint16_t flen[VDL2_MAX_FRAMES];
+	uint16_t fcrc[VDL2_MAX_FRAMES];
+};
+
+VDL2_HD uint8_t vdl2_gf_mul(const uint8_t *gexp, const uint8_t *glog, uint8_t a, uint8_t b) {
+	return (a && b) ? gexp[(int)glog[a] + (int)glog[b]] : (uint8_t)0;
+}
+VDL2_HD uint8_t vdl2_gf_alpha(const uint8_t *gexp, int e) { return gexp[e % 255]; }    /* e >= 0 */
+
+/* 8 burst bits starting at bit `pos`, first bit in bit 7, descrambled */
+VDL2_HD uint32_t vdl2_take8(const uint32_t *words, const uint32_t *lfsr, uint32_t pos) {
+	uint32_t w = pos >> 5, sh = pos & 31u;
+	uint64_t two = ((uint64_t)(words[w] ^ lfsr[w]) << 32) | (uint64_t)(words[w + 1] ^ lfsr[w + 1]);
+	return (uint32_t)(two >> (56u - sh)) & 0xFFu;
+}
+VDL2_HD uint8_t vdl2_brev8(uint32_t b) {
+	b = ((b & 0xF0u) >> 4) | ((b & 0x0Fu) << 4);
+	b = ((b & 0xCCu) >> 2) | ((b & 0x33u) << 2);
+	b = ((b & 0xAAu) >> 1) | ((b & 0x55u) << 1);
+	return (uint8_t)b;
+}
+
+/* geometry: src/decode.c:233-256.  Returns status. */
+VDL2_HD int vdl2_burst_geometry(vdl2_burst_work &w, uint32_t datalen_bits, uint32_t nbits) {
+	w.datalen_bits = datalen_bits;
+	w.datalen_octets = datalen_bits / 8 + ((datalen_bits % 8) != 0);
+	w.num_blocks = w.datalen_octets / VDL2_RS_K;
+	w.fec_octets = w.num_blocks * (VDL2_RS_N - VDL2_RS_K);
+	w.last_len = w.datalen_octets % VDL2_RS_K;
+	if(w.last_len != 0) w.num_blocks++;
+	w.last_fec = (uint32_t)vdl2_fec_octets_for(w.last_len);
+	w.fec_octets += w.last_fec;
+	if(w.last_len == 0) { w.last_len = VDL2_RS_K; w.last_fec = VDL2_RS_N - VDL2_RS_K; }
+	w.status = VDL2_BURST_OK;
+	w.fec_corr = 0;
+	w.n_frames = 0;
+	w.frame_bytes = 0;
+	for(int r = 0; r < VDL2_MAX_BLOCKS + 3; r++) w.rs_ret[r] = -128;
+	if(w.fec_octets == 0) return w.status = VDL2_ERR_NO_FEC;
+	if(w.num_blocks > VDL2_MAX_BLOCKS) return w.status = VDL2_ERR_TOO_LONG;
+	if(nbits < VDL2_HEADER_LEN + 8 * w.datalen_octets) return w.status = VDL2_ERR_DATA_TRUNCATED;
+	if(nbits < VDL2_HEADER_LEN + 8 * (w.datalen_octets + w.fec_octets)) return w.status = VDL2_ERR_FEC_TRUNCATED;
+	return VDL2_BURST_OK;
+}
+
+/* descramble (src/bitstream.c:94-107), octets LSB first (src/bitstream.c:70-81) and column-wise
+ * de-interleave (src/decode.c:135-163,282-297); work item t of the data part / FEC part is independent,
+ * so threads tid, tid+nthr, ... each place their own octets.  Rows must have been zeroed. */
+VDL2_HD void vdl2_burst_unpack(vdl2_burst_work &w, const uint32_t *words, const uint32_t *lfsr, uint32_t tid, uint32_t nthr) {
+	const uint32_t nb = w.num_blocks;
+	const uint32_t full = w.last_len * nb;            /* transmit positions that cover every row */
+	for(uint32_t t = tid; t < w.datalen_octets; t += nthr) {
+		uint32_t row, col;
+		if(t < full) { col = t / nb; row = t % nb; }
+		else { uint32_t u = t - full; col = w.last_len + u / (nb - 1); row = u % (nb - 1); }
+		w.tab[row][col] = vdl2_brev8(vdl2_take8(words, lfsr, VDL2_HEADER_LEN + 8 * t));
+	}
+	const uint32_t last_fec = (w.last_len == VDL2_RS_K) ? (uint32_t)(VDL2_RS_N - VDL2_RS_K) : w.last_fec;
+	const uint32_t fec_rows = nb - (last_fec == 0 ? 1u : 0u);
+	const uint32_t ffull = last_fec * fec_rows;       /* positions covering every FEC row (0 if last row has none left) */
+	for(uint32_t t = tid; t < w.fec_octets; t += nthr) {
+		uint32_t row, col;
+		if(fec_rows == nb && t >= ffull) { uint32_t u = t - ffull; col = last_fec + u / (nb - 1); row = u % (nb - 1); }
+		else { col = t / fec_rows; row = t % fec_rows; }
+		w.tab[row][VDL2_RS_K + col] = vdl2_brev8(vdl2_take8(words, lfsr, VDL2_HEADER_LEN + 8 * (w.datalen_octets + t)));
+	}
+}
+
+/* RS(255,249) errors-and-erasures decoder, one block per caller.  src/rs.c:32-49 ->
+ * src/libfec/decode_rs.h:71-298 (Karn): syndromes by Horner, erasure-seeded Berlekamp-Massey, Chien search
+ * with early exit, failure iff deg(lambda) != number of roots, Forney.  Polynomial (not log) form. */
+VDL2_HD int vdl2_rs_verify(uint8_t *data, int fec_octets, const uint8_t *gexp, const uint8_t *glog) {
+	enum { NR = VDL2_RS_N - VDL2_RS_K, FCR = 120 };
+	if(fec_octets == 0) return 0;
+	const int no_eras = NR - fec_octets;
+	uint8_t S[NR];
+	int any = 0;
+	for(int i = 0; i < NR; i++) {
+		uint8_t acc = data[0];
+		const int lr = FCR + i;                       /* log of the root */
+		for(int j = 1; j < VDL2_RS_N; j++)
+			acc = (uint8_t)((acc ? gexp[glog[acc] + lr] : 0) ^ data[j]);
+		S[i] = acc;
+		any |= acc;
+	}
+	if(!any) return 0;
+	uint8_t lambda[NR + 1] = { 1, 0, 0, 0, 0, 0, 0 };
+	if(no_eras > 0) {
+		/* erasures are the untransmitted parity octets RS_K+fec .. 254 (src/rs.c:40-43) */
+		lambda[1] = vdl2_gf_alpha(gexp, 254 - (VDL2_RS_K + fec_octets));
+		for(int i = 1; i < no_eras; i++) {
+			uint8_t x = vdl2_gf_alpha(gexp, 254 - (VDL2_RS_K + fec_octets + i));
+			for(int j = i + 1; j > 0; j--)
+				lambda[j] ^= vdl2_gf_mul(gexp, glog, x, lambda[j - 1]);
+		}
+	}
+	uint8_t B[NR + 1];
+	for(int i = 0; i <= NR; i++) B[i] = lambda[i];
+	int el = no_eras;
+	for(int r = no_eras + 1; r <= NR; r++) {
+		uint8_t discr = 0;
+		for(int i = 0; i < r; i++) discr ^= vdl2_gf_mul(gexp, glog, lambda[i], S[r - i - 1]);
+		if(discr == 0) {
+			for(int i = NR; i > 0; i--) B[i] = B[i - 1];
+			B[0] = 0;
+		} else {
+			uint8_t T[NR + 1];
+			T[0] = lambda[0];
+			for(int i = 0; i < NR; i++) T[i + 1] = lambda[i + 1] ^ vdl2_gf_mul(gexp, glog, discr, B[i]);
+			if(2 * el <= r + no_eras - 1) {
+				el = r + no_eras - el;
+				uint8_t inv = gexp[255 - glog[discr]];
+				for(int i = 0; i <= NR; i++) B[i] = vdl2_gf_mul(gexp, glog, lambda[i], inv);
+			} else {
+				for(int i = NR; i > 0; i--) B[i] = B[i - 1];
+				B[0] = 0;
+			}
+			for(int i = 0; i <= NR; i++) lambda[i] = T[i];
+		}
+	}
+	int deg = 0;
+	for(int i = 0; i <= NR; i++) if(lambda[i]) deg = i;
+	int root[NR], loc[NR], count = 0;
+	for(int i = 1; i <= 255; i++) {
+		uint8_t q = 1;
+		for(int j = deg; j > 0; j--)
+			if(lambda[j]) q ^= gexp[(glog[lambda[j]] + i * j) % 255];
+		if(q != 0) continue;
+		root[count] = i;
+		loc[count] = i - 1;
+		if(++count == deg) break;
+	}
+	if(deg != count) return -1;
+	const int deg_omega = deg - 1;
+	uint8_t omega[NR + 1] = { 0, 0, 0, 0, 0, 0, 0 };
+	for(int i = 0; i <= deg_omega; i++) {
+		uint8_t acc = 0;
+		for(int j = i; j >= 0; j--) acc ^= vdl2_gf_mul(gexp, glog, S[i - j], lambda[j]);
+		omega[i] = acc;
+	}
+	for(int j = count - 1; j >= 0; j--) {
+		uint8_t num1 = 0;
+		for(int i = deg_omega; i >= 0; i--)
+			if(omega[i]) num1 ^= gexp[(glog[omega[i]] + i * root[j]) % 255];
+		uint8_t num2 = gexp[(root[j] * (FCR - 1) + 255) % 255];
+		uint8_t den = 0;
+		int top = (deg < NR - 1 ? deg : NR - 1) & ~1;
+		for(int i = top; i >= 0; i -= 2)
+			if(lambda[i + 1]) den ^= gexp[(glog[lambda[i + 1]] + i * root[j]) % 255];
+		if(num1 != 0) {
+			/* decode_rs.h:289 uses log(0) = 255, so a zero denominator divides by alpha^0 */
+			int e = (int)glog[num1] + (int)glog[num2] + 255 - (den ? (int)glog[den] : 255);
+			data[loc[j]] ^= gexp[e % 255];
+		}
+	}
+	return count;
+}
+
+/* serialise corrected octets, cut to datalen bits, split on HDLC flags with zero-bit deletion:
+ * src/decode.c:325-370 + src/bitstream.c:109-150.  Single caller.  Returns status; frames found before a
+ * late error stay (the reference has already pushed them). */
+VDL2_HD int vdl2_burst_unstuff(vdl2_burst_work &w) {
+	const uint32_t total_bits = (8u * w.datalen_octets < w.datalen_bits) ? 8u * w.datalen_octets : w.datalen_bits;
+	uint32_t pos = 0;
+	uint32_t out_base = 0;
+	for(;;) {
+		uint32_t j = 0;          /* bits of the candidate frame, flag prefix included */
+		int ones = 0;
+		for(;;) {                /* one pass of bitstream_copy_next_frame, restarts folded in */
+			if(pos >= total_bits) break;
+			uint32_t o = pos >> 3;
+			uint32_t bit = (w.tab[o / VDL2_RS_K][o % VDL2_RS_K] >> (pos & 7u)) & 1u;
+			if(bit == 0 && ones == 5) { ones = 0; pos++; continue; }
+			if(bit == 1 && ++ones > 6) return w.status = VDL2_ERR_UNSTUFF;
+			uint32_t ob = out_base + (j >> 3);
+			if(ob >= sizeof(w.frames)) return w.status = VDL2_ERR_BITSTREAM;
+			if((j & 7u) == 0) w.frames[ob] = (uint8_t)bit;
+			else w.frames[ob] |= (uint8_t)(bit << (j & 7u));
+			if(bit == 0) {
+				if(ones == 6) {
+					if(j == 7) { pos++; j = 0; ones = 0; continue; }       /* opening flag: restart */
+					if(j < 7) return w.status = VDL2_ERR_UNSTUFF;
+					j -= 7; pos++;
+					goto frame_done;
+				}
+				ones = 0;
+			}
+			j++; pos++;
+		}
+	frame_done:
+		{
+			int more = pos < total_bits;
+			if(j % 8 != 0) return w.status = VDL2_ERR_TRUNCATED_OCTETS;
+			if(w.n_frames >= VDL2_MAX_FRAMES) return w.status = VDL2_ERR_BITSTREAM;
+			w.flen[w.n_frames++] = (uint16_t)(j / 8);
+			out_base += j / 8;
+			w.frame_bytes = out_base;
+			if(!more) break;
+		}
+	}
+	return VDL2_BURST_OK;
+}
+
+/* K4: AVLC FCS residue, src/crc.c:21-64 (reflected 0x1021), bitwise */
+VDL2_HD uint16_t vdl2_crc16(const uint8_t *p, uint32_t len) {
+	uint32_t crc = 0xFFFFu;
+	for(uint32_t n = 0; n < len; n++) {
+		crc ^= p[n];
+#pragma unroll
+		for(int b = 0; b < 8; b++) crc = (crc >> 1) ^ ((crc & 1u) ? 0x8408u : 0u);
+	}
+	return (uint16_t)crc;
+}
+
+#endif

@@ -1,0 +1,477 @@
+/*
+ * vdl2_kernels.cu — sm_100a kernels of libvdl2gpu.so and their extern "C" launch stubs.
+ *
+ *   K0  k0_convert            raw cu8/cs16 -> float samples        src/demod.c:339-365
+ *   K1  k1_mix_iir_decimate   NCO mix + 2-pole IIR + decimate      src/demod.c:58-79,200-203,288-337
+ *   K2  k2_sync_slice         preamble sync, D8PSK slicing, header src/demod.c:105-198,222-286; src/decode.c:198-258
+ *   K3  k3_burst_fec          descramble, de-interleave, RS, HDLC  src/decode.c:259-380; src/rs.c; src/libfec; src/bitstream.c
+ *   K4  (inside K3)           AVLC FCS residue per frame           src/crc.c:21-64
+ *
+ * Unit of parallelism: K0 sample; K1/K2 one thread per VDL2 channel (32 channels per warp, the sample
+ * stream is broadcast to the warp from shared memory); K3 one thread block per burst.
+ * No tensor cores: there is no dense contraction on this path.  Built with -fmad=false; all float
+ * arithmetic additionally goes through explicit round-to-nearest intrinsics / PTX.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "vdl2_core.cuh"
+#include "vdl2_kernels.h"
+
+/* ------------------------------------------------------------------------------------------------
+ * K0: sample conversion.  Output layout float4 {re, im, im, re} per complex sample: the packed K1
+ * consumes (re,im) and (im,re) as two f32x2 operands, so the swap is paid once per sample here
+ * instead of once per channel-sample there.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(256) k0_convert(const uint8_t *__restrict__ raw, uint32_t n_pairs, uint32_t fmt,
+		const float *__restrict__ levels, float4 *__restrict__ out) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n_pairs) return;
+	float re, im;
+	if(fmt == 0) {                                       /* src/demod.c:343-345, table from :349-354 */
+		uchar2 v = reinterpret_cast<const uchar2 *>(raw)[i];
+		re = __ldg(&levels[v.x]);
+		im = __ldg(&levels[v.y]);
+	} else {                                             /* src/demod.c:361-363 */
+		short2 v = reinterpret_cast<const short2 *>(raw)[i];
+		re = __fdiv_rn((float)v.x, 32768.0f);
+		im = __fdiv_rn((float)v.y, 32768.0f);
+	}
+	out[i] = make_float4(re, im, im, re);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K1, plain per-sample form (reference for the pipelined kernel; selected by VDL2GPU_FLAG_K1_SCALAR
+ * and for oversample values without a specialisation).
+ * ---------------------------------------------------------------------------------------------- */
+#define K1_TILE 2048
+
+__device__ __forceinline__ void k1_load_state(const vdl2_k1_params &p, uint32_t ch, float &xr1, float &xr2, float &xi1,
+		float &xi2, float &yr1, float &yr2, float &yi1, float &yi2, uint32_t &phi, uint32_t &dphi) {
+	const uint32_t *st = p.state;
+	const uint32_t s = p.n_chp;
+	xr1 = __uint_as_float(st[K1_XR1 * s + ch]); xr2 = __uint_as_float(st[K1_XR2 * s + ch]);
+	xi1 = __uint_as_float(st[K1_XI1 * s + ch]); xi2 = __uint_as_float(st[K1_XI2 * s + ch]);
+	yr1 = __uint_as_float(st[K1_YR1 * s + ch]); yr2 = __uint_as_float(st[K1_YR2 * s + ch]);
+	yi1 = __uint_as_float(st[K1_YI1 * s + ch]); yi2 = __uint_as_float(st[K1_YI2 * s + ch]);
+	phi = st[K1_PHI * s + ch]; dphi = st[K1_DPHI * s + ch];
+}
+
+__device__ __forceinline__ void k1_store_state(const vdl2_k1_params &p, uint32_t ch, float xr1, float xr2, float xi1,
+		float xi2, float yr1, float yr2, float yi1, float yi2, uint32_t phi) {
+	uint32_t *st = p.state;
+	const uint32_t s = p.n_chp;
+	st[K1_XR1 * s + ch] = __float_as_uint(xr1); st[K1_XR2 * s + ch] = __float_as_uint(xr2);
+	st[K1_XI1 * s + ch] = __float_as_uint(xi1); st[K1_XI2 * s + ch] = __float_as_uint(xi2);
+	st[K1_YR1 * s + ch] = __float_as_uint(yr1); st[K1_YR2 * s + ch] = __float_as_uint(yr2);
+	st[K1_YI1 * s + ch] = __float_as_uint(yi1); st[K1_YI2 * s + ch] = __float_as_uint(yi2);
+	st[K1_PHI * s + ch] = phi & 0xFFFFFFu;
+}
+
+template<int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_scalar(vdl2_k1_params p) {
+	__shared__ float4 s_lut[257];
+	__shared__ float2 s_tile[K1_TILE];
+	const uint32_t tid = threadIdx.x;
+	const uint32_t ch = blockIdx.x * BLOCK + tid;
+	const bool active = ch < p.n_ch;
+	for(uint32_t i = tid; i < 257; i += BLOCK) s_lut[i] = p.lut[i];
+	float xr1 = 0, xr2 = 0, xi1 = 0, xi2 = 0, yr1 = 0, yr2 = 0, yi1 = 0, yi2 = 0;
+	uint32_t phi = 0, dphi = 0;
+	if(active) k1_load_state(p, ch, xr1, xr2, xi1, xi2, yr1, yr2, yi1, yi2, phi, dphi);
+	uint32_t cnt = p.cnt0, m = 0;
+	const float a0 = p.a0, a1 = p.a1, a2 = p.a2, b1 = p.b1, b2 = p.b2;
+	for(uint32_t base = 0; base < p.n_pairs; base += K1_TILE) {
+		const uint32_t n = min((uint32_t)K1_TILE, p.n_pairs - base);
+		__syncthreads();
+		for(uint32_t i = tid; i < n; i += BLOCK) { float4 v = p.samples[base + i]; s_tile[i] = make_float2(v.x, v.y); }
+		__syncthreads();
+		if(!active) continue;
+		for(uint32_t k = 0; k < n; k++) {
+			const float2 s = s_tile[k];
+			/* NCO: src/demod.c:58-72 (table entry = {cos, sin, dcos*2^-16, dsin*2^-16}) */
+			const float4 e = s_lut[(phi >> 16) & 0xFFu];
+			const float fr = (float)(phi & 0xFFFFu);
+			const float cs = __fadd_rn(e.x, __fmul_rn(e.z, fr));
+			const float sn = __fadd_rn(e.y, __fmul_rn(e.w, fr));
+			phi += dphi;
+			/* complex multiply: src/demod.c:200-203 */
+			const float re = __fsub_rn(__fmul_rn(s.x, cs), __fmul_rn(s.y, sn));
+			const float im = __fadd_rn(__fmul_rn(s.y, cs), __fmul_rn(s.x, sn));
+			/* biquad, evaluation order of src/demod.c:74-79 */
+			float r = __fmul_rn(a0, re);
+			r = __fadd_rn(r, __fadd_rn(__fmul_rn(a1, xr1), __fmul_rn(a2, xr2)));
+			r = __fadd_rn(r, __fadd_rn(__fmul_rn(b1, yr1), __fmul_rn(b2, yr2)));
+			float q = __fmul_rn(a0, im);
+			q = __fadd_rn(q, __fadd_rn(__fmul_rn(a1, xi1), __fmul_rn(a2, xi2)));
+			q = __fadd_rn(q, __fadd_rn(__fmul_rn(b1, yi1), __fmul_rn(b2, yi2)));
+			xr2 = xr1; xr1 = re; yr2 = yr1; yr1 = r;
+			xi2 = xi1; xi1 = im; yi2 = yi1; yi1 = q;
+			if(++cnt == p.oversample) {                   /* src/demod.c:322-328 */
+				cnt = 0;
+				p.dec[(size_t)m * p.n_chp + ch] = make_float2(r, q);
+				m++;
+			}
+		}
+	}
+	if(active) k1_store_state(p, ch, xr1, xr2, xi1, xi2, yr1, yr2, yi1, yi2, phi);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K1, pipelined form.  I and Q ride in the two halves of one f32x2 register pair (FMUL2/FFMA2 on
+ * sm_100a): the two biquads of src/demod.c:319-320 become one instruction stream.  ptxas contracts
+ * mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false, which would change the rounding,
+ * so every addition is issued as fma(x, ONE, y) with ONE a run-time 1.0f the optimiser cannot see
+ * through: x*1+y rounds exactly like x+y and a product feeding it cannot be fused any further.
+ * The loop over one decimation group (OS samples) is fully unrolled so that the NCO/mix work of later
+ * samples fills the issue slots left by the serial y[n-1] -> y[n] recurrence.
+ * ---------------------------------------------------------------------------------------------- */
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 f2_mul(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 f2_fma(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 f2_pack(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float f2_lo(u64 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float f2_hi(u64 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+
+struct k1_packed_consts { u64 ONE, SGN, A0, A1, A2, B1, B2; };
+
+/* one input sample: s = {re, im, im, re}; returns the filtered (I,Q) pair */
+__device__ __forceinline__ u64 k1_packed_step(const float4 s, const float4 *s_lut, uint32_t &phi, const uint32_t dphi,
+		u64 &x1, u64 &x2, u64 &y1, u64 &y2, const k1_packed_consts &c) {
+	const float4 e = s_lut[(phi >> 16) & 0xFFu];
+	const float fr = (float)(phi & 0xFFFFu);
+	phi += dphi;
+	const u64 CS = f2_fma(f2_mul(f2_pack(e.z, e.w), f2_pack(fr, fr)), c.ONE, f2_pack(e.x, e.y));   /* (cos, sin) */
+	const float cs = f2_lo(CS), sn = f2_hi(CS);
+	const u64 P = f2_mul(f2_pack(s.x, s.y), f2_pack(cs, cs));      /* (re*c, im*c) */
+	const u64 Q = f2_mul(f2_pack(s.z, s.w), f2_pack(sn, sn));      /* (im*s, re*s) */
+	const u64 x0 = f2_fma(Q, c.SGN, P);                            /* (re*c - im*s, im*c + re*s) */
+	const u64 t = f2_fma(f2_mul(c.A1, x1), c.ONE, f2_mul(c.A2, x2));
+	const u64 r = f2_fma(f2_mul(c.A0, x0), c.ONE, t);
+	const u64 u = f2_fma(f2_mul(c.B1, y1), c.ONE, f2_mul(c.B2, y2));
+	const u64 y0 = f2_fma(r, c.ONE, u);
+	x2 = x1; x1 = x0; y2 = y1; y1 = y0;
+	return y0;
+}
+
+#define K1P_TILE_GROUPS(OS) (2560 / (OS))       /* 2560 samples = 40 KB of float4 per tile */
+
+template<int OS, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_params p) {
+	constexpr int TG = K1P_TILE_GROUPS(OS);
+	__shared__ float4 s_lut[257];
+	__shared__ float4 s_tile[TG * OS];
+	const uint32_t tid = threadIdx.x;
+	const uint32_t ch = blockIdx.x * BLOCK + tid;
+	const bool active = ch < p.n_ch;
+	for(uint32_t i = tid; i < 257; i += BLOCK) s_lut[i] = p.lut[i];
+	float xr1 = 0, xr2 = 0, xi1 = 0, xi2 = 0, yr1 = 0, yr2 = 0, yi1 = 0, yi2 = 0;
+	uint32_t phi = 0, dphi = 0;
+	if(active) k1_load_state(p, ch, xr1, xr2, xi1, xi2, yr1, yr2, yi1, yi2, phi, dphi);
+	u64 x1 = f2_pack(xr1, xi1), x2 = f2_pack(xr2, xi2), y1 = f2_pack(yr1, yi1), y2 = f2_pack(yr2, yi2);
+	k1_packed_consts c;
+	c.ONE = f2_pack(p.one, p.one); c.SGN = f2_pack(p.neg_one, p.one);
+	c.A0 = f2_pack(p.a0, p.a0); c.A1 = f2_pack(p.a1, p.a1); c.A2 = f2_pack(p.a2, p.a2);
+	c.B1 = f2_pack(p.b1, p.b1); c.B2 = f2_pack(p.b2, p.b2);
+	__syncthreads();
+
+	uint32_t cnt = p.cnt0, m = 0, pos = 0;
+	/* head: samples up to the first decimation-group boundary, straight from global memory */
+	const uint32_t head = min(p.n_pairs, (OS - p.cnt0 % OS) % OS);
+	if(active) {
+		for(; pos < head; pos++) {
+			u64 y0 = k1_packed_step(p.samples[pos], s_lut, phi, dphi, x1, x2, y1, y2, c);
+			if(++cnt == OS) { cnt = 0; p.dec[(size_t)m * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0)); m++; }
+		}
+	}
+	/* same bookkeeping for every lane, active or not */
+	pos = head;
+	m = (p.cnt0 + head) / OS;
+	cnt = (p.cnt0 + head) % OS;
+	/* body: whole groups, staged through shared memory tile by tile */
+	const uint32_t n_groups = (p.n_pairs - pos) / OS;
+	for(uint32_t g0 = 0; g0 < n_groups; g0 += TG) {
+		const uint32_t ng = min((uint32_t)TG, n_groups - g0);
+		__syncthreads();
+		for(uint32_t i = tid; i < ng * OS; i += BLOCK) s_tile[i] = p.samples[pos + i];
+		__syncthreads();
+		if(active) {
+			for(uint32_t g = 0; g < ng; g++) {
+				const float4 *sp = &s_tile[g * OS];
+				u64 y0 = 0;
+#pragma unroll
+				for(int k = 0; k < OS; k++)
+					y0 = k1_packed_step(sp[k], s_lut, phi, dphi, x1, x2, y1, y2, c);
+				p.dec[(size_t)(m + g) * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0));
+			}
+		}
+		m += ng;
+		pos += ng * OS;
+	}
+	/* tail: fewer than OS samples left */
+	if(active) {
+		for(; pos < p.n_pairs; pos++) {
+			u64 y0 = k1_packed_step(p.samples[pos], s_lut, phi, dphi, x1, x2, y1, y2, c);
+			if(++cnt == OS) { cnt = 0; p.dec[(size_t)m * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0)); m++; }
+		}
+		k1_store_state(p, ch, f2_lo(x1), f2_lo(x2), f2_hi(x1), f2_hi(x2), f2_lo(y1), f2_lo(y2), f2_hi(y1), f2_hi(y2), phi);
+	}
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K2: one thread per channel walks the chunk's decimated samples through the demodulator state
+ * machine (vdl2_demod_step).  The 160-deep phase ring lives in shared memory, one column per thread
+ * (bank = lane, conflict-free whatever the per-channel ring position).
+ * ---------------------------------------------------------------------------------------------- */
+#define K2_PREFETCH 8
+
+template<int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
+	__shared__ float s_ring[VDL2_SYNC_BUFLEN * BLOCK];
+	__shared__ float s_consts[33];
+	const uint32_t tid = threadIdx.x;
+	const uint32_t ch = blockIdx.x * BLOCK + tid;
+	if(tid < 16) { s_consts[tid] = p.tables->pr_phase[tid]; s_consts[16 + tid] = p.tables->lr_X[tid]; }
+	if(tid == 0) s_consts[32] = p.tables->lr_denom;
+	__syncthreads();
+	if(ch >= p.n_ch) return;
+	const uint32_t s = p.n_chp;
+	uint32_t *st = p.state;
+	vdl2_chan v;
+	v.prev_phi = __uint_as_float(st[K2_PREV_PHI * s + ch]); v.prev_dphi = __uint_as_float(st[K2_PREV_DPHI * s + ch]);
+	v.dphi = __uint_as_float(st[K2_DPHI * s + ch]); v.pherr0 = __uint_as_float(st[K2_PHERR0 * s + ch]);
+	v.pherr1 = __uint_as_float(st[K2_PHERR1 * s + ch]); v.pherr2 = __uint_as_float(st[K2_PHERR2 * s + ch]);
+	v.ppm_error = __uint_as_float(st[K2_PPM * s + ch]); v.mag_lp = __uint_as_float(st[K2_MAG_LP * s + ch]);
+	v.mag_nf = __uint_as_float(st[K2_MAG_NF * s + ch]); v.frame_pwr = __uint_as_float(st[K2_FRAME_PWR * s + ch]);
+	v.ring_pos = (int32_t)st[K2_RING_POS * s + ch]; v.sclk = (int32_t)st[K2_SCLK * s + ch];
+	v.nfcnt = (int32_t)st[K2_NFCNT * s + ch]; v.frame_pwr_cnt = (int32_t)st[K2_FRAME_PWR_CNT * s + ch];
+	v.state = st[K2_STATE * s + ch];
+	v.acc = (uint64_t)st[K2_ACC_LO * s + ch] | ((uint64_t)st[K2_ACC_HI * s + ch] << 32);
+	v.nbits = st[K2_NBITS * s + ch]; v.need_bits = st[K2_NEED_BITS * s + ch];
+	v.datalen = st[K2_DATALEN * s + ch]; v.syndrome = st[K2_SYNDROME * s + ch];
+	v.slot = (int32_t)st[K2_SLOT * s + ch]; v.burst_seq = st[K2_BURST_SEQ * s + ch];
+	v.sync_dec_index = (uint64_t)st[K2_SYNC_LO * s + ch] | ((uint64_t)st[K2_SYNC_HI * s + ch] << 32);
+	v.freq = st[K2_FREQ * s + ch];
+	v.cnt_sync = st[K2_CNT_SYNC * s + ch]; v.cnt_hdr_good = st[K2_CNT_HDR_GOOD * s + ch];
+	float *ring = &s_ring[tid];
+	for(int i = 0; i < VDL2_SYNC_BUFLEN; i++) ring[i * BLOCK] = p.ring[(size_t)i * s + ch];
+
+	vdl2_k2_env env;
+	env.pr_phase = s_consts; env.lr_X = s_consts + 16; env.lr_denom = s_consts[32];
+	env.max_ppm = p.max_ppm; env.s27 = p.s27;
+	env.pool = p.pool; env.free_list = p.free_list; env.ready = p.ready; env.ctl = p.ctl;
+	env.events = reinterpret_cast<vdl2_event_rec *>(p.events); env.event_cap = p.event_cap; env.trace = p.trace;
+	env.cnt_bursts = nullptr;
+
+	const float2 *dec = p.dec + ch;
+	uint32_t m = 0;
+	for(; m + K2_PREFETCH <= p.n_dec; m += K2_PREFETCH) {
+		float2 buf[K2_PREFETCH];
+#pragma unroll
+		for(int k = 0; k < K2_PREFETCH; k++) buf[k] = __ldg(&dec[(size_t)(m + k) * s]);
+#pragma unroll 1
+		for(int k = 0; k < K2_PREFETCH; k++)
+			vdl2_demod_step(v, ring, BLOCK, env, ch, p.dec_base + m + k, buf[k].x, buf[k].y);
+	}
+	for(; m < p.n_dec; m++) {
+		float2 d = __ldg(&dec[(size_t)m * s]);
+		vdl2_demod_step(v, ring, BLOCK, env, ch, p.dec_base + m, d.x, d.y);
+	}
+
+	for(int i = 0; i < VDL2_SYNC_BUFLEN; i++) p.ring[(size_t)i * s + ch] = ring[i * BLOCK];
+	st[K2_PREV_PHI * s + ch] = __float_as_uint(v.prev_phi); st[K2_PREV_DPHI * s + ch] = __float_as_uint(v.prev_dphi);
+	st[K2_DPHI * s + ch] = __float_as_uint(v.dphi); st[K2_PHERR0 * s + ch] = __float_as_uint(v.pherr0);
+	st[K2_PHERR1 * s + ch] = __float_as_uint(v.pherr1); st[K2_PHERR2 * s + ch] = __float_as_uint(v.pherr2);
+	st[K2_PPM * s + ch] = __float_as_uint(v.ppm_error); st[K2_MAG_LP * s + ch] = __float_as_uint(v.mag_lp);
+	st[K2_MAG_NF * s + ch] = __float_as_uint(v.mag_nf); st[K2_FRAME_PWR * s + ch] = __float_as_uint(v.frame_pwr);
+	st[K2_RING_POS * s + ch] = (uint32_t)v.ring_pos; st[K2_SCLK * s + ch] = (uint32_t)v.sclk;
+	st[K2_NFCNT * s + ch] = (uint32_t)v.nfcnt; st[K2_FRAME_PWR_CNT * s + ch] = (uint32_t)v.frame_pwr_cnt;
+	st[K2_STATE * s + ch] = v.state;
+	st[K2_ACC_LO * s + ch] = (uint32_t)v.acc; st[K2_ACC_HI * s + ch] = (uint32_t)(v.acc >> 32);
+	st[K2_NBITS * s + ch] = v.nbits; st[K2_NEED_BITS * s + ch] = v.need_bits;
+	st[K2_DATALEN * s + ch] = v.datalen; st[K2_SYNDROME * s + ch] = v.syndrome;
+	st[K2_SLOT * s + ch] = (uint32_t)v.slot; st[K2_BURST_SEQ * s + ch] = v.burst_seq;
+	st[K2_SYNC_LO * s + ch] = (uint32_t)v.sync_dec_index; st[K2_SYNC_HI * s + ch] = (uint32_t)(v.sync_dec_index >> 32);
+	st[K2_CNT_SYNC * s + ch] = v.cnt_sync; st[K2_CNT_HDR_GOOD * s + ch] = v.cnt_hdr_good;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K3: one block per completed burst (grid-stride over the ready list).
+ * ---------------------------------------------------------------------------------------------- */
+#define K3_BLOCK 128
+
+__global__ void __launch_bounds__(K3_BLOCK) k3_burst_fec(vdl2_k3_params p) {
+	__shared__ vdl2_burst_work w;
+	__shared__ uint8_t s_gexp[512];
+	__shared__ uint8_t s_glog[256];
+	__shared__ uint16_t s_foff[VDL2_MAX_FRAMES];
+	__shared__ uint32_t s_out_off;
+	const uint32_t tid = threadIdx.x;
+	for(uint32_t i = tid; i < 512; i += K3_BLOCK) s_gexp[i] = p.tables->gf_exp[i];
+	for(uint32_t i = tid; i < 256; i += K3_BLOCK) s_glog[i] = p.tables->gf_log[i];
+	const uint32_t n_ready = p.ctl->n_ready;
+	for(uint32_t b = blockIdx.x; b < n_ready; b += gridDim.x) {
+		__syncthreads();
+		const uint32_t slot_idx = p.ready[b];
+		const vdl2_burst_slot *slot = &p.pool[slot_idx];
+		if(tid == 0) vdl2_burst_geometry(w, slot->datalen_bits, slot->nbits);
+		for(uint32_t i = tid; i < VDL2_MAX_BLOCKS * 256 / 4; i += K3_BLOCK) reinterpret_cast<uint32_t *>(w.tab)[i] = 0;
+		__syncthreads();
+		if(w.status == VDL2_BURST_OK) {
+			vdl2_burst_unpack(w, slot->words, p.tables->lfsr_words, tid, K3_BLOCK);
+			__syncthreads();
+			if(tid < w.num_blocks) {
+				int nfec = (tid == w.num_blocks - 1) ? (int)w.last_fec : (VDL2_RS_N - VDL2_RS_K);
+				w.rs_ret[tid] = vdl2_rs_verify(w.tab[tid], nfec, s_gexp, s_glog);
+			}
+			__syncthreads();
+			if(tid == 0) {
+				/* blocks are judged in order; the first failure drops the burst (src/decode.c:305-334) */
+				for(uint32_t r = 0; r < w.num_blocks; r++) {
+					int nfec = (r == w.num_blocks - 1) ? (int)w.last_fec : (VDL2_RS_N - VDL2_RS_K);
+					int ret = w.rs_ret[r];
+					if(ret < 0) {
+						w.status = VDL2_ERR_FEC_BAD;
+						for(uint32_t q = r + 1; q < w.num_blocks; q++) w.rs_ret[q] = -128;
+						break;
+					}
+					if(ret > 0) w.fec_corr += ret - (VDL2_RS_N - VDL2_RS_K - nfec);
+				}
+				if(w.status == VDL2_BURST_OK) vdl2_burst_unstuff(w);
+				uint32_t off = 0;
+				for(uint32_t k = 0; k < w.n_frames; k++) { s_foff[k] = (uint16_t)off; off += w.flen[k]; }
+			}
+			__syncthreads();
+			for(uint32_t k = tid; k < w.n_frames; k += K3_BLOCK)          /* K4 */
+				w.fcrc[k] = vdl2_crc16(&w.frames[s_foff[k]], w.flen[k]);
+		}
+		__syncthreads();
+		/* record -> host-mapped output region */
+		const uint32_t rec_bytes = (uint32_t)((sizeof(vdl2_burst_record) + 4u * w.n_frames + w.frame_bytes + 15u) & ~15u);
+		if(tid == 0) {
+			uint32_t off = atomicAdd(&p.ctl->out_used, rec_bytes);
+			if(off + rec_bytes > p.out_cap) { atomicAdd(&p.ctl->out_overflows, 1u); off = 0xFFFFFFFFu; }
+			else atomicAdd(&p.ctl->out_records, 1u);
+			s_out_off = off;
+		}
+		__syncthreads();
+		if(s_out_off != 0xFFFFFFFFu) {
+			uint8_t *dst = p.out + sizeof(vdl2_out_header) + s_out_off;
+			if(tid == 0) {
+				vdl2_burst_record r;
+				r.rec_bytes = rec_bytes; r.channel = slot->channel; r.burst_seq = slot->burst_seq; r.status = w.status;
+				r.n_frames = w.n_frames; r.datalen_bits = slot->datalen_bits; r.syndrome = slot->syndrome;
+				r.num_fec_corrections = w.fec_corr; r.frame_pwr = slot->frame_pwr; r.mag_nf = slot->mag_nf;
+				r.ppm_error = slot->ppm_error; r.num_blocks = w.num_blocks; r.sync_lo = slot->sync_lo; r.sync_hi = slot->sync_hi;
+				r.freq = slot->freq; r.frame_bytes = w.frame_bytes;
+				for(int q = 0; q < 12; q++) r.rs_ret[q] = (int8_t)w.rs_ret[q];
+				r.pad = 0;
+				const uint32_t *src = reinterpret_cast<const uint32_t *>(&r);
+				uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+				for(uint32_t q = 0; q < sizeof(r) / 4; q++) d32[q] = src[q];
+			}
+			uint32_t *tab32 = reinterpret_cast<uint32_t *>(dst + sizeof(vdl2_burst_record));
+			for(uint32_t k = tid; k < w.n_frames; k += K3_BLOCK) tab32[k] = (uint32_t)w.flen[k] | ((uint32_t)w.fcrc[k] << 16);
+			uint32_t *fr32 = tab32 + w.n_frames;
+			const uint32_t *fsrc = reinterpret_cast<const uint32_t *>(w.frames);
+			for(uint32_t k = tid; k < (w.frame_bytes + 3u) / 4u; k += K3_BLOCK) fr32[k] = fsrc[k];
+		}
+		/* per-channel counters (names: src/decode.c statsd counters) */
+		if(tid == 0) {
+			const uint32_t c = slot->channel, s = p.n_chp;
+			atomicAdd(&p.counters[VDL2_CNT_BURSTS * s + c], 1u);
+			if(w.status != VDL2_BURST_OK) atomicAdd(&p.counters[VDL2_CNT_BURST_ERR * s + c], 1u);
+			uint32_t run = 0, ok = 0;
+			for(uint32_t r = 0; r < w.num_blocks && r < VDL2_MAX_BLOCKS; r++)
+				if(w.rs_ret[r] != -128) { run++; if(w.rs_ret[r] >= 0) ok++; }
+			atomicAdd(&p.counters[VDL2_CNT_BLOCKS_PROCESSED * s + c], run);
+			atomicAdd(&p.counters[VDL2_CNT_BLOCKS_FEC_OK * s + c], ok);
+			atomicAdd(&p.counters[VDL2_CNT_MSG_GOOD * s + c], w.n_frames);
+			uint32_t good = 0, bad = 0;
+			for(uint32_t k = 0; k < w.n_frames; k++)
+				if(w.flen[k] >= 11) { if(w.fcrc[k] == 0xF0B8u) good++; else bad++; }
+			atomicAdd(&p.counters[VDL2_CNT_FCS_GOOD * s + c], good);
+			atomicAdd(&p.counters[VDL2_CNT_FCS_BAD * s + c], bad);
+			/* give the slot back */
+			int32_t top = atomicAdd(&p.ctl->free_top, 1);
+			p.free_list[top] = (int32_t)slot_idx;
+		}
+	}
+}
+
+/* publish the chunk's totals into the mapped region and re-arm the queues for the next chunk */
+__global__ void k_chunk_finish(vdl2_k3_params p) {
+	vdl2_out_header *h = reinterpret_cast<vdl2_out_header *>(p.out);
+	h->bytes_used = min(p.ctl->out_used, p.out_cap);
+	h->n_records = p.ctl->out_records;
+	h->pool_overflows = p.ctl->pool_overflows;
+	h->out_overflows = p.ctl->out_overflows;
+	h->n_events_total = p.ctl->n_events;
+	p.ctl->n_ready = 0;
+	p.ctl->out_used = 0;
+	p.ctl->out_records = 0;
+	__threadfence_system();
+}
+
+/* stand-alone K4 and RS kernels behind the raw launch stubs */
+__global__ void k4_fcs_crc16(const uint8_t *frames, const uint32_t *offsets, const uint32_t *lens, uint32_t n, uint16_t *out) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < n) out[i] = vdl2_crc16(frames + offsets[i], lens[i]);
+}
+
+__global__ void k_rs_verify(uint8_t *blocks, const int32_t *fec_octets, uint32_t n, int32_t *ret, const vdl2_tables *tables) {
+	__shared__ uint8_t s_gexp[512];
+	__shared__ uint8_t s_glog[256];
+	for(uint32_t i = threadIdx.x; i < 512; i += blockDim.x) s_gexp[i] = tables->gf_exp[i];
+	for(uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_glog[i] = tables->gf_log[i];
+	__syncthreads();
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < n) ret[i] = vdl2_rs_verify(blocks + (size_t)i * VDL2_RS_N, fec_octets[i], s_gexp, s_glog);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * launch stubs
+ * ---------------------------------------------------------------------------------------------- */
+#define K1_BLOCK 32
+#define K2_BLOCK 32
+
+extern "C" int vdl2_launch_k0(const void *raw, uint32_t n_pairs, uint32_t fmt, const float *levels, float *out4, cudaStream_t st) {
+	if(n_pairs == 0) return 0;
+	k0_convert<<<(n_pairs + 255) / 256, 256, 0, st>>>(static_cast<const uint8_t *>(raw), n_pairs, fmt, levels, reinterpret_cast<float4 *>(out4));
+	return (int)cudaGetLastError();
+}
+
+extern "C" int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, cudaStream_t st) {
+	if(p->n_pairs == 0 || p->n_ch == 0) return 0;
+	const uint32_t blocks = (p->n_ch + K1_BLOCK - 1) / K1_BLOCK;
+	if(!force_scalar && p->oversample == 20) k1_mix_iir_decimate_packed<20, K1_BLOCK><<<blocks, K1_BLOCK, 0, st>>>(*p);
+	else if(!force_scalar && p->oversample == 10) k1_mix_iir_decimate_packed<10, K1_BLOCK><<<blocks, K1_BLOCK, 0, st>>>(*p);
+	else k1_mix_iir_decimate_scalar<K1_BLOCK><<<blocks, K1_BLOCK, 0, st>>>(*p);
+	return (int)cudaGetLastError();
+}
+
+extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
+	if(p->n_dec == 0 || p->n_ch == 0) return 0;
+	const uint32_t blocks = (p->n_ch + K2_BLOCK - 1) / K2_BLOCK;
+	k2_sync_slice<K2_BLOCK><<<blocks, K2_BLOCK, 0, st>>>(*p);
+	return (int)cudaGetLastError();
+}
+
+extern "C" int vdl2_launch_k3(const vdl2_k3_params *p, uint32_t grid, cudaStream_t st) {
+	k3_burst_fec<<<grid, K3_BLOCK, 0, st>>>(*p);
+	int e = (int)cudaGetLastError();
+	if(e) return e;
+	k_chunk_finish<<<1, 1, 0, st>>>(*p);
+	return (int)cudaGetLastError();
+}
+
+extern "C" int vdl2_launch_k4(const uint8_t *frames, const uint32_t *offsets, const uint32_t *lens, uint32_t n, uint16_t *out, cudaStream_t st) {
+	if(n == 0) return 0;
+	k4_fcs_crc16<<<(n + 127) / 128, 128, 0, st>>>(frames, offsets, lens, n, out);
+	return (int)cudaGetLastError();
+}
+
+extern "C" int vdl2_launch_rs(uint8_t *blocks, const int32_t *fec_octets, uint32_t n, int32_t *ret, const vdl2_tables *tables, cudaStream_t st) {
+	if(n == 0) return 0;
+	k_rs_verify<<<(n + 63) / 64, 64, 0, st>>>(blocks, fec_octets, n, ret, tables);
+	return (int)cudaGetLastError();
+}

@@ -1,0 +1,64 @@
+/* vdl2_kernels.h — kernel parameter blocks and launch prototypes (internal to libvdl2gpu.so). */
+#ifndef VDL2_KERNELS_H
+#define VDL2_KERNELS_H
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "vdl2_types.h"
+
+typedef struct {
+	const float4 *samples;       /* K0 output: {re, im, im, re} per complex sample */
+	uint32_t n_pairs;
+	uint32_t oversample;
+	uint32_t cnt0;               /* decimation counter on entry (src/demod.c:289,322), same for all channels */
+	uint32_t n_ch, n_chp;
+	float2 *dec;                 /* [n_dec][n_chp] */
+	uint32_t *state;             /* [K1_NFIELDS][n_chp] */
+	const float4 *lut;           /* 257 x {cos, sin, dcos*2^-16, dsin*2^-16} */
+	float a0, a1, a2, b1, b2;
+	float one, neg_one;          /* run-time 1.0f / -1.0f (see k1_mix_iir_decimate_packed) */
+} vdl2_k1_params;
+
+typedef struct {
+	const float2 *dec;
+	uint32_t n_dec;
+	uint32_t n_ch, n_chp;
+	uint64_t dec_base;           /* absolute index of dec[0] */
+	uint32_t *state;             /* [K2_NFIELDS][n_chp] */
+	float *ring;                 /* [160][n_chp] */
+	const vdl2_tables *tables;
+	float max_ppm;
+	uint32_t s27;
+	vdl2_burst_slot *pool;
+	int32_t *free_list;
+	uint32_t *ready;
+	vdl2_queue_ctl *ctl;
+	void *events;
+	uint32_t event_cap;
+	uint32_t trace;
+} vdl2_k2_params;
+
+typedef struct {
+	vdl2_burst_slot *pool;
+	int32_t *free_list;
+	const uint32_t *ready;
+	vdl2_queue_ctl *ctl;
+	const vdl2_tables *tables;
+	uint8_t *out;                /* device address of the mapped pinned output region (header + records) */
+	uint32_t out_cap;            /* bytes available for records */
+	uint32_t n_chp;
+	uint32_t *counters;          /* [VDL2_NUM_COUNTERS][n_chp] */
+} vdl2_k3_params;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+int vdl2_launch_k0(const void *raw, uint32_t n_pairs, uint32_t fmt, const float *levels, float *out4, cudaStream_t st);
+int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, cudaStream_t st);
+int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st);
+int vdl2_launch_k3(const vdl2_k3_params *p, uint32_t grid, cudaStream_t st);
+int vdl2_launch_k4(const uint8_t *frames, const uint32_t *offsets, const uint32_t *lens, uint32_t n, uint16_t *out, cudaStream_t st);
+int vdl2_launch_rs(uint8_t *blocks, const int32_t *fec_octets, uint32_t n, int32_t *ret, const vdl2_tables *tables, cudaStream_t st);
+#ifdef __cplusplus
+}
+#endif
+#endif

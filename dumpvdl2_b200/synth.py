@@ -254,6 +254,12 @@ def synth_stream(fs, duration_s, bursts, es_n0_db=None, noise_power=None, fmt="u
     raise ValueError(fmt)
 
 
+def burst_duration_s(frames, ramp_up=4, ramp_down=2):
+    """On-air duration of the burst carrying `frames` (ramp + preamble + header/data symbols)."""
+    _, info = burst_bits(frames)
+    return (ramp_up + len(PREAMBLE_STEPS) + info["n_symbols"] + ramp_down) / SYMBOL_RATE
+
+
 def random_frames(rng, n_frames=None, lo=32, hi=240):
     n_frames = n_frames or int(rng.integers(1, 3))
     return [random_avlc_frame(rng, int(rng.integers(lo, hi + 1))) for _ in range(n_frames)]

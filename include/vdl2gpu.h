@@ -1,0 +1,178 @@
+/*
+ * include/vdl2gpu.h — C-ABI of libvdl2gpu.so: the B200 (sm_100a) implementation of dumpvdl2's
+ * per-channel DSP hot path (reference src/demod.c + src/decode.c burst part + src/chebyshev.c +
+ * src/rs.c + src/libfec + the src/bitstream.c helpers).
+ *
+ * Plain C: pointers and sizes only, no CUDA or torch types (a cudaStream_t travels as void*).
+ * Every entry point returns 0 on success or a negative VDL2GPU_E* code; the library never calls
+ * exit().  There is NO CPU fallback: without a CUDA device every call that needs one fails with
+ * VDL2GPU_ENODEV.
+ *
+ * Two front doors (INTEGRATION.md shows the reference-side binding for both):
+ *
+ *  (1) batch API (this file): one context = one IQ stream fanned out to N channels.  It replaces, as a
+ *      unit, what the reference spreads over
+ *        process_buf_uchar/process_buf_short   (src/demod.c:339-365)    -> vdl2gpu_submit
+ *        N x process_samples threads + barriers (src/demod.c:288-337)   -> kernels K0-K3 on a stream
+ *        decode_vdl2_burst -> avlc_decoder_queue_push (src/decode.c:165-194,196-384) -> vdl2gpu_poll/flush callback
+ *
+ *  (2) drop-in symbols (include/vdl2_dropin.h): the exact names/signatures of src/dumpvdl2.h:371-389 so
+ *      that the unmodified front-ends and main() of the reference link against this library.
+ */
+#ifndef VDL2GPU_H
+#define VDL2GPU_H
+#include <stddef.h>
+#include <stdint.h>
+#include <sys/time.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VDL2GPU_ABI_VERSION 1
+
+/* error codes */
+enum {
+	VDL2GPU_OK = 0,
+	VDL2GPU_EINVAL = -1,      /* bad argument */
+	VDL2GPU_ENODEV = -2,      /* no usable CUDA device / extension not usable */
+	VDL2GPU_ECUDA = -3,       /* CUDA runtime error (vdl2gpu_last_error() has the text) */
+	VDL2GPU_ENOMEM = -4,
+	VDL2GPU_ETOOBIG = -5,     /* chunk larger than max_chunk_bytes */
+	VDL2GPU_EOVERFLOW = -6    /* an internal device queue overflowed; bursts were dropped (see stats) */
+};
+
+/* sample formats: reference enum sample_formats (src/dumpvdl2.h:319) */
+enum { VDL2GPU_FMT_U8 = 0, VDL2GPU_FMT_S16_LE = 1 };
+
+/* config flags */
+enum {
+	VDL2GPU_FLAG_TRACE = 1u << 0,        /* record sync/header/burst events (debug, parity tests) */
+	VDL2GPU_FLAG_KEEP_DEC = 1u << 1,     /* keep the decimated samples of the last chunk readable (parity tests) */
+	VDL2GPU_FLAG_K1_SCALAR = 1u << 2     /* use the plain per-sample K1 kernel instead of the pipelined one */
+};
+
+typedef struct {
+	uint32_t sample_rate;        /* Hz; must equal 105000 * oversample (src/dumpvdl2.c:1073) */
+	uint32_t oversample;         /* src/dumpvdl2.h:348 */
+	uint32_t sample_fmt;         /* VDL2GPU_FMT_* */
+	uint32_t centerfreq;         /* Hz */
+	uint32_t n_channels;
+	const uint32_t *freqs;       /* n_channels channel frequencies, Hz (src/demod.c:379-392) */
+	float max_ppm;               /* Config.max_ppm (src/demod.c:192); 0 = off */
+	uint32_t max_chunk_bytes;    /* largest len ever passed to submit; 0 = 1 MiB */
+	int32_t device;              /* CUDA device ordinal; -1 = current device */
+	uint32_t flags;              /* VDL2GPU_FLAG_* */
+	uint32_t n_inflight;         /* chunks in flight before submit blocks (back-pressure); 0 = 4 */
+	uint32_t reserved[5];
+} vdl2gpu_config;
+
+/* One AVLC frame with the metadata the reference attaches in decode_frame (src/decode.c:173-194,
+ * struct vdl2_msg_metadata src/output-common.h:31-43).  `data` is valid only during the callback. */
+typedef struct {
+	uint32_t channel;            /* index into freqs[] */
+	uint32_t freq;
+	uint32_t burst_seq;          /* per-channel count of bursts that reached the data stage */
+	int32_t idx;                 /* frame number within the burst (metadata->idx) */
+	const uint8_t *data;         /* frame octets, FCS included, flags excluded */
+	uint32_t len;
+	uint32_t synd_weight;
+	uint32_t datalen_octets;
+	int32_t num_fec_corrections;
+	float frame_pwr_dbfs, nf_pwr_dbfs, ppm_error;
+	float frame_pwr, mag_nf;     /* the raw values the two dBFS figures derive from */
+	uint64_t sync_dec_index;     /* decimated-sample index at which preamble sync was declared */
+	struct timeval burst_timestamp; /* chunk arrival time + sample offset (the reference calls gettimeofday at sync) */
+	uint16_t fcs_residue;        /* crc16 over the frame; 0xF0B8 = good (src/avlc.c:40,177-179) */
+	uint16_t fcs_ok;             /* len >= 11 && residue good */
+} vdl2gpu_frame;
+
+typedef void (*vdl2gpu_frame_cb)(const vdl2gpu_frame *frame, void *user);
+
+/* per-context counters; names follow the reference's statsd counters (src/statsd.c:33-64) */
+typedef struct {
+	uint64_t chunks_submitted, chunks_completed;
+	uint64_t iq_samples;                 /* complex samples accepted */
+	uint64_t dec_samples;                /* decimated samples produced per channel */
+	uint64_t demod_sync_good;            /* demod.sync.good */
+	uint64_t decoder_crc_good;           /* decoder.crc.good (header syndrome 0) */
+	uint64_t bursts;                     /* bursts that reached DEC_DATA */
+	uint64_t burst_errors;               /* bursts dropped in DEC_DATA (any decoder.errors.*) */
+	uint64_t blocks_processed, blocks_fec_ok;
+	uint64_t msg_good;                   /* decoder.msg.good = frames pushed */
+	uint64_t fcs_good, fcs_bad;          /* avlc.frames.good / avlc.errors.bad_fcs (len >= 11 only) */
+	uint64_t pool_overflows;             /* bursts lost because the device burst pool was exhausted (must be 0) */
+	uint64_t out_overflows;              /* bursts lost because the output region was exhausted (must be 0) */
+	uint64_t kernel_launches;            /* kernels launched by this context so far */
+	uint64_t reserved[4];
+} vdl2gpu_stats;
+
+/* trace event (VDL2GPU_FLAG_TRACE): same layout as the oracle's vo_event */
+typedef struct {
+	uint32_t channel, kind;      /* kind: 1 sync, 2 header, 3 burst */
+	uint64_t dec_index;
+	int32_t i[8];
+	float f[8];
+} vdl2gpu_event;
+
+typedef struct vdl2gpu_ctx vdl2gpu_ctx;
+
+/* ---- life cycle ---- */
+int vdl2gpu_abi_version(void);
+int vdl2gpu_device_count(void);
+int vdl2gpu_create(const vdl2gpu_config *cfg, vdl2gpu_ctx **out);
+int vdl2gpu_destroy(vdl2gpu_ctx *ctx);
+const char *vdl2gpu_strerror(int code);
+const char *vdl2gpu_last_error(void);
+
+/* ---- data path ---- */
+/* == process_buf_uchar / process_buf_short (src/demod.c:339-365): `iq` is interleaved I,Q, `len` is in BYTES,
+ * the caller may reuse `iq` as soon as the call returns.  Asynchronous: copies into a pinned staging ring,
+ * enqueues H2D + kernels.  Blocks only when n_inflight chunks are pending (the reference's back-pressure). */
+int vdl2gpu_submit(vdl2gpu_ctx *ctx, const void *iq, uint32_t len);
+/* Same, but `dev_iq` already lives in this GPU's memory (e.g. the receive buffer of an NCCL broadcast).
+ * `producer_stream` (cudaStream_t, may be NULL = legacy default stream) is the stream on which the buffer
+ * was produced; the library orders its work after it.  The buffer may be overwritten once
+ * vdl2gpu_wait_input_consumed() has been enqueued on the stream that overwrites it. */
+int vdl2gpu_submit_device(vdl2gpu_ctx *ctx, const void *dev_iq, uint32_t len, void *producer_stream);
+int vdl2gpu_wait_input_consumed(vdl2gpu_ctx *ctx, void *stream);
+/* Deliver the frames of every chunk that has finished, in (chunk, channel, burst, idx) order.  Returns the
+ * number of frames delivered or a negative error.  cb may be NULL (frames are dropped, counters kept). */
+int vdl2gpu_poll(vdl2gpu_ctx *ctx, vdl2gpu_frame_cb cb, void *user);
+/* Block until everything submitted so far has been processed, then deliver like poll. */
+int vdl2gpu_flush(vdl2gpu_ctx *ctx, vdl2gpu_frame_cb cb, void *user);
+int vdl2gpu_get_stats(vdl2gpu_ctx *ctx, vdl2gpu_stats *out);
+/* per-channel counters, 9 x uint64 per channel in the order: sync_good, hdr_crc_good, bursts, burst_err,
+ * blocks_processed, blocks_fec_ok, msg_good, fcs_good, fcs_bad.  Implies a flush of device work. */
+int vdl2gpu_get_channel_counters(vdl2gpu_ctx *ctx, uint64_t *out, uint32_t n_channels);
+
+/* ---- introspection for parity tests / profiling ---- */
+/* tables the kernels use, computed by the library's own host code (restating src/demod.c:349-377,367-370,84-96) */
+int vdl2gpu_get_tables(vdl2gpu_ctx *ctx, float levels[256], float sin_lut[257], float cos_lut[257],
+		float A[3], float B[3], float lr_X[16], float *lr_denom, float pr_phase[16]);
+/* decimated samples of the most recent chunk (VDL2GPU_FLAG_KEEP_DEC): out[n_dec][n_channels][2] floats.
+ * *n_dec receives the count; cap_floats is the capacity of out.  Synchronises. */
+int vdl2gpu_read_dec(vdl2gpu_ctx *ctx, float *out, size_t cap_floats, uint32_t *n_dec);
+/* drain trace events (VDL2GPU_FLAG_TRACE).  Synchronises.  Returns the number copied. */
+int vdl2gpu_read_events(vdl2gpu_ctx *ctx, vdl2gpu_event *out, uint32_t cap);
+/* device time (ms) spent in each kernel for the chunks completed so far, measured with CUDA events on
+ * the library's stream when timing was enabled with vdl2gpu_enable_timing(ctx, 1). Order: K0,K1,K2,K3. */
+int vdl2gpu_enable_timing(vdl2gpu_ctx *ctx, int on);
+int vdl2gpu_get_kernel_ms(vdl2gpu_ctx *ctx, double ms[4], uint64_t launches[4]);
+
+/* ---- raw launch stubs (extern "C", plain pointers; used by the micro-parity tests and by hosts that
+ *      manage device memory themselves).  All pointers are DEVICE pointers; stream is a cudaStream_t. ---- */
+/* K0: raw cu8/cs16 -> float2 samples (src/demod.c:339-365) */
+int vdl2gpu_launch_convert(const void *raw, uint32_t n_pairs, uint32_t sample_fmt, const float *levels256,
+		float *samples_out /* [n_pairs][2] */, void *stream);
+/* K4: FCS residue of n frames stored back to back (src/crc.c:21-64 as used at src/avlc.c:177) */
+int vdl2gpu_launch_fcs_crc16(const uint8_t *frames, const uint32_t *offsets, const uint32_t *lens,
+		uint32_t n_frames, uint16_t *residues_out, void *stream);
+/* RS(255,249) errors-and-erasures decode of n blocks in place (src/rs.c:32-49); fec_octets[i] in {0,2,4,6} */
+int vdl2gpu_launch_rs_verify(uint8_t *blocks /* [n][255] */, const int32_t *fec_octets, uint32_t n_blocks,
+		int32_t *ret_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
