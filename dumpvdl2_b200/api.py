@@ -48,7 +48,7 @@ class _Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("chunks_submitted", "chunks_completed", "iq_samples", "dec_samples", "demod_sync_good",
                  "decoder_crc_good", "bursts", "burst_errors", "blocks_processed", "blocks_fec_ok", "msg_good",
-                 "fcs_good", "fcs_bad", "pool_overflows", "out_overflows", "kernel_launches")] + [("reserved", C.c_uint64 * 4)]
+                 "fcs_good", "fcs_bad", "pool_overflows", "out_overflows", "kernel_launches", "out_bytes")] + [("reserved", C.c_uint64 * 3)]
 
 
 class _Event(C.Structure):
@@ -74,6 +74,7 @@ def load_library():
     L.vdl2gpu_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.vdl2gpu_submit_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.vdl2gpu_wait_input_consumed.argtypes = [C.c_void_p, C.c_void_p]
+    L.vdl2gpu_stream_wait.argtypes = [C.c_void_p, C.c_void_p]
     L.vdl2gpu_poll.argtypes = [C.c_void_p, _FRAME_CB, C.c_void_p]
     L.vdl2gpu_flush.argtypes = [C.c_void_p, _FRAME_CB, C.c_void_p]
     L.vdl2gpu_get_stats.argtypes = [C.c_void_p, C.POINTER(_Stats)]
@@ -179,6 +180,9 @@ class Vdl2Channels:
 
     def wait_input_consumed(self, stream=0):
         _check(self.L, self.L.vdl2gpu_wait_input_consumed(self.h, C.c_void_p(stream)), "vdl2gpu_wait_input_consumed")
+
+    def stream_wait(self, stream=0):
+        _check(self.L, self.L.vdl2gpu_stream_wait(self.h, C.c_void_p(stream)), "vdl2gpu_stream_wait")
 
     def process_chunked(self, buf, chunk_bytes):
         b = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)

@@ -35,9 +35,10 @@ static int fail_cuda(cudaError_t e, const char *what, int line) {
 /* ------------------------------------------------------------------------------------------------
  * context
  * ---------------------------------------------------------------------------------------------- */
+/* frames harvested but not yet delivered; their octets live in per-chunk blobs (one copy per chunk) */
 struct pending_frame {
 	vdl2gpu_frame f;
-	std::vector<uint8_t> bytes;
+	uint32_t blob, offset;
 };
 
 struct chunk_slot {
@@ -79,6 +80,8 @@ struct vdl2gpu_ctx {
 	uint64_t k_launches[4] = { 0, 0, 0, 0 };
 	vdl2gpu_stats stats;
 	std::vector<pending_frame> pending;
+	std::vector<std::vector<uint8_t>> blobs;
+	cudaEvent_t ev_drain = nullptr;
 };
 
 static uint32_t dphi_for(uint32_t centerfreq, uint32_t freq, uint32_t rate) {      /* src/demod.c:385 */
@@ -124,6 +127,7 @@ static int free_ctx(vdl2gpu_ctx *c) {
 	cudaFree(c->d_ctl); cudaFree(c->d_events);
 	if(c->ev_input_ready) cudaEventDestroy(c->ev_input_ready);
 	if(c->ev_input_consumed) cudaEventDestroy(c->ev_input_consumed);
+	if(c->ev_drain) cudaEventDestroy(c->ev_drain);
 	if(c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 	return VDL2GPU_OK;
@@ -166,6 +170,7 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CU(cudaEventCreateWithFlags(&c->ev_input_ready, cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&c->ev_input_consumed, cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&c->ev_drain, cudaEventDisableTiming));
 	CU(cudaMalloc(&c->d_tab, sizeof(vdl2_tables)));
 	CU(cudaMemcpy(c->d_tab, &c->tab.t, sizeof(vdl2_tables), cudaMemcpyHostToDevice));
 	CU(cudaMalloc(&c->d_samples, (size_t)c->max_pairs * sizeof(float4)));
@@ -256,6 +261,12 @@ static void harvest(vdl2gpu_ctx *c, chunk_slot &s) {
 	}
 	const vdl2_out_header *h = reinterpret_cast<const vdl2_out_header *>(s.h_out);
 	const uint8_t *base = s.h_out + sizeof(vdl2_out_header);
+	const vdl2_out_header hcopy = *h; h = &hcopy;
+	/* one copy out of the mapped region, so the region can be handed back to the device at once */
+	c->blobs.emplace_back(base, base + std::min(h->bytes_used, c->out_cap));
+	const uint32_t blob_id = (uint32_t)c->blobs.size() - 1;
+	base = c->blobs.back().data();
+	c->stats.out_bytes += h->bytes_used;            /* out_bytes: record bytes written by K3 (D2H traffic) */
 	std::vector<const vdl2_burst_record *> recs;
 	uint32_t off = 0;
 	for(uint32_t k = 0; k < h->n_records && off + sizeof(vdl2_burst_record) <= h->bytes_used; k++) {
@@ -283,7 +294,8 @@ static void harvest(vdl2gpu_ctx *c, chunk_slot &s) {
 			const uint32_t len = tab[k] & 0xFFFFu, crc = tab[k] >> 16;
 			pending_frame pf;
 			memset(&pf.f, 0, sizeof(pf.f));
-			pf.bytes.assign(bytes + foff, bytes + foff + len);
+			pf.blob = blob_id;
+			pf.offset = (uint32_t)((bytes + foff) - base);
 			foff += len;
 			pf.f.channel = r->channel; pf.f.freq = r->freq; pf.f.burst_seq = r->burst_seq; pf.f.idx = (int32_t)k;
 			pf.f.len = len;
@@ -305,7 +317,7 @@ static void harvest(vdl2gpu_ctx *c, chunk_slot &s) {
 			pf.f.fcs_ok = (len >= 11 && crc == 0xF0B8u) ? 1 : 0;
 			c->stats.msg_good++;
 			if(len >= 11) { if(crc == 0xF0B8u) c->stats.fcs_good++; else c->stats.fcs_bad++; }
-			c->pending.push_back(std::move(pf));
+			c->pending.push_back(pf);
 		}
 	}
 	c->stats.chunks_completed++;
@@ -314,11 +326,14 @@ static void harvest(vdl2gpu_ctx *c, chunk_slot &s) {
 
 static int deliver(vdl2gpu_ctx *c, vdl2gpu_frame_cb cb, void *user) {
 	int n = (int)c->pending.size();
-	for(auto &pf : c->pending) {
-		pf.f.data = pf.bytes.data();
-		if(cb) cb(&pf.f, user);
+	if(cb) {
+		for(auto &pf : c->pending) {
+			pf.f.data = c->blobs[pf.blob].data() + pf.offset;
+			cb(&pf.f, user);
+		}
 	}
 	c->pending.clear();
+	c->blobs.clear();
 	return n;
 }
 
@@ -418,6 +433,14 @@ extern "C" int vdl2gpu_submit_device(vdl2gpu_ctx *c, const void *dev_iq, uint32_
 extern "C" int vdl2gpu_wait_input_consumed(vdl2gpu_ctx *c, void *stream) {
 	if(!c) return VDL2GPU_EINVAL;
 	CU(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_input_consumed, 0));
+	return VDL2GPU_OK;
+}
+
+extern "C" int vdl2gpu_stream_wait(vdl2gpu_ctx *c, void *stream) {
+	if(!c) return VDL2GPU_EINVAL;
+	CU(cudaSetDevice(c->device));
+	CU(cudaEventRecord(c->ev_drain, c->stream));
+	CU(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_drain, 0));
 	return VDL2GPU_OK;
 }
 

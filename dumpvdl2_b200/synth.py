@@ -263,3 +263,29 @@ def burst_duration_s(frames, ramp_up=4, ramp_down=2):
 def random_frames(rng, n_frames=None, lo=32, hi=240):
     n_frames = n_frames or int(rng.integers(1, 3))
     return [random_avlc_frame(rng, int(rng.integers(lo, hi + 1))) for _ in range(n_frames)]
+
+
+def slot_offsets(n_slots=64, spacing_hz=25e3):
+    """n_slots channel offsets on the 25 kHz raster, symmetric about (and excluding) the centre frequency."""
+    half = n_slots // 2
+    return [spacing_hz * k for k in range(-half, half + 1) if k != 0][:n_slots]
+
+
+def traffic_stream(fs=2100000, duration_s=4.0, n_slots=64, bursts_per_s=2.0, es_n0_db=20.0, power_dbfs=-20.0,
+                   seed=0x56444C33, fmt="u8"):
+    """BASELINE.json config 3/5 traffic model: n_slots 25 kHz slots, Poisson burst arrivals
+    per slot, 1-2 AVLC frames of 32-240 octets per burst.  Returns (iq array, slot offsets, bursts)."""
+    rng = np.random.default_rng(seed)
+    offs = slot_offsets(n_slots)
+    bursts = []
+    for o in offs:
+        t = float(rng.exponential(1.0 / bursts_per_s))
+        while True:
+            frames = random_frames(rng)
+            d = burst_duration_s(frames)
+            if t + d > duration_s - 0.005:
+                break
+            bursts.append(BurstSpec(t, o, frames, power_dbfs=power_dbfs))
+            t += d + 0.005 + float(rng.exponential(1.0 / bursts_per_s))
+    iq = synth_stream(fs, duration_s, bursts, es_n0_db=es_n0_db, fmt=fmt, seed=seed + 1)
+    return iq, offs, bursts

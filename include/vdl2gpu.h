@@ -104,7 +104,8 @@ typedef struct {
 	uint64_t pool_overflows;             /* bursts lost because the device burst pool was exhausted (must be 0) */
 	uint64_t out_overflows;              /* bursts lost because the output region was exhausted (must be 0) */
 	uint64_t kernel_launches;            /* kernels launched by this context so far */
-	uint64_t reserved[4];
+	uint64_t out_bytes;                  /* burst-record bytes K3 wrote to host memory (device->host traffic) */
+	uint64_t reserved[3];
 } vdl2gpu_stats;
 
 /* trace event (VDL2GPU_FLAG_TRACE): same layout as the oracle's vo_event */
@@ -136,6 +137,9 @@ int vdl2gpu_submit(vdl2gpu_ctx *ctx, const void *iq, uint32_t len);
  * vdl2gpu_wait_input_consumed() has been enqueued on the stream that overwrites it. */
 int vdl2gpu_submit_device(vdl2gpu_ctx *ctx, const void *dev_iq, uint32_t len, void *producer_stream);
 int vdl2gpu_wait_input_consumed(vdl2gpu_ctx *ctx, void *stream);
+/* Make `stream` (cudaStream_t) wait for all device work enqueued by this context so far (for timing with
+ * events recorded on the caller's stream, and for ordering consumers of device-side results). */
+int vdl2gpu_stream_wait(vdl2gpu_ctx *ctx, void *stream);
 /* Deliver the frames of every chunk that has finished, in (chunk, channel, burst, idx) order.  Returns the
  * number of frames delivered or a negative error.  cb may be NULL (frames are dropped, counters kept). */
 int vdl2gpu_poll(vdl2gpu_ctx *ctx, vdl2gpu_frame_cb cb, void *user);

@@ -62,7 +62,8 @@ def assert_matches_golden(frames, golden, flavour, what):
         assert a.channel == b["channel"] and a.idx == b["idx"], f"{what}: order mismatch {a} vs {b['channel']}/{b['idx']}"
         assert a.data.hex() == b["hex"], f"{what}: frame bytes differ for {a}"
         assert a.synd_weight == b["synd_weight"] and a.datalen_octets == b["datalen_octets"]
-        assert a.num_fec_corrections == b["num_fec_corrections"]
+        if flavour == "strict":     # -ffast-math float differences may flip a marginal symbol; RS repairs it, the count differs
+            assert a.num_fec_corrections == b["num_fec_corrections"]
         tol = 0.0 if flavour == "strict" else 0.01           # 0.01 dB / 0.01 ppm vs the -ffast-math build
         for fld in ("frame_pwr_dbfs", "nf_pwr_dbfs", "ppm_error"):
             x, y = float(np.float32(getattr(a, fld))), float(np.float32(b[fld]))
