@@ -40,6 +40,8 @@ def build(force=False):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir("/root/reference/src"):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+        if os.path.exists(os.path.join(_HERE, "..", "dumpvdl2_b200", "libvdl2gpu.so")):
+            subprocess.check_call(["make", "-C", _HERE, "dropin"], stdout=subprocess.DEVNULL)
     return so
 
 

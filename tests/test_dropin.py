@@ -1,0 +1,60 @@
+"""The drop-in boundary: the reference's own init/feed protocol (oracle/ref_harness.c = what src/dumpvdl2.c does:
+vdl2_channel_init xN, rs_init, ..., barriers, one process_samples pthread per channel, process_buf_* per chunk,
+final demods_ready wait) and the reference's own src/decode.c (avlc_decoder_queue_push) linked against
+libvdl2gpu.so instead of src/demod.c + src/rs.c + src/libfec.  Output must equal the unmodified reference's."""
+import os
+import subprocess
+import tempfile
+import pytest
+from tests import cases, util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HARNESS = os.path.join(ROOT, "tests", "_bin", "vdl2_dropin_harness")
+LAYOUT = os.path.join(ROOT, "tests", "_bin", "layout_check")
+
+
+@pytest.mark.skipif(not os.path.exists(LAYOUT), reason="tests/_bin not built (needs /root/reference at build time)")
+def test_layout_mirrors_match_reference_headers():
+    r = subprocess.run([LAYOUT], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    assert "MISMATCH" not in r.stdout and r.stdout.count(" ok") >= 10
+
+
+@pytest.mark.skipif(not os.path.exists(HARNESS), reason="tests/_bin not built")
+def test_harness_links_against_the_product_library():
+    out = subprocess.run(["ldd", HARNESS], capture_output=True, text=True).stdout
+    assert "libvdl2gpu.so" in out and "not found" not in out.split("libvdl2gpu.so")[1].splitlines()[0]
+
+
+def _run_harness(case):
+    with tempfile.NamedTemporaryFile(suffix=".iq", delete=False) as tf:
+        tf.write(util.case_bytes(case).tobytes())
+        path = tf.name
+    try:
+        cmd = [HARNESS, "--fmt", "s16" if case["fmt"] == "s16" else "u8", "--oversample", str(case["oversample"]),
+               "--centerfreq", str(case["centerfreq"]), "--freqs", ",".join(str(f) for f in case["freqs"]),
+               "--chunk", str(case["chunk"]), path]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        frames = []
+        for line in r.stdout.splitlines():
+            if line.startswith("FRAME"):
+                frames.append(dict(t.split("=", 1) for t in line.split()[1:]))
+        return frames
+    finally:
+        os.unlink(path)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(HARNESS), reason="tests/_bin not built")
+@pytest.mark.parametrize("name", ["wav", "cfg2", "mixed_s16"])
+def test_dropin_harness_reproduces_reference_output(name):
+    c = cases.ALL_GOLDEN[name]()
+    got = _run_harness(c)
+    want = util.load_golden(name)["strict"]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):          # same print order: per channel, push order
+        assert int(a["ch"]) == b["channel"] and int(a["idx"]) == b["idx"] and a.get("hex", "") == b["hex"]
+        assert int(a["synd"]) == b["synd_weight"] and int(a["datalen"]) == b["datalen_octets"] and int(a["fec"]) == b["num_fec_corrections"]
+        for k, g in (("pwr", "frame_pwr_dbfs"), ("nf", "nf_pwr_dbfs"), ("ppm", "ppm_error")):
+            assert float(a[k]) == float(f"{b[g]:.9g}"), (k, a[k], b[g])
