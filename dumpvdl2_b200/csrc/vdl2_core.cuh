@@ -335,17 +335,25 @@ VDL2_HD void vdl2_burst_complete(vdl2_chan &v, const vdl2_k2_env &env, uint32_t 
 	vdl2_set_dec_state(v, VDL2_DEC_IDLE);
 }
 
-/* src/demod.c:222-286 — one decimated sample of one channel */
-VDL2_HD void vdl2_demod_step(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env,
-		uint32_t chan_idx, uint64_t dec_index, float re, float im) {
+/* phase and magnitude of one decimated sample, exactly as the reference obtains them:
+ *   (float)atan2((double)im, (double)re)                 src/demod.c:232,256 (double atan2, narrowed on store)
+ *   hypotf(re, im)                                       src/demod.c:238; glibc evaluates sqrt(x*x + y*y) in double and narrows
+ * Both are pure functions of the sample, so the K2a pre-pass computes them for every decimated sample of the
+ * chunk in parallel and the sequential state machine only consumes them. */
+VDL2_HD float vdl2_phase_of(float re, float im) { return D_TO_F(atan2((double)im, (double)re)); }
+VDL2_HD float vdl2_mag_of(float re, float im) {
+	return D_TO_F(D_SQRT(D_ADD(D_MUL((double)re, (double)re), D_MUL((double)im, (double)im))));
+}
+
+/* src/demod.c:222-286 — one decimated sample of one channel; `phi`/`mag` = vdl2_phase_of / vdl2_mag_of of it */
+VDL2_HD void vdl2_demod_step_pm(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env,
+		uint32_t chan_idx, uint64_t dec_index, float re, float im, float phi, float mag) {
 	if(vdl2_dec_state(v) == VDL2_DEC_IDLE) vdl2_demod_reset(v);
 	if(!(v.state & VDL2_ST_LOCKED)) {
 		v.ring_pos = (v.ring_pos + 1 == VDL2_SYNC_BUFLEN) ? 0 : v.ring_pos + 1;
-		ring[v.ring_pos * rs] = D_TO_F(atan2((double)im, (double)re));
+		ring[v.ring_pos * rs] = phi;
 		if(++v.sclk < VDL2_SYNC_SKIP) return;
 		v.sclk = 0;
-		/* hypotf(re, im): glibc evaluates sqrt(x*x + y*y) in double and narrows (checked in tests) */
-		float mag = D_TO_F(D_SQRT(D_ADD(D_MUL((double)re, (double)re), D_MUL((double)im, (double)im))));
 		const float one_minus_mag_lp = 1.0f - 0.9f, one_minus_nf_lp = 1.0f - 0.85f;
 		v.mag_lp = F_ADD(F_MUL(v.mag_lp, 0.9f), F_MUL(mag, one_minus_mag_lp));
 		if(++v.nfcnt == 1000) {
@@ -361,7 +369,6 @@ VDL2_HD void vdl2_demod_step(vdl2_chan &v, float *ring, int rs, const vdl2_k2_en
 	}
 	if(++v.sclk < VDL2_SPS) return;
 	v.sclk = 0;
-	float phi = D_TO_F(atan2((double)im, (double)re));
 	float dphi = F_SUB(F_SUB(phi, v.prev_phi), v.dphi);
 	if(dphi < 0.f) dphi = D_TO_F(D_ADD((double)dphi, VDL2_TWO_PI));
 	else if(dphi >= VDL2_TWO_PI_F_ABOVE) dphi = D_TO_F(D_SUB((double)dphi, VDL2_TWO_PI));
@@ -383,6 +390,12 @@ VDL2_HD void vdl2_demod_step(vdl2_chan &v, float *ring, int rs, const vdl2_k2_en
 		if(vdl2_dec_state(v) == VDL2_DEC_HEADER) vdl2_header_step(v, env, chan_idx, dec_index);
 		else if(vdl2_dec_state(v) == VDL2_DEC_DATA) vdl2_burst_complete(v, env, chan_idx);
 	}
+}
+
+/* same, computing phase and magnitude in place (host simulation, unit tests) */
+VDL2_HD void vdl2_demod_step(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env,
+		uint32_t chan_idx, uint64_t dec_index, float re, float im) {
+	vdl2_demod_step_pm(v, ring, rs, env, chan_idx, dec_index, re, im, vdl2_phase_of(re, im), vdl2_mag_of(re, im));
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -62,7 +62,7 @@ struct vdl2gpu_ctx {
 	host_tables tab;
 	vdl2_tables *d_tab = nullptr;
 	float4 *d_samples = nullptr;
-	float2 *d_dec = nullptr;
+	float2 *d_dec = nullptr, *d_pm = nullptr;
 	uint32_t *d_k1 = nullptr, *d_k2 = nullptr, *d_counters = nullptr, *d_ready = nullptr;
 	float *d_ring = nullptr;
 	vdl2_burst_slot *d_pool = nullptr;
@@ -122,7 +122,7 @@ static int free_ctx(vdl2gpu_ctx *c) {
 		if(s.done) cudaEventDestroy(s.done);
 		for(auto &e : s.tk) if(e) cudaEventDestroy(e);
 	}
-	cudaFree(c->d_tab); cudaFree(c->d_samples); cudaFree(c->d_dec); cudaFree(c->d_k1); cudaFree(c->d_k2);
+	cudaFree(c->d_tab); cudaFree(c->d_samples); cudaFree(c->d_dec); cudaFree(c->d_pm); cudaFree(c->d_k1); cudaFree(c->d_k2);
 	cudaFree(c->d_counters); cudaFree(c->d_ready); cudaFree(c->d_ring); cudaFree(c->d_pool); cudaFree(c->d_free);
 	cudaFree(c->d_ctl); cudaFree(c->d_events);
 	if(c->ev_input_ready) cudaEventDestroy(c->ev_input_ready);
@@ -175,6 +175,7 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	CU(cudaMemcpy(c->d_tab, &c->tab.t, sizeof(vdl2_tables), cudaMemcpyHostToDevice));
 	CU(cudaMalloc(&c->d_samples, (size_t)c->max_pairs * sizeof(float4)));
 	CU(cudaMalloc(&c->d_dec, (size_t)c->max_dec * c->n_chp * sizeof(float2)));
+	CU(cudaMalloc(&c->d_pm, (size_t)c->max_dec * c->n_chp * sizeof(float2)));
 	CU(cudaMalloc(&c->d_k1, (size_t)K1_NFIELDS * c->n_chp * 4));
 	CU(cudaMalloc(&c->d_k2, (size_t)K2_NFIELDS * c->n_chp * 4));
 	CU(cudaMalloc(&c->d_counters, (size_t)VDL2_NUM_COUNTERS * c->n_chp * 4));
@@ -374,7 +375,7 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	KL(vdl2_launch_k1(&p1, (c->cfg.flags & VDL2GPU_FLAG_K1_SCALAR) ? 1 : 0, c->stream));
 	if(s.timed) CU(cudaEventRecord(s.tk[2], c->stream));
 	vdl2_k2_params p2;
-	p2.dec = c->d_dec; p2.n_dec = s.n_dec; p2.n_ch = c->n_ch; p2.n_chp = c->n_chp; p2.dec_base = s.dec_base;
+	p2.dec = c->d_dec; p2.pm = c->d_pm; p2.n_dec = s.n_dec; p2.n_ch = c->n_ch; p2.n_chp = c->n_chp; p2.dec_base = s.dec_base;
 	p2.state = c->d_k2; p2.ring = c->d_ring; p2.tables = c->d_tab; p2.max_ppm = c->cfg.max_ppm; p2.s27 = c->tab.s27;
 	p2.pool = c->d_pool; p2.free_list = c->d_free; p2.ready = c->d_ready; p2.ctl = c->d_ctl;
 	p2.events = c->d_events; p2.event_cap = c->event_cap; p2.trace = (c->cfg.flags & VDL2GPU_FLAG_TRACE) ? 1u : 0u;
@@ -383,7 +384,7 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	vdl2_k3_params p3;
 	p3.pool = c->d_pool; p3.free_list = c->d_free; p3.ready = c->d_ready; p3.ctl = c->d_ctl; p3.tables = c->d_tab;
 	p3.out = s.d_out; p3.out_cap = c->out_cap; p3.n_chp = c->n_chp; p3.counters = c->d_counters;
-	KL(vdl2_launch_k3(&p3, 296u, c->stream));
+	KL(vdl2_launch_k3(&p3, 148u * 8u, c->stream));
 	if(s.timed) CU(cudaEventRecord(s.tk[4], c->stream));
 	CU(cudaEventRecord(s.done, c->stream));
 	s.busy = true;
@@ -396,7 +397,7 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	c->stats.chunks_submitted++;
 	c->stats.iq_samples += n_pairs;
 	c->stats.dec_samples += s.n_dec;
-	c->stats.kernel_launches += (n_pairs ? 2 : 0) + (s.n_dec ? 1 : 0) + 2;
+	c->stats.kernel_launches += (n_pairs ? 2 : 0) + (s.n_dec ? 2 : 0) + 2;
 	return VDL2GPU_OK;
 }
 

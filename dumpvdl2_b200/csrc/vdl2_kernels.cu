@@ -14,6 +14,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "vdl2_core.cuh"
 #include "vdl2_kernels.h"
 
@@ -153,9 +154,26 @@ __device__ __forceinline__ u64 k1_packed_step(const float4 s, const float4 *s_lu
 	return y0;
 }
 
+/* the same step with the table entry, the phase fraction and the sample already in registers (the batched
+ * body loads a whole batch first so that no shared-memory latency sits inside the arithmetic) */
+__device__ __forceinline__ u64 k1_packed_math(const float4 s, const float4 e, const float fr,
+		u64 &x1, u64 &x2, u64 &y1, u64 &y2, const k1_packed_consts &c) {
+	const u64 CS = f2_fma(f2_mul(f2_pack(e.z, e.w), f2_pack(fr, fr)), c.ONE, f2_pack(e.x, e.y));
+	const float cs = f2_lo(CS), sn = f2_hi(CS);
+	const u64 P = f2_mul(f2_pack(s.x, s.y), f2_pack(cs, cs));
+	const u64 Q = f2_mul(f2_pack(s.z, s.w), f2_pack(sn, sn));
+	const u64 x0 = f2_fma(Q, c.SGN, P);
+	const u64 t = f2_fma(f2_mul(c.A1, x1), c.ONE, f2_mul(c.A2, x2));
+	const u64 r = f2_fma(f2_mul(c.A0, x0), c.ONE, t);
+	const u64 u = f2_fma(f2_mul(c.B1, y1), c.ONE, f2_mul(c.B2, y2));
+	const u64 y0 = f2_fma(r, c.ONE, u);
+	x2 = x1; x1 = x0; y2 = y1; y1 = y0;
+	return y0;
+}
+
 #define K1P_TILE_GROUPS(OS) (2560 / (OS))       /* 2560 samples = 40 KB of float4 per tile */
 
-template<int OS, int BLOCK>
+template<int OS, int BLOCK, int BATCH>
 __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_params p) {
 	constexpr int TG = K1P_TILE_GROUPS(OS);
 	__shared__ float4 s_lut[257];
@@ -198,9 +216,44 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 			for(uint32_t g = 0; g < ng; g++) {
 				const float4 *sp = &s_tile[g * OS];
 				u64 y0 = 0;
+				if(BATCH == 0) {
 #pragma unroll
-				for(int k = 0; k < OS; k++)
-					y0 = k1_packed_step(sp[k], s_lut, phi, dphi, x1, x2, y1, y2, c);
+					for(int k = 0; k < OS; k++)
+						y0 = k1_packed_step(sp[k], s_lut, phi, dphi, x1, x2, y1, y2, c);
+				} else {
+					/* software pipeline written out over the unrolled group: loads run LA samples ahead of the
+					 * mixer, the mixer MA samples ahead of the filter recurrence */
+					constexpr int LA = BATCH, MA = BATCH / 2;
+					float4 S[OS], E[OS];
+					float FR[OS];
+					u64 X0[OS];
+#pragma unroll
+					for(int k = -LA; k < OS; k++) {
+						const int kl = k + LA, km = k + MA;
+						if(kl < OS) {
+							const uint32_t ph = phi + (uint32_t)kl * dphi;
+							E[kl] = s_lut[(ph >> 16) & 0xFFu];
+							FR[kl] = (float)(ph & 0xFFFFu);
+							S[kl] = sp[kl];
+						}
+						if(km >= 0 && km < OS) {
+							const u64 CS = f2_fma(f2_mul(f2_pack(E[km].z, E[km].w), f2_pack(FR[km], FR[km])), c.ONE, f2_pack(E[km].x, E[km].y));
+							const float cs = f2_lo(CS), sn = f2_hi(CS);
+							const u64 P = f2_mul(f2_pack(S[km].x, S[km].y), f2_pack(cs, cs));
+							const u64 Q = f2_mul(f2_pack(S[km].z, S[km].w), f2_pack(sn, sn));
+							X0[km] = f2_fma(Q, c.SGN, P);
+						}
+						if(k >= 0) {
+							const u64 x0 = X0[k];
+							const u64 t = f2_fma(f2_mul(c.A1, x1), c.ONE, f2_mul(c.A2, x2));
+							const u64 r = f2_fma(f2_mul(c.A0, x0), c.ONE, t);
+							const u64 u = f2_fma(f2_mul(c.B1, y1), c.ONE, f2_mul(c.B2, y2));
+							y0 = f2_fma(r, c.ONE, u);
+							x2 = x1; x1 = x0; y2 = y1; y1 = y0;
+						}
+					}
+					phi += (uint32_t)OS * dphi;
+				}
 				p.dec[(size_t)(m + g) * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0));
 			}
 		}
@@ -223,6 +276,16 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
  * (bank = lane, conflict-free whatever the per-channel ring position).
  * ---------------------------------------------------------------------------------------------- */
 #define K2_PREFETCH 8
+
+/* K2a: phase and magnitude of every decimated sample of the chunk (src/demod.c:232,238,256), one thread per
+ * (time, channel) element: the double-precision atan2/sqrt run at full occupancy here instead of inside the
+ * sequential per-channel walk of K2. */
+__global__ void __launch_bounds__(256) k2a_phase_mag(const float2 *__restrict__ dec, float2 *__restrict__ pm, uint32_t n_elems) {
+	uint32_t i = blockIdx.x * 256u + threadIdx.x;
+	if(i >= n_elems) return;
+	const float2 d = dec[i];
+	pm[i] = make_float2(vdl2_phase_of(d.x, d.y), vdl2_mag_of(d.x, d.y));
+}
 
 template<int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
@@ -263,18 +326,19 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	env.cnt_bursts = nullptr;
 
 	const float2 *dec = p.dec + ch;
+	const float2 *pm = p.pm + ch;
 	uint32_t m = 0;
 	for(; m + K2_PREFETCH <= p.n_dec; m += K2_PREFETCH) {
-		float2 buf[K2_PREFETCH];
+		float2 buf[K2_PREFETCH], bpm[K2_PREFETCH];
 #pragma unroll
-		for(int k = 0; k < K2_PREFETCH; k++) buf[k] = __ldg(&dec[(size_t)(m + k) * s]);
+		for(int k = 0; k < K2_PREFETCH; k++) { buf[k] = __ldg(&dec[(size_t)(m + k) * s]); bpm[k] = __ldg(&pm[(size_t)(m + k) * s]); }
 #pragma unroll 1
 		for(int k = 0; k < K2_PREFETCH; k++)
-			vdl2_demod_step(v, ring, BLOCK, env, ch, p.dec_base + m + k, buf[k].x, buf[k].y);
+			vdl2_demod_step_pm(v, ring, BLOCK, env, ch, p.dec_base + m + k, buf[k].x, buf[k].y, bpm[k].x, bpm[k].y);
 	}
 	for(; m < p.n_dec; m++) {
-		float2 d = __ldg(&dec[(size_t)m * s]);
-		vdl2_demod_step(v, ring, BLOCK, env, ch, p.dec_base + m, d.x, d.y);
+		float2 d = __ldg(&dec[(size_t)m * s]), q = __ldg(&pm[(size_t)m * s]);
+		vdl2_demod_step_pm(v, ring, BLOCK, env, ch, p.dec_base + m, d.x, d.y, q.x, q.y);
 	}
 
 	for(int i = 0; i < VDL2_SYNC_BUFLEN; i++) p.ring[(size_t)i * s + ch] = ring[i * BLOCK];
@@ -443,15 +507,27 @@ extern "C" int vdl2_launch_k0(const void *raw, uint32_t n_pairs, uint32_t fmt, c
 extern "C" int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, cudaStream_t st) {
 	if(p->n_pairs == 0 || p->n_ch == 0) return 0;
 	const uint32_t blocks = (p->n_ch + K1_BLOCK - 1) / K1_BLOCK;
-	if(!force_scalar && p->oversample == 20) k1_mix_iir_decimate_packed<20, K1_BLOCK><<<blocks, K1_BLOCK, 0, st>>>(*p);
-	else if(!force_scalar && p->oversample == 10) k1_mix_iir_decimate_packed<10, K1_BLOCK><<<blocks, K1_BLOCK, 0, st>>>(*p);
-	else k1_mix_iir_decimate_scalar<K1_BLOCK><<<blocks, K1_BLOCK, 0, st>>>(*p);
+	static int variant = -1;
+	if(variant < 0) { const char *e = getenv("VDL2GPU_K1_VARIANT"); variant = e ? atoi(e) : 2; }
+	if(!force_scalar && p->oversample == 20) {
+		if(variant == 0) k1_mix_iir_decimate_packed<20, K1_BLOCK, 0><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		else if(variant == 1) k1_mix_iir_decimate_packed<20, K1_BLOCK, 5><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		else if(variant == 3) k1_mix_iir_decimate_packed<20, K1_BLOCK, 20><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		else k1_mix_iir_decimate_packed<20, K1_BLOCK, 10><<<blocks, K1_BLOCK, 0, st>>>(*p);
+	} else if(!force_scalar && p->oversample == 10) {
+		if(variant == 0) k1_mix_iir_decimate_packed<10, K1_BLOCK, 0><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		else k1_mix_iir_decimate_packed<10, K1_BLOCK, 10><<<blocks, K1_BLOCK, 0, st>>>(*p);
+	} else k1_mix_iir_decimate_scalar<K1_BLOCK><<<blocks, K1_BLOCK, 0, st>>>(*p);
 	return (int)cudaGetLastError();
 }
 
 extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
 	if(p->n_dec == 0 || p->n_ch == 0) return 0;
 	const uint32_t blocks = (p->n_ch + K2_BLOCK - 1) / K2_BLOCK;
+	const uint32_t n_elems = p->n_dec * p->n_chp;
+	k2a_phase_mag<<<(n_elems + 255u) / 256u, 256, 0, st>>>(p->dec, p->pm, n_elems);
+	int e = (int)cudaGetLastError();
+	if(e) return e;
 	k2_sync_slice<K2_BLOCK><<<blocks, K2_BLOCK, 0, st>>>(*p);
 	return (int)cudaGetLastError();
 }

@@ -20,6 +20,7 @@ typedef struct {
 
 typedef struct {
 	const float2 *dec;
+	float2 *pm;                  /* [n_dec][n_chp] {phase, magnitude}, written by K2a */
 	uint32_t n_dec;
 	uint32_t n_ch, n_chp;
 	uint64_t dec_base;           /* absolute index of dec[0] */

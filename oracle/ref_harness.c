@@ -87,6 +87,8 @@ static chan_capture_t *captures;
 static int num_channels;
 static int keep_frames = 1;
 static __thread int tl_chan = -1;
+static uint32_t *chan_freqs;
+static pthread_mutex_t capture_lock = PTHREAD_MUTEX_INITIALIZER;
 
 struct shim_async_queue { int unused; };
 static struct shim_async_queue the_queue;
@@ -101,7 +103,15 @@ void g_async_queue_push(GAsyncQueue *q, void *item) {
 		fprintf(stderr, "frame pushed from a non-channel thread\n");
 		_exit(4);
 	}
-	chan_capture_t *cc = &captures[tl_chan];   /* only this channel's thread touches cc */
+	/* The reference pushes from the channel's own thread.  A drop-in demodulator may push every channel's
+	 * frames from one thread: then the channel is recovered from the metadata (first channel on that frequency). */
+	int chan = tl_chan;
+	if(chan_freqs[chan] != e->metadata->freq) {
+		for(chan = 0; chan < num_channels && chan_freqs[chan] != e->metadata->freq; chan++) ;
+		if(chan == num_channels) { fprintf(stderr, "frame for an unknown frequency\n"); _exit(4); }
+	}
+	pthread_mutex_lock(&capture_lock);
+	chan_capture_t *cc = &captures[chan];
 	cc->count++;
 	if(keep_frames) {
 		captured_t *c = calloc(1, sizeof(*c));
@@ -112,6 +122,7 @@ void g_async_queue_push(GAsyncQueue *q, void *item) {
 		if(cc->tail) cc->tail->next = c; else cc->head = c;
 		cc->tail = c;
 	}
+	pthread_mutex_unlock(&capture_lock);
 	octet_string_destroy(e->frame);
 	free(e->metadata);
 	free(e);
@@ -171,6 +182,7 @@ int main(int argc, char **argv) {
 		free(dup);
 	}
 	if(centerfreq == 0) centerfreq = freqs[0];
+	chan_freqs = freqs;
 	uint32_t sample_rate = SYMBOL_RATE * SPS * oversample;       /* reference src/dumpvdl2.c:1073 */
 
 	/* load the whole input into RAM */
