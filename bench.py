@@ -276,7 +276,7 @@ def main():
 
     for _ in range(W):
         step_device()
-    g.enable_timing(True)
+    g.enable_timing(True)           # CUDA events between the kernels, on the library's stream
     k0 = g.kernel_ms()
     ms_dev, frames_dev, d_dev, clocks, wall_dev = timed(step_device, K, sample_clocks=True)
     k1 = g.kernel_ms()
@@ -338,7 +338,8 @@ def main():
                           note="effective-bandwidth model of SURVEY.md §8d (each channel streams the float IQ buffer); the shared stream is "
                                "served from shared memory so DRAM traffic is far lower and the kernel is FP32-issue bound",
                           kernel_share_of_step={k: v[0] / tot_k for k, v in kms.items()},
-                          kernel_ms_per_launch={k: v[0] / max(v[1], 1) for k, v in kms.items()}),
+                          kernel_ms_per_launch={k: v[0] / max(v[1], 1) for k, v in kms.items()},
+                          measured="CUDA events on the library's stream inside the timed region (device-resident pass)"),
             clocks=clocks,
             parity=dict(pool_overflows=int(d_dev["pool_overflows"] + d_e2e["pool_overflows"]), out_overflows=int(d_dev["out_overflows"] + d_e2e["out_overflows"]),
                         bursts_per_step=d_dev["bursts"] / K, fcs_good_per_step=d_dev["fcs_good"] / K, fcs_bad_per_step=d_dev["fcs_bad"] / K),

@@ -45,7 +45,7 @@ struct chunk_slot {
 	uint8_t *h_raw = nullptr, *d_raw = nullptr;
 	uint8_t *h_out = nullptr, *d_out = nullptr;
 	cudaEvent_t done = nullptr;
-	cudaEvent_t tk[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+	cudaEvent_t tk[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   /* front: 0,1,2  back: 3,4,5 */
 	bool busy = false, timed = false;
 	uint64_t first_pair = 0, dec_base = 0;
 	uint32_t n_pairs = 0, n_dec = 0;
@@ -56,13 +56,18 @@ struct vdl2gpu_ctx {
 	vdl2gpu_config cfg;
 	std::vector<uint32_t> freqs;
 	int device = 0;
-	cudaStream_t stream = nullptr;
+	/* `stream` (front) carries H2D + K0 + K1, `s_back` K2a/K2/K3.  By default they are the same stream.  With
+	 * VDL2GPU_FLAG_OVERLAP they differ and chunk c+1's front stage may run beside chunk c's back stage; measured on
+	 * B200 this gains little (K1 keeps the FP32 pipe ~65 % busy on its own) and is erratic, so it is opt-in */
+	cudaStream_t stream = nullptr, s_back = nullptr;
+	cudaEvent_t ev_k1_done[2] = { nullptr, nullptr }, ev_back_done[2] = { nullptr, nullptr };
+	uint64_t chunk_seq = 0;
 	cudaEvent_t ev_input_ready = nullptr, ev_input_consumed = nullptr;
 	uint32_t n_ch = 0, n_chp = 0, max_pairs = 0, max_dec = 0, n_slots = 0, out_cap = 0, event_cap = 0;
 	host_tables tab;
 	vdl2_tables *d_tab = nullptr;
 	float4 *d_samples = nullptr;
-	float2 *d_dec = nullptr, *d_pm = nullptr;
+	float2 *d_dec2[2] = { nullptr, nullptr }, *d_pm = nullptr;
 	uint32_t *d_k1 = nullptr, *d_k2 = nullptr, *d_counters = nullptr, *d_ready = nullptr;
 	float *d_ring = nullptr;
 	vdl2_burst_slot *d_pool = nullptr;
@@ -115,6 +120,7 @@ static int free_ctx(vdl2gpu_ctx *c) {
 	if(!c) return VDL2GPU_OK;
 	cudaSetDevice(c->device);
 	if(c->stream) cudaStreamSynchronize(c->stream);
+	if(c->s_back) cudaStreamSynchronize(c->s_back);
 	for(auto &s : c->chunks) {
 		if(s.h_raw) cudaFreeHost(s.h_raw);
 		if(s.d_raw) cudaFree(s.d_raw);
@@ -122,12 +128,14 @@ static int free_ctx(vdl2gpu_ctx *c) {
 		if(s.done) cudaEventDestroy(s.done);
 		for(auto &e : s.tk) if(e) cudaEventDestroy(e);
 	}
-	cudaFree(c->d_tab); cudaFree(c->d_samples); cudaFree(c->d_dec); cudaFree(c->d_pm); cudaFree(c->d_k1); cudaFree(c->d_k2);
+	cudaFree(c->d_tab); cudaFree(c->d_samples); cudaFree(c->d_dec2[0]); cudaFree(c->d_dec2[1]); cudaFree(c->d_pm); cudaFree(c->d_k1); cudaFree(c->d_k2);
 	cudaFree(c->d_counters); cudaFree(c->d_ready); cudaFree(c->d_ring); cudaFree(c->d_pool); cudaFree(c->d_free);
 	cudaFree(c->d_ctl); cudaFree(c->d_events);
 	if(c->ev_input_ready) cudaEventDestroy(c->ev_input_ready);
 	if(c->ev_input_consumed) cudaEventDestroy(c->ev_input_consumed);
 	if(c->ev_drain) cudaEventDestroy(c->ev_drain);
+	for(int i = 0; i < 2; i++) { if(c->ev_k1_done[i]) cudaEventDestroy(c->ev_k1_done[i]); if(c->ev_back_done[i]) cudaEventDestroy(c->ev_back_done[i]); }
+	if(c->s_back && c->s_back != c->stream) cudaStreamDestroy(c->s_back);
 	if(c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 	return VDL2GPU_OK;
@@ -168,13 +176,22 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	memset(&c->stats, 0, sizeof(c->stats));
 
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	if(cfg->flags & VDL2GPU_FLAG_OVERLAP) CU(cudaStreamCreateWithFlags(&c->s_back, cudaStreamNonBlocking));
+	else c->s_back = c->stream;
+	for(int i = 0; i < 2; i++) {
+		CU(cudaEventCreateWithFlags(&c->ev_k1_done[i], cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&c->ev_back_done[i], cudaEventDisableTiming));
+	}
 	CU(cudaEventCreateWithFlags(&c->ev_input_ready, cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&c->ev_input_consumed, cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&c->ev_drain, cudaEventDisableTiming));
 	CU(cudaMalloc(&c->d_tab, sizeof(vdl2_tables)));
 	CU(cudaMemcpy(c->d_tab, &c->tab.t, sizeof(vdl2_tables), cudaMemcpyHostToDevice));
 	CU(cudaMalloc(&c->d_samples, (size_t)c->max_pairs * sizeof(float4)));
-	CU(cudaMalloc(&c->d_dec, (size_t)c->max_dec * c->n_chp * sizeof(float2)));
+	for(int i = 0; i < 2; i++) {
+		CU(cudaMalloc(&c->d_dec2[i], (size_t)c->max_dec * c->n_chp * sizeof(float2)));
+		CU(cudaMemset(c->d_dec2[i], 0, (size_t)c->max_dec * c->n_chp * sizeof(float2)));
+	}
 	CU(cudaMalloc(&c->d_pm, (size_t)c->max_dec * c->n_chp * sizeof(float2)));
 	CU(cudaMalloc(&c->d_k1, (size_t)K1_NFIELDS * c->n_chp * 4));
 	CU(cudaMalloc(&c->d_k2, (size_t)K2_NFIELDS * c->n_chp * 4));
@@ -185,7 +202,6 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	CU(cudaMalloc(&c->d_ready, (size_t)c->n_slots * 4));
 	CU(cudaMalloc(&c->d_ctl, sizeof(vdl2_queue_ctl)));
 	CU(cudaMalloc(&c->d_events, (size_t)c->event_cap * sizeof(vdl2gpu_event)));
-	CU(cudaMemset(c->d_dec, 0, (size_t)c->max_dec * c->n_chp * sizeof(float2)));
 	CU(cudaMemset(c->d_counters, 0, (size_t)VDL2_NUM_COUNTERS * c->n_chp * 4));
 	CU(cudaMemset(c->d_ring, 0, (size_t)VDL2_SYNC_BUFLEN * c->n_chp * 4));
 	CU(cudaMemset(c->d_pool, 0, (size_t)c->n_slots * sizeof(vdl2_burst_slot)));
@@ -254,9 +270,10 @@ static uint32_t synd_weight_of(uint32_t syn) {       /* src/decode.c:98-100 */
 
 static void harvest(vdl2gpu_ctx *c, chunk_slot &s) {
 	if(s.timed) {
+		static const int from[4] = { 0, 1, 3, 4 };              /* K0, K1 on the front stream; K2(+K2a), K3 on the back stream */
 		for(int k = 0; k < 4; k++) {
 			float ms = 0.f;
-			if(cudaEventElapsedTime(&ms, s.tk[k], s.tk[k + 1]) == cudaSuccess) { c->k_ms[k] += ms; c->k_launches[k]++; }
+			if(cudaEventElapsedTime(&ms, s.tk[from[k]], s.tk[from[k] + 1]) == cudaSuccess) { c->k_ms[k] += ms; c->k_launches[k]++; }
 		}
 		s.timed = false;
 	}
@@ -362,31 +379,41 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	s.n_dec = (c->decim_cnt + n_pairs) / os;
 	gettimeofday(&s.arrival, NULL);
 	s.timed = c->timing;
+	const int db = (int)(c->chunk_seq & 1u);                 /* decimated-sample buffer of this chunk */
+	float2 *d_dec = c->d_dec2[db];
+	/* ---- front stage: K0, K1 ---- */
 	if(s.timed) CU(cudaEventRecord(s.tk[0], c->stream));
 	KL(vdl2_launch_k0(d_raw, n_pairs, c->cfg.sample_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->stream));
 	CU(cudaEventRecord(c->ev_input_consumed, c->stream));
 	if(s.timed) CU(cudaEventRecord(s.tk[1], c->stream));
+	if(c->chunk_seq >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_back_done[db], 0));   /* K2 of chunk c-2 has read this buffer */
 	vdl2_k1_params p1;
 	p1.samples = c->d_samples; p1.n_pairs = n_pairs; p1.oversample = os; p1.cnt0 = c->decim_cnt;
-	p1.n_ch = c->n_ch; p1.n_chp = c->n_chp; p1.dec = c->d_dec; p1.state = c->d_k1;
+	p1.n_ch = c->n_ch; p1.n_chp = c->n_chp; p1.dec = d_dec; p1.state = c->d_k1;
 	p1.lut = reinterpret_cast<const float4 *>(c->d_tab->lut);
 	p1.a0 = c->tab.t.A[0]; p1.a1 = c->tab.t.A[1]; p1.a2 = c->tab.t.A[2]; p1.b1 = c->tab.t.B[1]; p1.b2 = c->tab.t.B[2];
 	p1.one = 1.0f; p1.neg_one = -1.0f;
 	KL(vdl2_launch_k1(&p1, (c->cfg.flags & VDL2GPU_FLAG_K1_SCALAR) ? 1 : 0, c->stream));
 	if(s.timed) CU(cudaEventRecord(s.tk[2], c->stream));
+	CU(cudaEventRecord(c->ev_k1_done[db], c->stream));
+	/* ---- back stage: K2a, K2, K3 ---- */
+	CU(cudaStreamWaitEvent(c->s_back, c->ev_k1_done[db], 0));
+	if(s.timed) CU(cudaEventRecord(s.tk[3], c->s_back));
 	vdl2_k2_params p2;
-	p2.dec = c->d_dec; p2.pm = c->d_pm; p2.n_dec = s.n_dec; p2.n_ch = c->n_ch; p2.n_chp = c->n_chp; p2.dec_base = s.dec_base;
+	p2.dec = d_dec; p2.pm = c->d_pm; p2.n_dec = s.n_dec; p2.n_ch = c->n_ch; p2.n_chp = c->n_chp; p2.dec_base = s.dec_base;
 	p2.state = c->d_k2; p2.ring = c->d_ring; p2.tables = c->d_tab; p2.max_ppm = c->cfg.max_ppm; p2.s27 = c->tab.s27;
 	p2.pool = c->d_pool; p2.free_list = c->d_free; p2.ready = c->d_ready; p2.ctl = c->d_ctl;
 	p2.events = c->d_events; p2.event_cap = c->event_cap; p2.trace = (c->cfg.flags & VDL2GPU_FLAG_TRACE) ? 1u : 0u;
-	KL(vdl2_launch_k2(&p2, c->stream));
-	if(s.timed) CU(cudaEventRecord(s.tk[3], c->stream));
+	KL(vdl2_launch_k2(&p2, c->s_back));
+	CU(cudaEventRecord(c->ev_back_done[db], c->s_back));
+	if(s.timed) CU(cudaEventRecord(s.tk[4], c->s_back));
 	vdl2_k3_params p3;
 	p3.pool = c->d_pool; p3.free_list = c->d_free; p3.ready = c->d_ready; p3.ctl = c->d_ctl; p3.tables = c->d_tab;
 	p3.out = s.d_out; p3.out_cap = c->out_cap; p3.n_chp = c->n_chp; p3.counters = c->d_counters;
-	KL(vdl2_launch_k3(&p3, 148u * 8u, c->stream));
-	if(s.timed) CU(cudaEventRecord(s.tk[4], c->stream));
-	CU(cudaEventRecord(s.done, c->stream));
+	KL(vdl2_launch_k3(&p3, 148u * 8u, c->s_back));
+	if(s.timed) CU(cudaEventRecord(s.tk[5], c->s_back));
+	CU(cudaEventRecord(s.done, c->s_back));
+	c->chunk_seq++;
 	s.busy = true;
 	c->inflight.push_back(c->next_slot);
 	c->next_slot = (c->next_slot + 1) % (uint32_t)c->chunks.size();
@@ -440,7 +467,7 @@ extern "C" int vdl2gpu_wait_input_consumed(vdl2gpu_ctx *c, void *stream) {
 extern "C" int vdl2gpu_stream_wait(vdl2gpu_ctx *c, void *stream) {
 	if(!c) return VDL2GPU_EINVAL;
 	CU(cudaSetDevice(c->device));
-	CU(cudaEventRecord(c->ev_drain, c->stream));
+	CU(cudaEventRecord(c->ev_drain, c->s_back));        /* every chunk's chain ends on the back stream */
 	CU(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_drain, 0));
 	return VDL2GPU_OK;
 }
@@ -464,6 +491,7 @@ extern "C" int vdl2gpu_flush(vdl2gpu_ctx *c, vdl2gpu_frame_cb cb, void *user) {
 	if(!c) return VDL2GPU_EINVAL;
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->s_back));
 	while(!c->inflight.empty()) {
 		chunk_slot &s = c->chunks[c->inflight.front()];
 		if(s.busy) harvest(c, s);
@@ -475,6 +503,7 @@ extern "C" int vdl2gpu_flush(vdl2gpu_ctx *c, vdl2gpu_frame_cb cb, void *user) {
 static int read_counters(vdl2gpu_ctx *c, std::vector<uint32_t> &k3, std::vector<uint32_t> &sync, std::vector<uint32_t> &hdr) {
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->s_back));
 	k3.resize((size_t)VDL2_NUM_COUNTERS * c->n_chp);
 	sync.resize(c->n_chp); hdr.resize(c->n_chp);
 	CU(cudaMemcpy(k3.data(), c->d_counters, k3.size() * 4, cudaMemcpyDeviceToHost));
@@ -528,10 +557,11 @@ extern "C" int vdl2gpu_read_dec(vdl2gpu_ctx *c, float *out, size_t cap_floats, u
 	if(!c || !out || !n_dec) return VDL2GPU_EINVAL;
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->s_back));
 	*n_dec = c->last_n_dec;
 	if((size_t)c->last_n_dec * c->n_ch * 2 > cap_floats) return VDL2GPU_ETOOBIG;
 	if(c->last_n_dec == 0) return VDL2GPU_OK;
-	CU(cudaMemcpy2D(out, (size_t)c->n_ch * sizeof(float2), c->d_dec, (size_t)c->n_chp * sizeof(float2),
+	CU(cudaMemcpy2D(out, (size_t)c->n_ch * sizeof(float2), c->d_dec2[(c->chunk_seq + 1) & 1u], (size_t)c->n_chp * sizeof(float2),
 			(size_t)c->n_ch * sizeof(float2), c->last_n_dec, cudaMemcpyDeviceToHost));
 	return VDL2GPU_OK;
 }
@@ -541,6 +571,7 @@ extern "C" int vdl2gpu_read_events(vdl2gpu_ctx *c, vdl2gpu_event *out, uint32_t 
 	if(!(c->cfg.flags & VDL2GPU_FLAG_TRACE)) return 0;
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaStreamSynchronize(c->s_back));
 	vdl2_queue_ctl ctl;
 	CU(cudaMemcpy(&ctl, c->d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost));
 	uint32_t total = std::min(ctl.n_events, c->event_cap);

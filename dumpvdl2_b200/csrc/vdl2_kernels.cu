@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) k0_convert(const uint8_t *__restrict__ ra
  * K1, plain per-sample form (reference for the pipelined kernel; selected by VDL2GPU_FLAG_K1_SCALAR
  * and for oversample values without a specialisation).
  * ---------------------------------------------------------------------------------------------- */
-#define K1_TILE 2048
+#define K1_TILE 1024
 
 __device__ __forceinline__ void k1_load_state(const vdl2_k1_params &p, uint32_t ch, float &xr1, float &xr2, float &xi1,
 		float &xi2, float &yr1, float &yr2, float &yi1, float &yi2, uint32_t &phi, uint32_t &dphi) {
@@ -171,7 +171,7 @@ __device__ __forceinline__ u64 k1_packed_math(const float4 s, const float4 e, co
 	return y0;
 }
 
-#define K1P_TILE_GROUPS(OS) (2560 / (OS))       /* 2560 samples = 40 KB of float4 per tile */
+#define K1P_TILE_GROUPS(OS) (640 / (OS))        /* 640 samples = 10 KB of float4 per tile: leaves room for K2's blocks on the same SM */
 
 template<int OS, int BLOCK, int BATCH>
 __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_params p) {
@@ -327,19 +327,22 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 
 	const float2 *dec = p.dec + ch;
 	const float2 *pm = p.pm + ch;
+	/* register-resident prefetch, two samples per trip: the replacements for both are requested before the
+	 * (~2 us of) dependent work on the current pair and only moved into place after it */
+	float2 d0 = make_float2(0.f, 0.f), q0 = d0, d1 = d0, q1 = d0;
+	if(p.n_dec > 0) { d0 = __ldg(&dec[0]); q0 = __ldg(&pm[0]); }
+	if(p.n_dec > 1) { d1 = __ldg(&dec[s]); q1 = __ldg(&pm[s]); }
 	uint32_t m = 0;
-	for(; m + K2_PREFETCH <= p.n_dec; m += K2_PREFETCH) {
-		float2 buf[K2_PREFETCH], bpm[K2_PREFETCH];
-#pragma unroll
-		for(int k = 0; k < K2_PREFETCH; k++) { buf[k] = __ldg(&dec[(size_t)(m + k) * s]); bpm[k] = __ldg(&pm[(size_t)(m + k) * s]); }
 #pragma unroll 1
-		for(int k = 0; k < K2_PREFETCH; k++)
-			vdl2_demod_step_pm(v, ring, BLOCK, env, ch, p.dec_base + m + k, buf[k].x, buf[k].y, bpm[k].x, bpm[k].y);
+	for(; m + 2 <= p.n_dec; m += 2) {
+		float2 e0 = d0, r0 = q0, e1 = d1, r1 = q1;
+		if(m + 2 < p.n_dec) { e0 = __ldg(&dec[(size_t)(m + 2) * s]); r0 = __ldg(&pm[(size_t)(m + 2) * s]); }
+		if(m + 3 < p.n_dec) { e1 = __ldg(&dec[(size_t)(m + 3) * s]); r1 = __ldg(&pm[(size_t)(m + 3) * s]); }
+		vdl2_demod_step_pm(v, ring, BLOCK, env, ch, p.dec_base + m, d0.x, d0.y, q0.x, q0.y);
+		vdl2_demod_step_pm(v, ring, BLOCK, env, ch, p.dec_base + m + 1, d1.x, d1.y, q1.x, q1.y);
+		d0 = e0; q0 = r0; d1 = e1; q1 = r1;
 	}
-	for(; m < p.n_dec; m++) {
-		float2 d = __ldg(&dec[(size_t)m * s]), q = __ldg(&pm[(size_t)m * s]);
-		vdl2_demod_step_pm(v, ring, BLOCK, env, ch, p.dec_base + m, d.x, d.y, q.x, q.y);
-	}
+	if(m < p.n_dec) vdl2_demod_step_pm(v, ring, BLOCK, env, ch, p.dec_base + m, d0.x, d0.y, q0.x, q0.y);
 
 	for(int i = 0; i < VDL2_SYNC_BUFLEN; i++) p.ring[(size_t)i * s + ch] = ring[i * BLOCK];
 	st[K2_PREV_PHI * s + ch] = __float_as_uint(v.prev_phi); st[K2_PREV_DPHI * s + ch] = __float_as_uint(v.prev_dphi);
