@@ -56,6 +56,11 @@ static inline int32_t vdl2_host_fetch_add_i32(int32_t *p, int32_t v) { int32_t o
 #define VDL2_THREADFENCE() do {} while (0)
 #endif
 
+#define VDL2_PURE_SATURATED 0x40000000u
+/* the metric at sample n reads the phases of samples n-150, n-140, ..., n: it is a pure function of the
+ * decimated stream (and can be precomputed in parallel) once that many samples were written without a reset */
+#define VDL2_PURE_NEEDED 151u
+
 #define VDL2_PI 3.14159265358979323846          /* M_PI */
 #define VDL2_TWO_PI 6.28318530717958647692      /* 2.0f * M_PI evaluated in double */
 #define VDL2_PI_4 0.78539816339744830962        /* M_PI_4 */
@@ -78,6 +83,7 @@ struct vdl2_chan {
 	uint64_t sync_dec_index;
 	uint32_t freq;
 	uint32_t cnt_sync, cnt_hdr_good;
+	uint32_t pure_run;           /* consecutive DM_INIT samples since the last demod_reset (saturating) */
 };
 
 struct vdl2_event_rec {          /* == vdl2gpu_event / vo_event */
@@ -116,6 +122,7 @@ VDL2_HD void vdl2_demod_reset(vdl2_chan &v) {
 	v.pherr1 = v.pherr2 = 1000.f;
 	v.frame_pwr = 0.f;
 	v.frame_pwr_cnt = 0;
+	v.pure_run = 0;
 }
 
 /* src/demod.c:379-392 */
@@ -125,6 +132,7 @@ VDL2_HD void vdl2_chan_init(vdl2_chan &v, uint32_t freq) {
 	v.freq = freq;
 	v.slot = -1;
 	vdl2_demod_reset(v);
+	v.pure_run = VDL2_PURE_SATURATED;      /* the ring starts as zeros == "phases" of the samples before the stream */
 }
 
 VDL2_HD void vdl2_emit_event(const vdl2_k2_env &env, const vdl2_event_rec &e) {
@@ -191,21 +199,17 @@ VDL2_HD float vdl2_para_vertex(float x, float y1, float y2, float y3) {
 	return F_DIV(-qb, F_MUL(2.f, qa));
 }
 
-/* src/demod.c:105-198.  `ring` points at this channel's column, consecutive phases `rs` floats apart. */
-VDL2_HD int vdl2_preamble_metric(vdl2_chan &v, const float *ring, int rs, const vdl2_k2_env &env,
-		uint32_t chan_idx, uint64_t dec_index) {
+/* src/demod.c:129-171: regression metric over the 16 preamble-spaced phases ph[0..15] (oldest first).
+ * Returns the squared-error sum, *slope_out = the fitted phase slope (freq_err). */
+VDL2_HD float vdl2_metric_core(const float *ph, const float *pr_phase, const float *lr_X, float lr_denom, float *slope_out) {
 	float err[VDL2_PREAMBLE_SYMS];
-	int idx = v.ring_pos + VDL2_SPS;
-	if(idx >= VDL2_SYNC_BUFLEN) idx -= VDL2_SYNC_BUFLEN;
 	float unwrap = 0.f;
-	float prev = F_SUB(ring[idx * rs], env.pr_phase[0]);
+	float prev = F_SUB(ph[0], pr_phase[0]);
 	float mean = prev;
 	err[0] = prev;
 #pragma unroll
 	for(int i = 1; i < VDL2_PREAMBLE_SYMS; i++) {
-		idx += VDL2_SPS;
-		if(idx >= VDL2_SYNC_BUFLEN) idx -= VDL2_SYNC_BUFLEN;
-		float cur = F_SUB(ring[idx * rs], env.pr_phase[i]);
+		float cur = F_SUB(ph[i], pr_phase[i]);
 		float step = F_SUB(cur, prev);
 		prev = cur;
 		if(step >= VDL2_PI_F_ABOVE) unwrap = D_TO_F(D_SUB((double)unwrap, VDL2_TWO_PI));
@@ -218,14 +222,37 @@ VDL2_HD int vdl2_preamble_metric(vdl2_chan &v, const float *ring, int rs, const 
 #pragma unroll
 	for(int i = 0; i < VDL2_PREAMBLE_SYMS; i++) {
 		err[i] = F_SUB(err[i], mean);
-		slope = F_ADD(slope, F_MUL(env.lr_X[i], err[i]));
+		slope = F_ADD(slope, F_MUL(lr_X[i], err[i]));
 	}
-	slope = F_DIV(slope, env.lr_denom);
+	slope = F_DIV(slope, lr_denom);
 	float p0 = 0.f;
 #pragma unroll
 	for(int i = 0; i < VDL2_PREAMBLE_SYMS; i++) {
-		float e = F_SUB(err[i], F_MUL(slope, env.lr_X[i]));
+		float e = F_SUB(err[i], F_MUL(slope, lr_X[i]));
 		p0 = F_ADD(p0, F_MUL(e, e));
+	}
+	*slope_out = slope;
+	return p0;
+}
+
+/* src/demod.c:105-198.  `ring` points at this channel's column, consecutive phases `rs` floats apart.
+ * When `have_pre` the metric pair (pre_p0, pre_slope) was computed by the parallel pre-pass from the same 16
+ * phases and is used as is; otherwise it is evaluated here from the ring. */
+VDL2_HD int vdl2_preamble_metric(vdl2_chan &v, const float *ring, int rs, const vdl2_k2_env &env,
+		uint32_t chan_idx, uint64_t dec_index, bool have_pre, float pre_p0, float pre_slope) {
+	float p0, slope;
+	if(have_pre) {
+		p0 = pre_p0; slope = pre_slope;
+	} else {
+		float ph[VDL2_PREAMBLE_SYMS];
+		int idx = v.ring_pos;
+#pragma unroll
+		for(int i = 0; i < VDL2_PREAMBLE_SYMS; i++) {
+			idx += VDL2_SPS;
+			if(idx >= VDL2_SYNC_BUFLEN) idx -= VDL2_SYNC_BUFLEN;
+			ph[i] = ring[idx * rs];
+		}
+		p0 = vdl2_metric_core(ph, env.pr_phase, env.lr_X, env.lr_denom, &slope);
 	}
 	v.pherr0 = p0;
 	if(v.pherr1 < 4.f && p0 > v.pherr1) {
@@ -347,11 +374,13 @@ VDL2_HD float vdl2_mag_of(float re, float im) {
 
 /* src/demod.c:222-286 — one decimated sample of one channel; `phi`/`mag` = vdl2_phase_of / vdl2_mag_of of it */
 VDL2_HD void vdl2_demod_step_pm(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env,
-		uint32_t chan_idx, uint64_t dec_index, float re, float im, float phi, float mag) {
+		uint32_t chan_idx, uint64_t dec_index, float re, float im, float phi, float mag,
+		bool pre_valid, float pre_p0, float pre_slope) {
 	if(vdl2_dec_state(v) == VDL2_DEC_IDLE) vdl2_demod_reset(v);
 	if(!(v.state & VDL2_ST_LOCKED)) {
 		v.ring_pos = (v.ring_pos + 1 == VDL2_SYNC_BUFLEN) ? 0 : v.ring_pos + 1;
 		ring[v.ring_pos * rs] = phi;
+		if(v.pure_run < VDL2_PURE_SATURATED) v.pure_run++;
 		if(++v.sclk < VDL2_SYNC_SKIP) return;
 		v.sclk = 0;
 		const float one_minus_mag_lp = 1.0f - 0.9f, one_minus_nf_lp = 1.0f - 0.85f;
@@ -360,7 +389,8 @@ VDL2_HD void vdl2_demod_step_pm(vdl2_chan &v, float *ring, int rs, const vdl2_k2
 			v.nfcnt = 0;
 			v.mag_nf = F_ADD(F_ADD(F_MUL(0.85f, v.mag_nf), F_MUL(one_minus_nf_lp, fminf(v.mag_lp, v.mag_nf))), 0.0001f);
 		}
-		if(vdl2_preamble_metric(v, ring, rs, env, chan_idx, dec_index)) {
+		if(vdl2_preamble_metric(v, ring, rs, env, chan_idx, dec_index,
+				pre_valid && v.pure_run >= VDL2_PURE_NEEDED, pre_p0, pre_slope)) {
 			v.cnt_sync++;
 			v.sync_dec_index = dec_index;
 			v.state |= VDL2_ST_LOCKED;
@@ -395,7 +425,7 @@ VDL2_HD void vdl2_demod_step_pm(vdl2_chan &v, float *ring, int rs, const vdl2_k2
 /* same, computing phase and magnitude in place (host simulation, unit tests) */
 VDL2_HD void vdl2_demod_step(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env,
 		uint32_t chan_idx, uint64_t dec_index, float re, float im) {
-	vdl2_demod_step_pm(v, ring, rs, env, chan_idx, dec_index, re, im, vdl2_phase_of(re, im), vdl2_mag_of(re, im));
+	vdl2_demod_step_pm(v, ring, rs, env, chan_idx, dec_index, re, im, vdl2_phase_of(re, im), vdl2_mag_of(re, im), false, 0.f, 0.f);
 }
 
 /* ------------------------------------------------------------------------------------------------

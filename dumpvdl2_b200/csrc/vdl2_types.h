@@ -6,6 +6,10 @@
  *   samples   float2[max_pairs]            K0 -> K1   converted stream (src/demod.c:339-365)
  *   dec       float2[max_dec][n_chp]       K1 -> K2   decimated samples, TIME-MAJOR: a warp of 32 channels
  *                                                     reads/writes 256 contiguous bytes per time step
+ *   phase     float[160+max_dec][n_chp]    K2a -> K2b,K2   atan2 of every decimated sample; the first 160 rows carry the
+ *                                                     tail of the previous chunk (the preamble metric looks 150 back)
+ *   mag       float[max_dec][n_chp]        K2a -> K2  hypot of every decimated sample
+ *   metric    float2[max_dec][n_chp]       K2b -> K2  {squared-error sum, slope} of the preamble regression at every sample
  *   k1 state  u32[K1_NFIELDS][n_chp]       SoA        filter delay lines + NCO (src/demod.c:289-298)
  *   k2 state  u32[K2_NFIELDS][n_chp]       SoA        demodulator/decoder scalars (src/dumpvdl2.h:321-352)
  *   ring      float[160][n_chp]                       syncbuf phase ring (src/dumpvdl2.h:324)
@@ -55,7 +59,7 @@ enum {
 	K2_PREV_PHI = 0, K2_PREV_DPHI, K2_DPHI, K2_PHERR0, K2_PHERR1, K2_PHERR2, K2_PPM, K2_MAG_LP, K2_MAG_NF,
 	K2_FRAME_PWR, K2_RING_POS, K2_SCLK, K2_NFCNT, K2_FRAME_PWR_CNT, K2_STATE, K2_ACC_LO, K2_ACC_HI, K2_NBITS,
 	K2_NEED_BITS, K2_DATALEN, K2_SYNDROME, K2_SLOT, K2_BURST_SEQ, K2_SYNC_LO, K2_SYNC_HI, K2_FREQ,
-	K2_CNT_SYNC, K2_CNT_HDR_GOOD, K2_NFIELDS
+	K2_CNT_SYNC, K2_CNT_HDR_GOOD, K2_PURE_RUN, K2_NFIELDS
 };
 /* K2_STATE bit layout */
 #define VDL2_ST_LOCKED 1u            /* demod_state == DM_SYNC (src/dumpvdl2.h:294) */

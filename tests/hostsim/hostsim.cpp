@@ -57,7 +57,8 @@ int hostsim_k1(const float *samples /*[n][2]*/, uint32_t n_pairs, uint32_t rate,
  * frame table + frame bytes), events in vdl2_event_rec format. */
 int hostsim_k2k3(const float *dec /*[n_dec][n_ch][2]*/, uint32_t n_dec, uint32_t n_ch, const uint32_t *freqs,
 		uint32_t rate, float max_ppm, uint8_t *out, uint32_t out_cap, uint32_t *out_used, uint32_t *n_records,
-		vdl2_event_rec *events, uint32_t event_cap, uint32_t *n_events, uint32_t *chan_counters /*[n_ch][2]: sync, hdr_good*/) {
+		vdl2_event_rec *events, uint32_t event_cap, uint32_t *n_events, uint32_t *chan_counters /*[n_ch][2]: sync, hdr_good*/,
+		int use_pre /* 1: consume the parallel pre-pass like K2 does; 0: always evaluate from the ring */) {
 	host_tables *h = new host_tables();
 	make_tables(*h, rate);
 	const uint32_t n_slots = 3 * n_ch + 16;
@@ -79,12 +80,29 @@ int hostsim_k2k3(const float *dec /*[n_dec][n_ch][2]*/, uint32_t n_dec, uint32_t
 	vdl2_burst_work *w = new vdl2_burst_work();
 	/* the kernels process chunk by chunk: K2 over all channels, then K3 over the ready list; mimic with
 	 * chunks of 1024 decimated samples so that slot recycling is exercised */
+	/* K2a + K2b emulation: phase plane with a 160-row zero history, metric for every sample */
+	std::vector<float> phase((size_t)(n_dec + VDL2_SYNC_BUFLEN) * n_ch, 0.f), mag((size_t)n_dec * n_ch), met((size_t)n_dec * n_ch * 2);
+	for(uint32_t m = 0; m < n_dec; m++)
+		for(uint32_t ch = 0; ch < n_ch; ch++) {
+			const float *d = &dec[((size_t)m * n_ch + ch) * 2];
+			phase[(size_t)(m + VDL2_SYNC_BUFLEN) * n_ch + ch] = vdl2_phase_of(d[0], d[1]);
+			mag[(size_t)m * n_ch + ch] = vdl2_mag_of(d[0], d[1]);
+		}
+	for(uint32_t m = 0; m < n_dec; m++)
+		for(uint32_t ch = 0; ch < n_ch; ch++) {
+			float ph[VDL2_PREAMBLE_SYMS], slope;
+			for(int i = 0; i < VDL2_PREAMBLE_SYMS; i++) ph[i] = phase[(size_t)(m + 10 + 10 * i) * n_ch + ch];
+			met[((size_t)m * n_ch + ch) * 2] = vdl2_metric_core(ph, h->t.pr_phase, h->t.lr_X, h->t.lr_denom, &slope);
+			met[((size_t)m * n_ch + ch) * 2 + 1] = slope;
+		}
 	for(uint32_t base = 0; base < n_dec; base += 1024) {
 		uint32_t n = n_dec - base < 1024 ? n_dec - base : 1024;
 		for(uint32_t ch = 0; ch < n_ch; ch++)
 			for(uint32_t m = 0; m < n; m++) {
-				const float *d = &dec[((size_t)(base + m) * n_ch + ch) * 2];
-				vdl2_demod_step(chans[ch], &rings[(size_t)ch * VDL2_SYNC_BUFLEN], 1, env, ch, base + m, d[0], d[1]);
+				const size_t o = (size_t)(base + m) * n_ch + ch;
+				const float *d = &dec[o * 2];
+				vdl2_demod_step_pm(chans[ch], &rings[(size_t)ch * VDL2_SYNC_BUFLEN], 1, env, ch, base + m, d[0], d[1],
+						phase[o + (size_t)VDL2_SYNC_BUFLEN * n_ch], mag[o], use_pre != 0, met[o * 2], met[o * 2 + 1]);
 			}
 		for(uint32_t b = 0; b < ctl.n_ready; b++) {
 			const vdl2_burst_slot *slot = &pool[ready[b]];

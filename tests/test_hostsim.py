@@ -16,8 +16,9 @@ def _samples(case):
     return po.levels_u8()[b]
 
 
+@pytest.mark.parametrize("use_pre", [True, False])
 @pytest.mark.parametrize("name", ["cfg2", "mixed_s16", "fec", "noisy", "wav"])
-def test_device_functions_on_host_match_oracle(name):
+def test_device_functions_on_host_match_oracle(name, use_pre):
     c = cases.ALL_GOLDEN[name]()
     o = util.run_oracle(c, trace=True, dec_tap=True)
     odec = o.dec_samples()
@@ -26,7 +27,7 @@ def test_device_functions_on_host_match_oracle(name):
     hdec = hs.k1(s, c["fs"], c["oversample"], c["centerfreq"], c["freqs"])
     assert hdec.shape == odec.shape
     assert np.array_equal(hdec.view(np.uint32), odec.view(np.uint32)), "K1 arithmetic differs from the oracle"
-    recs, ev, cnt = hs.k2k3(odec, c["freqs"], c["fs"])
+    recs, ev, cnt = hs.k2k3(odec, c["freqs"], c["fs"], use_pre=use_pre)
     got = []
     for r in recs:
         for k, (data, crc) in enumerate(r["frames"]):
