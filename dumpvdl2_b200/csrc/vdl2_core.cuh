@@ -14,6 +14,7 @@
 #ifndef VDL2_CORE_CUH
 #define VDL2_CORE_CUH
 #include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <string.h>
 #include "vdl2_types.h"
@@ -38,7 +39,9 @@
 #define VDL2_ATOMIC_ADD_U32(p, v) atomicAdd((unsigned int *)(p), (unsigned int)(v))
 #define VDL2_ATOMIC_ADD_I32(p, v) atomicAdd((int *)(p), (int)(v))
 #define VDL2_THREADFENCE() __threadfence()
+#define VDL2_LDG(p) __ldg(p)
 #else
+#define VDL2_LDG(p) (*(p))
 #define F_MUL(a, b) ((float)(a) * (float)(b))
 #define F_ADD(a, b) ((float)(a) + (float)(b))
 #define F_SUB(a, b) ((float)(a) - (float)(b))
@@ -199,39 +202,63 @@ VDL2_HD float vdl2_para_vertex(float x, float y1, float y2, float y3) {
 	return F_DIV(-qb, F_MUL(2.f, qa));
 }
 
-/* src/demod.c:129-171: regression metric over the 16 preamble-spaced phases ph[0..15] (oldest first).
- * Returns the squared-error sum, *slope_out = the fitted phase slope (freq_err). */
-VDL2_HD float vdl2_metric_core(const float *ph, const float *pr_phase, const float *lr_X, float lr_denom, float *slope_out) {
-	float err[VDL2_PREAMBLE_SYMS];
-	float unwrap = 0.f;
-	float prev = F_SUB(ph[0], pr_phase[0]);
-	float mean = prev;
-	err[0] = prev;
+/* src/demod.c:129-171: regression metric over the 16 preamble-spaced phases ph[.][0..15] (oldest first) for N
+ * independent evaluations at once.  p0[k] = squared-error sum, slope[k] = fitted phase slope (freq_err).
+ * The N evaluations share nothing; interleaving them in one instruction stream gives the N-fold instruction
+ * level parallelism a single warp per SM sub-partition needs to hide the FP32/FP64 pipeline latency.
+ * Every evaluation performs exactly the reference's operations in the reference's order. */
+template<int N>
+VDL2_HD void vdl2_metric_core_n(const float (*ph)[VDL2_PREAMBLE_SYMS], const float *pr_phase, const float *lr_X,
+		float lr_denom, float *p0_out, float *slope_out) {
+	float err[N][VDL2_PREAMBLE_SYMS];
+	float unwrap[N], prev[N], mean[N], slope[N], p0[N];
+#pragma unroll
+	for(int k = 0; k < N; k++) {
+		unwrap[k] = 0.f;
+		prev[k] = F_SUB(ph[k][0], pr_phase[0]);
+		mean[k] = prev[k];
+		err[k][0] = prev[k];
+	}
 #pragma unroll
 	for(int i = 1; i < VDL2_PREAMBLE_SYMS; i++) {
-		float cur = F_SUB(ph[i], pr_phase[i]);
-		float step = F_SUB(cur, prev);
-		prev = cur;
-		if(step >= VDL2_PI_F_ABOVE) unwrap = D_TO_F(D_SUB((double)unwrap, VDL2_TWO_PI));
-		else if(step <= -VDL2_PI_F_ABOVE) unwrap = D_TO_F(D_ADD((double)unwrap, VDL2_TWO_PI));
-		err[i] = F_ADD(cur, unwrap);
-		mean = F_ADD(mean, err[i]);
+#pragma unroll
+		for(int k = 0; k < N; k++) {
+			float cur = F_SUB(ph[k][i], pr_phase[i]);
+			float step = F_SUB(cur, prev[k]);
+			prev[k] = cur;
+			if(step >= VDL2_PI_F_ABOVE) unwrap[k] = D_TO_F(D_SUB((double)unwrap[k], VDL2_TWO_PI));
+			else if(step <= -VDL2_PI_F_ABOVE) unwrap[k] = D_TO_F(D_ADD((double)unwrap[k], VDL2_TWO_PI));
+			err[k][i] = F_ADD(cur, unwrap[k]);
+			mean[k] = F_ADD(mean[k], err[k][i]);
+		}
 	}
-	mean = F_MUL(mean, 0.0625f);               /* /= 16: exact power-of-two scaling */
-	float slope = 0.f;
+#pragma unroll
+	for(int k = 0; k < N; k++) { mean[k] = F_MUL(mean[k], 0.0625f); slope[k] = 0.f; p0[k] = 0.f; }   /* /= 16: exact */
 #pragma unroll
 	for(int i = 0; i < VDL2_PREAMBLE_SYMS; i++) {
-		err[i] = F_SUB(err[i], mean);
-		slope = F_ADD(slope, F_MUL(lr_X[i], err[i]));
+#pragma unroll
+		for(int k = 0; k < N; k++) {
+			err[k][i] = F_SUB(err[k][i], mean[k]);
+			slope[k] = F_ADD(slope[k], F_MUL(lr_X[i], err[k][i]));
+		}
 	}
-	slope = F_DIV(slope, lr_denom);
-	float p0 = 0.f;
+#pragma unroll
+	for(int k = 0; k < N; k++) slope[k] = F_DIV(slope[k], lr_denom);
 #pragma unroll
 	for(int i = 0; i < VDL2_PREAMBLE_SYMS; i++) {
-		float e = F_SUB(err[i], F_MUL(slope, lr_X[i]));
-		p0 = F_ADD(p0, F_MUL(e, e));
+#pragma unroll
+		for(int k = 0; k < N; k++) {
+			float e = F_SUB(err[k][i], F_MUL(slope[k], lr_X[i]));
+			p0[k] = F_ADD(p0[k], F_MUL(e, e));
+		}
 	}
-	*slope_out = slope;
+#pragma unroll
+	for(int k = 0; k < N; k++) { p0_out[k] = p0[k]; slope_out[k] = slope[k]; }
+}
+
+VDL2_HD float vdl2_metric_core(const float *ph, const float *pr_phase, const float *lr_X, float lr_denom, float *slope_out) {
+	float p0;
+	vdl2_metric_core_n<1>(reinterpret_cast<const float (*)[VDL2_PREAMBLE_SYMS]>(ph), pr_phase, lr_X, lr_denom, &p0, slope_out);
 	return p0;
 }
 
@@ -372,33 +399,32 @@ VDL2_HD float vdl2_mag_of(float re, float im) {
 	return D_TO_F(D_SQRT(D_ADD(D_MUL((double)re, (double)re), D_MUL((double)im, (double)im))));
 }
 
-/* src/demod.c:222-286 — one decimated sample of one channel; `phi`/`mag` = vdl2_phase_of / vdl2_mag_of of it */
-VDL2_HD void vdl2_demod_step_pm(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env,
-		uint32_t chan_idx, uint64_t dec_index, float re, float im, float phi, float mag,
-		bool pre_valid, float pre_p0, float pre_slope) {
-	if(vdl2_dec_state(v) == VDL2_DEC_IDLE) vdl2_demod_reset(v);
-	if(!(v.state & VDL2_ST_LOCKED)) {
-		v.ring_pos = (v.ring_pos + 1 == VDL2_SYNC_BUFLEN) ? 0 : v.ring_pos + 1;
-		ring[v.ring_pos * rs] = phi;
-		if(v.pure_run < VDL2_PURE_SATURATED) v.pure_run++;
-		if(++v.sclk < VDL2_SYNC_SKIP) return;
-		v.sclk = 0;
-		const float one_minus_mag_lp = 1.0f - 0.9f, one_minus_nf_lp = 1.0f - 0.85f;
-		v.mag_lp = F_ADD(F_MUL(v.mag_lp, 0.9f), F_MUL(mag, one_minus_mag_lp));
-		if(++v.nfcnt == 1000) {
-			v.nfcnt = 0;
-			v.mag_nf = F_ADD(F_ADD(F_MUL(0.85f, v.mag_nf), F_MUL(one_minus_nf_lp, fminf(v.mag_lp, v.mag_nf))), 0.0001f);
-		}
-		if(vdl2_preamble_metric(v, ring, rs, env, chan_idx, dec_index,
-				pre_valid && v.pure_run >= VDL2_PURE_NEEDED, pre_p0, pre_slope)) {
-			v.cnt_sync++;
-			v.sync_dec_index = dec_index;
-			v.state |= VDL2_ST_LOCKED;
-		}
-		return;
+/* DM_INIT, every sample: src/demod.c:231-232 */
+VDL2_HD void vdl2_init_write(vdl2_chan &v, float *ring, int rs, float phi) {
+	v.ring_pos = (v.ring_pos + 1 == VDL2_SYNC_BUFLEN) ? 0 : v.ring_pos + 1;
+	ring[v.ring_pos * rs] = phi;
+	if(v.pure_run < VDL2_PURE_SATURATED) v.pure_run++;
+}
+
+/* DM_INIT, every SYNC_SKIP-th sample: noise floor + sync attempt, src/demod.c:236-249 */
+VDL2_HD void vdl2_init_eval(vdl2_chan &v, const float *ring, int rs, const vdl2_k2_env &env, uint32_t chan_idx,
+		uint64_t dec_index, float mag, bool have_pre, float pre_p0, float pre_slope) {
+	const float one_minus_mag_lp = 1.0f - 0.9f, one_minus_nf_lp = 1.0f - 0.85f;
+	v.mag_lp = F_ADD(F_MUL(v.mag_lp, 0.9f), F_MUL(mag, one_minus_mag_lp));
+	if(++v.nfcnt == 1000) {
+		v.nfcnt = 0;
+		v.mag_nf = F_ADD(F_ADD(F_MUL(0.85f, v.mag_nf), F_MUL(one_minus_nf_lp, fminf(v.mag_lp, v.mag_nf))), 0.0001f);
 	}
-	if(++v.sclk < VDL2_SPS) return;
-	v.sclk = 0;
+	if(vdl2_preamble_metric(v, ring, rs, env, chan_idx, dec_index, have_pre, pre_p0, pre_slope)) {
+		v.cnt_sync++;
+		v.sync_dec_index = dec_index;
+		v.state |= VDL2_ST_LOCKED;
+	}
+}
+
+/* DM_SYNC, every SPS-th sample: one D8PSK symbol, src/demod.c:256-283 */
+VDL2_HD void vdl2_symbol(vdl2_chan &v, const vdl2_k2_env &env, uint32_t chan_idx, uint64_t dec_index,
+		float re, float im, float phi) {
 	float dphi = F_SUB(F_SUB(phi, v.prev_phi), v.dphi);
 	if(dphi < 0.f) dphi = D_TO_F(D_ADD((double)dphi, VDL2_TWO_PI));
 	else if(dphi >= VDL2_TWO_PI_F_ABOVE) dphi = D_TO_F(D_SUB((double)dphi, VDL2_TWO_PI));
@@ -419,6 +445,88 @@ VDL2_HD void vdl2_demod_step_pm(vdl2_chan &v, float *ring, int rs, const vdl2_k2
 	if(v.nbits >= v.need_bits) {
 		if(vdl2_dec_state(v) == VDL2_DEC_HEADER) vdl2_header_step(v, env, chan_idx, dec_index);
 		else if(vdl2_dec_state(v) == VDL2_DEC_DATA) vdl2_burst_complete(v, env, chan_idx);
+	}
+}
+
+/* src/demod.c:222-286 — one decimated sample of one channel; `phi`/`mag` = vdl2_phase_of / vdl2_mag_of of it */
+VDL2_HD void vdl2_demod_step_pm(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env,
+		uint32_t chan_idx, uint64_t dec_index, float re, float im, float phi, float mag,
+		bool pre_valid, float pre_p0, float pre_slope) {
+	if(vdl2_dec_state(v) == VDL2_DEC_IDLE) vdl2_demod_reset(v);
+	if(!(v.state & VDL2_ST_LOCKED)) {
+		vdl2_init_write(v, ring, rs, phi);
+		if(++v.sclk < VDL2_SYNC_SKIP) return;
+		v.sclk = 0;
+		vdl2_init_eval(v, ring, rs, env, chan_idx, dec_index, mag, pre_valid && v.pure_run >= VDL2_PURE_NEEDED, pre_p0, pre_slope);
+		return;
+	}
+	if(++v.sclk < VDL2_SPS) return;
+	v.sclk = 0;
+	vdl2_symbol(v, env, chan_idx, dec_index, re, im, phi);
+}
+
+/* K2 walks the chunk in blocks of VDL2_WALK_BLOCK decimated samples per channel.  `dec`, `phase`, `mag` point at
+ * this channel's entry for the first sample of the block; consecutive samples are `stride` elements apart and
+ * phase[-k*stride] is valid for k <= 160 (history prefix).  Three paths, chosen per channel:
+ *   fast    searching (DM_INIT) with a pure phase ring: the four sync attempts that fall into the block are
+ *           evaluated together (vdl2_metric_core_n<4>) from the phase plane, then the twelve samples are applied;
+ *   locked  in a burst (DM_SYNC): only the one or two symbol instants of the block are touched;
+ *   generic anything else (the 150 samples after a reset, the sample after a burst): the per-sample step.
+ * All three produce exactly what twelve calls of vdl2_demod_step_pm would. */
+#define VDL2_WALK_BLOCK 12
+VDL2_HD void vdl2_walk_block(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env, uint32_t chan_idx, uint64_t idx0,
+		const float2 *dec, const float *phase, const float *mag, size_t stride) {
+	int resume = 0;
+	if(!(v.state & VDL2_ST_LOCKED) && vdl2_dec_state(v) != VDL2_DEC_IDLE && v.pure_run >= VDL2_PURE_NEEDED) {
+		const int first = (VDL2_SYNC_SKIP - 1) - v.sclk;                  /* offset of the first attempt in the block */
+		float ph[4][VDL2_PREAMBLE_SYMS], p0[4], sl[4], mg[4], pw[VDL2_WALK_BLOCK];
+#pragma unroll
+		for(int j = 0; j < 4; j++) {
+			const ptrdiff_t e = (ptrdiff_t)(first + VDL2_SYNC_SKIP * j);
+#pragma unroll
+			for(int i = 0; i < VDL2_PREAMBLE_SYMS; i++)
+				ph[j][i] = VDL2_LDG(phase + (e - 150 + 10 * i) * (ptrdiff_t)stride);
+			mg[j] = VDL2_LDG(mag + e * (ptrdiff_t)stride);
+		}
+#pragma unroll
+		for(int t = 0; t < VDL2_WALK_BLOCK; t++) pw[t] = VDL2_LDG(phase + (ptrdiff_t)t * (ptrdiff_t)stride);
+		vdl2_metric_core_n<4>(ph, env.pr_phase, env.lr_X, env.lr_denom, p0, sl);
+		int j = 0;
+		bool go = true;
+#pragma unroll
+		for(int t = 0; t < VDL2_WALK_BLOCK; t++) {
+			if(go) {
+				vdl2_init_write(v, ring, rs, pw[t]);
+				if(++v.sclk == VDL2_SYNC_SKIP) {
+					v.sclk = 0;
+					const float pj = j == 0 ? p0[0] : j == 1 ? p0[1] : j == 2 ? p0[2] : p0[3];
+					const float sj = j == 0 ? sl[0] : j == 1 ? sl[1] : j == 2 ? sl[2] : sl[3];
+					const float mj = j == 0 ? mg[0] : j == 1 ? mg[1] : j == 2 ? mg[2] : mg[3];
+					j++;
+					vdl2_init_eval(v, ring, rs, env, chan_idx, idx0 + (uint64_t)t, mj, true, pj, sj);
+					if(v.state & VDL2_ST_LOCKED) { go = false; resume = t + 1; }
+				}
+			}
+		}
+		if(go) resume = VDL2_WALK_BLOCK;
+	}
+	int t = resume;
+	while(t < VDL2_WALK_BLOCK) {
+		if((v.state & VDL2_ST_LOCKED) && vdl2_dec_state(v) != VDL2_DEC_IDLE) {
+			const int tsym = t + (VDL2_SPS - 1) - v.sclk;                  /* sample on which ++sclk reaches SPS */
+			if(tsym >= VDL2_WALK_BLOCK) { v.sclk += VDL2_WALK_BLOCK - t; break; }
+			const float2 d = VDL2_LDG(dec + (ptrdiff_t)tsym * (ptrdiff_t)stride);
+			const float phi = VDL2_LDG(phase + (ptrdiff_t)tsym * (ptrdiff_t)stride);
+			v.sclk = 0;
+			vdl2_symbol(v, env, chan_idx, idx0 + (uint64_t)tsym, d.x, d.y, phi);
+			t = tsym + 1;
+		} else {
+			const float2 d = VDL2_LDG(dec + (ptrdiff_t)t * (ptrdiff_t)stride);
+			const float phi = VDL2_LDG(phase + (ptrdiff_t)t * (ptrdiff_t)stride);
+			const float mgt = VDL2_LDG(mag + (ptrdiff_t)t * (ptrdiff_t)stride);
+			vdl2_demod_step_pm(v, ring, rs, env, chan_idx, idx0 + (uint64_t)t, d.x, d.y, phi, mgt, false, 0.f, 0.f);
+			t++;
+		}
 	}
 }
 

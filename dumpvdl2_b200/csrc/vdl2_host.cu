@@ -67,7 +67,7 @@ struct vdl2gpu_ctx {
 	host_tables tab;
 	vdl2_tables *d_tab = nullptr;
 	float4 *d_samples = nullptr;
-	float2 *d_dec2[2] = { nullptr, nullptr }, *d_metric = nullptr;
+	float2 *d_dec2[2] = { nullptr, nullptr };
 	float *d_phase = nullptr, *d_mag = nullptr, *d_hist_tmp = nullptr;
 	uint32_t *d_k1 = nullptr, *d_k2 = nullptr, *d_counters = nullptr, *d_ready = nullptr;
 	float *d_ring = nullptr;
@@ -129,7 +129,7 @@ static int free_ctx(vdl2gpu_ctx *c) {
 		if(s.done) cudaEventDestroy(s.done);
 		for(auto &e : s.tk) if(e) cudaEventDestroy(e);
 	}
-	cudaFree(c->d_tab); cudaFree(c->d_samples); cudaFree(c->d_dec2[0]); cudaFree(c->d_dec2[1]); cudaFree(c->d_metric); cudaFree(c->d_phase); cudaFree(c->d_mag); cudaFree(c->d_hist_tmp); cudaFree(c->d_k1); cudaFree(c->d_k2);
+	cudaFree(c->d_tab); cudaFree(c->d_samples); cudaFree(c->d_dec2[0]); cudaFree(c->d_dec2[1]); cudaFree(c->d_phase); cudaFree(c->d_mag); cudaFree(c->d_hist_tmp); cudaFree(c->d_k1); cudaFree(c->d_k2);
 	cudaFree(c->d_counters); cudaFree(c->d_ready); cudaFree(c->d_ring); cudaFree(c->d_pool); cudaFree(c->d_free);
 	cudaFree(c->d_ctl); cudaFree(c->d_events);
 	if(c->ev_input_ready) cudaEventDestroy(c->ev_input_ready);
@@ -193,7 +193,6 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 		CU(cudaMalloc(&c->d_dec2[i], (size_t)c->max_dec * c->n_chp * sizeof(float2)));
 		CU(cudaMemset(c->d_dec2[i], 0, (size_t)c->max_dec * c->n_chp * sizeof(float2)));
 	}
-	CU(cudaMalloc(&c->d_metric, (size_t)c->max_dec * c->n_chp * sizeof(float2)));
 	CU(cudaMalloc(&c->d_phase, (size_t)(c->max_dec + VDL2_SYNC_BUFLEN) * c->n_chp * sizeof(float)));
 	CU(cudaMemset(c->d_phase, 0, (size_t)(c->max_dec + VDL2_SYNC_BUFLEN) * c->n_chp * sizeof(float)));
 	CU(cudaMalloc(&c->d_mag, (size_t)c->max_dec * c->n_chp * sizeof(float)));
@@ -406,7 +405,7 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	CU(cudaStreamWaitEvent(c->s_back, c->ev_k1_done[db], 0));
 	if(s.timed) CU(cudaEventRecord(s.tk[3], c->s_back));
 	vdl2_k2_params p2;
-	p2.dec = d_dec; p2.phase = c->d_phase; p2.mag = c->d_mag; p2.metric = c->d_metric; p2.hist_tmp = c->d_hist_tmp; p2.n_dec = s.n_dec; p2.n_ch = c->n_ch; p2.n_chp = c->n_chp; p2.dec_base = s.dec_base;
+	p2.dec = d_dec; p2.phase = c->d_phase; p2.mag = c->d_mag; p2.hist_tmp = c->d_hist_tmp; p2.n_dec = s.n_dec; p2.n_ch = c->n_ch; p2.n_chp = c->n_chp; p2.dec_base = s.dec_base;
 	p2.state = c->d_k2; p2.ring = c->d_ring; p2.tables = c->d_tab; p2.max_ppm = c->cfg.max_ppm; p2.s27 = c->tab.s27;
 	p2.pool = c->d_pool; p2.free_list = c->d_free; p2.ready = c->d_ready; p2.ctl = c->d_ctl;
 	p2.events = c->d_events; p2.event_cap = c->event_cap; p2.trace = (c->cfg.flags & VDL2GPU_FLAG_TRACE) ? 1u : 0u;
@@ -430,7 +429,7 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	c->stats.chunks_submitted++;
 	c->stats.iq_samples += n_pairs;
 	c->stats.dec_samples += s.n_dec;
-	c->stats.kernel_launches += (n_pairs ? 2 : 0) + (s.n_dec ? (s.n_dec >= VDL2_SYNC_BUFLEN ? 4 : 5) : 0) + 2;
+	c->stats.kernel_launches += (n_pairs ? 2 : 0) + (s.n_dec ? (s.n_dec >= VDL2_SYNC_BUFLEN ? 3 : 4) : 0) + 2;
 	return VDL2GPU_OK;
 }
 

@@ -289,36 +289,13 @@ __global__ void __launch_bounds__(256) k2a_phase_mag(const float2 *__restrict__ 
 	mag[i] = vdl2_mag_of(d.x, d.y);
 }
 
-/* K2b: the preamble regression metric of got_sync (src/demod.c:129-171) for EVERY decimated sample of the
- * chunk, one thread per (time, channel).  At sample n it reads the phases of samples n-150, n-140, ..., n
- * (`phase` carries a 160-row history prefix).  The sequential walker K2 uses the result wherever its own phase
- * ring is known to hold exactly those samples (>= 151 samples since the last demod_reset) and recomputes from
- * its ring otherwise, so results do not depend on this pre-pass. */
-__global__ void __launch_bounds__(128) k2b_sync_metric(const float *__restrict__ phase, float2 *__restrict__ metric,
-		const vdl2_tables *__restrict__ tables, uint32_t n_dec, uint32_t n_chp) {
-	__shared__ float s_consts[33];
-	if(threadIdx.x < 16) { s_consts[threadIdx.x] = tables->pr_phase[threadIdx.x]; s_consts[16 + threadIdx.x] = tables->lr_X[threadIdx.x]; }
-	if(threadIdx.x == 0) s_consts[32] = tables->lr_denom;
-	__syncthreads();
-	const uint32_t ch = blockIdx.x * 128u + threadIdx.x;
-	const uint32_t m = blockIdx.y;
-	if(ch >= n_chp || m >= n_dec) return;
-	float ph[VDL2_PREAMBLE_SYMS];
-#pragma unroll
-	for(int i = 0; i < VDL2_PREAMBLE_SYMS; i++)
-		ph[i] = __ldg(&phase[(size_t)(m + 10u + 10u * (uint32_t)i) * n_chp + ch]);     /* row m+160 is sample m */
-	float slope;
-	const float p0 = vdl2_metric_core(ph, s_consts, s_consts + 16, s_consts[32], &slope);
-	metric[(size_t)m * n_chp + ch] = make_float2(p0, slope);
-}
-
 /* carry the last 160 phase rows over to the front of the plane for the next chunk */
 __global__ void __launch_bounds__(256) k_copy_rows(const float *__restrict__ src, float *__restrict__ dst, uint32_t n) {
 	uint32_t i = blockIdx.x * 256u + threadIdx.x;
 	if(i < n) dst[i] = src[i];
 }
 
-template<int BLOCK>
+template<int BLOCK, bool BLOCKED>
 __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	__shared__ float s_ring[VDL2_SYNC_BUFLEN * BLOCK];
 	__shared__ float s_consts[33];
@@ -358,28 +335,22 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	env.cnt_bursts = nullptr;
 
 	const float2 *dec = p.dec + ch;
-	const float *phs = p.phase + (size_t)VDL2_SYNC_BUFLEN * s + ch;
+	const float *phs = p.phase + (size_t)VDL2_SYNC_BUFLEN * s + ch;      /* row 0 of phs = first sample of this chunk */
 	const float *mgs = p.mag + ch;
-	const float2 *met = p.metric + ch;
-	/* register-resident prefetch, two samples per trip: the replacements for both are requested before the
-	 * dependent work on the current pair and only moved into place after it */
-	struct smp { float2 d; float ph, mg; float2 mt; };
-	auto fetch = [&](uint32_t m) { smp r; const size_t o = (size_t)m * s; r.d = __ldg(&dec[o]); r.ph = __ldg(&phs[o]); r.mg = __ldg(&mgs[o]); r.mt = __ldg(&met[o]); return r; };
-	smp a, b;
-	a.d = make_float2(0.f, 0.f); a.ph = a.mg = 0.f; a.mt = a.d; b = a;
-	if(p.n_dec > 0) a = fetch(0);
-	if(p.n_dec > 1) b = fetch(1);
 	uint32_t m = 0;
+	if(BLOCKED) {
 #pragma unroll 1
-	for(; m + 2 <= p.n_dec; m += 2) {
-		smp na = a, nb = b;
-		if(m + 2 < p.n_dec) na = fetch(m + 2);
-		if(m + 3 < p.n_dec) nb = fetch(m + 3);
-		vdl2_demod_step_pm(v, ring, BLOCK, env, ch, p.dec_base + m, a.d.x, a.d.y, a.ph, a.mg, true, a.mt.x, a.mt.y);
-		vdl2_demod_step_pm(v, ring, BLOCK, env, ch, p.dec_base + m + 1, b.d.x, b.d.y, b.ph, b.mg, true, b.mt.x, b.mt.y);
-		a = na; b = nb;
+		for(; m + VDL2_WALK_BLOCK <= p.n_dec; m += VDL2_WALK_BLOCK) {
+			const size_t o = (size_t)m * s;
+			vdl2_walk_block(v, ring, BLOCK, env, ch, p.dec_base + m, dec + o, phs + o, mgs + o, s);
+		}
 	}
-	if(m < p.n_dec) vdl2_demod_step_pm(v, ring, BLOCK, env, ch, p.dec_base + m, a.d.x, a.d.y, a.ph, a.mg, true, a.mt.x, a.mt.y);
+#pragma unroll 1
+	for(; m < p.n_dec; m++) {
+		const size_t o = (size_t)m * s;
+		const float2 d = __ldg(&dec[o]);
+		vdl2_demod_step_pm(v, ring, BLOCK, env, ch, p.dec_base + m, d.x, d.y, __ldg(&phs[o]), __ldg(&mgs[o]), false, 0.f, 0.f);
+	}
 
 	for(int i = 0; i < VDL2_SYNC_BUFLEN; i++) p.ring[(size_t)i * s + ch] = ring[i * BLOCK];
 	st[K2_PREV_PHI * s + ch] = __float_as_uint(v.prev_phi); st[K2_PREV_DPHI * s + ch] = __float_as_uint(v.prev_dphi);
@@ -570,10 +541,10 @@ extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
 	k2a_phase_mag<<<(n_elems + 255u) / 256u, 256, 0, st>>>(p->dec, p->phase + hist, p->mag, n_elems);
 	int e = (int)cudaGetLastError();
 	if(e) return e;
-	k2b_sync_metric<<<dim3((p->n_chp + 127u) / 128u, p->n_dec), 128, 0, st>>>(p->phase, p->metric, p->tables, p->n_dec, p->n_chp);
-	e = (int)cudaGetLastError();
-	if(e) return e;
-	k2_sync_slice<K2_BLOCK><<<blocks, K2_BLOCK, 0, st>>>(*p);
+	static int variant = -1;
+	if(variant < 0) { const char *ev = getenv("VDL2GPU_K2_VARIANT"); variant = ev ? atoi(ev) : 1; }
+	if(variant == 0) k2_sync_slice<K2_BLOCK, false><<<blocks, K2_BLOCK, 0, st>>>(*p);
+	else k2_sync_slice<K2_BLOCK, true><<<blocks, K2_BLOCK, 0, st>>>(*p);
 	e = (int)cudaGetLastError();
 	if(e) return e;
 	/* history for the next chunk: rows [n_dec, n_dec+160) -> [0, 160) */

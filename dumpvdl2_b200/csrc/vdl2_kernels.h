@@ -22,7 +22,6 @@ typedef struct {
 	const float2 *dec;
 	float *phase;                /* [160 + n_dec][n_chp]: rows 0..159 = last 160 phases of the previous chunks */
 	float *mag;                  /* [n_dec][n_chp] */
-	float2 *metric;              /* [n_dec][n_chp] {pherr, slope} from K2b */
 	float *hist_tmp;             /* [160][n_chp] scratch for the history shift of short chunks */
 	uint32_t n_dec;
 	uint32_t n_ch, n_chp;

@@ -6,10 +6,9 @@
  *   samples   float2[max_pairs]            K0 -> K1   converted stream (src/demod.c:339-365)
  *   dec       float2[max_dec][n_chp]       K1 -> K2   decimated samples, TIME-MAJOR: a warp of 32 channels
  *                                                     reads/writes 256 contiguous bytes per time step
- *   phase     float[160+max_dec][n_chp]    K2a -> K2b,K2   atan2 of every decimated sample; the first 160 rows carry the
+ *   phase     float[160+max_dec][n_chp]    K2a -> K2  atan2 of every decimated sample; the first 160 rows carry the
  *                                                     tail of the previous chunk (the preamble metric looks 150 back)
  *   mag       float[max_dec][n_chp]        K2a -> K2  hypot of every decimated sample
- *   metric    float2[max_dec][n_chp]       K2b -> K2  {squared-error sum, slope} of the preamble regression at every sample
  *   k1 state  u32[K1_NFIELDS][n_chp]       SoA        filter delay lines + NCO (src/demod.c:289-298)
  *   k2 state  u32[K2_NFIELDS][n_chp]       SoA        demodulator/decoder scalars (src/dumpvdl2.h:321-352)
  *   ring      float[160][n_chp]                       syncbuf phase ring (src/dumpvdl2.h:324)

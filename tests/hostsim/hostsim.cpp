@@ -9,6 +9,10 @@
 #include <string.h>
 #include <vector>
 #include "vdl2_tables_host.h"
+#ifndef __CUDACC__
+struct float2 { float x, y; };
+#endif
+typedef float2 float2x;
 #include "vdl2_core.cuh"
 
 extern "C" {
@@ -80,30 +84,33 @@ int hostsim_k2k3(const float *dec /*[n_dec][n_ch][2]*/, uint32_t n_dec, uint32_t
 	vdl2_burst_work *w = new vdl2_burst_work();
 	/* the kernels process chunk by chunk: K2 over all channels, then K3 over the ready list; mimic with
 	 * chunks of 1024 decimated samples so that slot recycling is exercised */
-	/* K2a + K2b emulation: phase plane with a 160-row zero history, metric for every sample */
-	std::vector<float> phase((size_t)(n_dec + VDL2_SYNC_BUFLEN) * n_ch, 0.f), mag((size_t)n_dec * n_ch), met((size_t)n_dec * n_ch * 2);
+	/* K2a emulation: phase plane with a 160-row zero history, magnitude plane */
+	std::vector<float> phase((size_t)(n_dec + VDL2_SYNC_BUFLEN) * n_ch, 0.f), mag((size_t)n_dec * n_ch);
 	for(uint32_t m = 0; m < n_dec; m++)
 		for(uint32_t ch = 0; ch < n_ch; ch++) {
 			const float *d = &dec[((size_t)m * n_ch + ch) * 2];
 			phase[(size_t)(m + VDL2_SYNC_BUFLEN) * n_ch + ch] = vdl2_phase_of(d[0], d[1]);
 			mag[(size_t)m * n_ch + ch] = vdl2_mag_of(d[0], d[1]);
 		}
-	for(uint32_t m = 0; m < n_dec; m++)
-		for(uint32_t ch = 0; ch < n_ch; ch++) {
-			float ph[VDL2_PREAMBLE_SYMS], slope;
-			for(int i = 0; i < VDL2_PREAMBLE_SYMS; i++) ph[i] = phase[(size_t)(m + 10 + 10 * i) * n_ch + ch];
-			met[((size_t)m * n_ch + ch) * 2] = vdl2_metric_core(ph, h->t.pr_phase, h->t.lr_X, h->t.lr_denom, &slope);
-			met[((size_t)m * n_ch + ch) * 2 + 1] = slope;
-		}
+	const float2x *dec2 = reinterpret_cast<const float2x *>(dec);
 	for(uint32_t base = 0; base < n_dec; base += 1024) {
 		uint32_t n = n_dec - base < 1024 ? n_dec - base : 1024;
-		for(uint32_t ch = 0; ch < n_ch; ch++)
-			for(uint32_t m = 0; m < n; m++) {
+		for(uint32_t ch = 0; ch < n_ch; ch++) {
+			uint32_t m = 0;
+			if(use_pre) {                     /* the kernel's blocked walk */
+				for(; m + VDL2_WALK_BLOCK <= n; m += VDL2_WALK_BLOCK) {
+					const size_t o = (size_t)(base + m) * n_ch + ch;
+					vdl2_walk_block(chans[ch], &rings[(size_t)ch * VDL2_SYNC_BUFLEN], 1, env, ch, base + m,
+							reinterpret_cast<const float2 *>(dec2 + o), &phase[o + (size_t)VDL2_SYNC_BUFLEN * n_ch], &mag[o], n_ch);
+				}
+			}
+			for(; m < n; m++) {
 				const size_t o = (size_t)(base + m) * n_ch + ch;
 				const float *d = &dec[o * 2];
 				vdl2_demod_step_pm(chans[ch], &rings[(size_t)ch * VDL2_SYNC_BUFLEN], 1, env, ch, base + m, d[0], d[1],
-						phase[o + (size_t)VDL2_SYNC_BUFLEN * n_ch], mag[o], use_pre != 0, met[o * 2], met[o * 2 + 1]);
+						phase[o + (size_t)VDL2_SYNC_BUFLEN * n_ch], mag[o], false, 0.f, 0.f);
 			}
+		}
 		for(uint32_t b = 0; b < ctl.n_ready; b++) {
 			const vdl2_burst_slot *slot = &pool[ready[b]];
 			vdl2_burst_geometry(*w, slot->datalen_bits, slot->nbits);
