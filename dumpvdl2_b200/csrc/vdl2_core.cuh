@@ -202,6 +202,23 @@ VDL2_HD float vdl2_para_vertex(float x, float y1, float y2, float y3) {
 	return F_DIV(-qb, F_MUL(2.f, qa));
 }
 
+/* src/demod.c:137-141: `unwrap -= 2.0f * M_PI` / `unwrap += 2.0f * M_PI` — double arithmetic narrowed to float on
+ * store: unwrap' = fl32((double)unwrap -/+ 2pi_d).  The same value is obtained here in FP32 only, branch-free:
+ * with 2pi_d = H + L (H = fl32(2pi_d), L = fl32(2pi_d - H)) and (s, e) = TwoSum(unwrap, sg*H) exactly,
+ * unwrap' = fl32(s + fl32(e + sg*L)).  unwrap can only take the 77 values reachable from 0 in at most 15 steps of
+ * +-2pi; the identity holds for every one of their 138 transitions (tests/test_hostsim.py enumerates them), and
+ * for sg == 0 it returns unwrap unchanged.  No double-precision conversions, no divergent branch. */
+#define VDL2_TWO_PI_HI 6.28318548202514648f      /* fl32(2*M_PI) */
+#define VDL2_TWO_PI_LO -1.74845553146951715e-7f  /* fl32(2*M_PI - VDL2_TWO_PI_HI) */
+VDL2_HD float vdl2_unwrap_step(float unwrap, float step) {
+	const float sg = (step >= VDL2_PI_F_ABOVE) ? -1.f : ((step <= -VDL2_PI_F_ABOVE) ? 1.f : 0.f);
+	const float b = F_MUL(sg, VDL2_TWO_PI_HI);
+	const float s = F_ADD(unwrap, b);
+	const float bb = F_SUB(s, unwrap);
+	const float e = F_ADD(F_SUB(unwrap, F_SUB(s, bb)), F_SUB(b, bb));
+	return F_ADD(s, F_ADD(e, F_MUL(sg, VDL2_TWO_PI_LO)));
+}
+
 /* src/demod.c:129-171: regression metric over the 16 preamble-spaced phases ph[.][0..15] (oldest first) for N
  * independent evaluations at once.  p0[k] = squared-error sum, slope[k] = fitted phase slope (freq_err).
  * The N evaluations share nothing; interleaving them in one instruction stream gives the N-fold instruction
@@ -226,8 +243,7 @@ VDL2_HD void vdl2_metric_core_n(const float (*ph)[VDL2_PREAMBLE_SYMS], const flo
 			float cur = F_SUB(ph[k][i], pr_phase[i]);
 			float step = F_SUB(cur, prev[k]);
 			prev[k] = cur;
-			if(step >= VDL2_PI_F_ABOVE) unwrap[k] = D_TO_F(D_SUB((double)unwrap[k], VDL2_TWO_PI));
-			else if(step <= -VDL2_PI_F_ABOVE) unwrap[k] = D_TO_F(D_ADD((double)unwrap[k], VDL2_TWO_PI));
+			unwrap[k] = vdl2_unwrap_step(unwrap[k], step);
 			err[k][i] = F_ADD(cur, unwrap[k]);
 			mean[k] = F_ADD(mean[k], err[k][i]);
 		}
@@ -491,20 +507,26 @@ VDL2_HD void vdl2_walk_block(vdl2_chan &v, float *ring, int rs, const vdl2_k2_en
 #pragma unroll
 		for(int t = 0; t < VDL2_WALK_BLOCK; t++) pw[t] = VDL2_LDG(phase + (ptrdiff_t)t * (ptrdiff_t)stride);
 		vdl2_metric_core_n<4>(ph, env.pr_phase, env.lr_X, env.lr_denom, p0, sl);
-		int j = 0;
+		/* the block is four groups of SYNC_SKIP samples; in each the attempt falls on local offset `first`,
+		 * and the sample clock is back at its entry value at every group boundary */
+		const int sclk_entry = v.sclk;
 		bool go = true;
 #pragma unroll
-		for(int t = 0; t < VDL2_WALK_BLOCK; t++) {
+		for(int g = 0; g < 4; g++) {
 			if(go) {
-				vdl2_init_write(v, ring, rs, pw[t]);
-				if(++v.sclk == VDL2_SYNC_SKIP) {
-					v.sclk = 0;
-					const float pj = j == 0 ? p0[0] : j == 1 ? p0[1] : j == 2 ? p0[2] : p0[3];
-					const float sj = j == 0 ? sl[0] : j == 1 ? sl[1] : j == 2 ? sl[2] : sl[3];
-					const float mj = j == 0 ? mg[0] : j == 1 ? mg[1] : j == 2 ? mg[2] : mg[3];
-					j++;
-					vdl2_init_eval(v, ring, rs, env, chan_idx, idx0 + (uint64_t)t, mj, true, pj, sj);
-					if(v.state & VDL2_ST_LOCKED) { go = false; resume = t + 1; }
+#pragma unroll
+				for(int u = 0; u < VDL2_SYNC_SKIP; u++)
+					if(u <= first) vdl2_init_write(v, ring, rs, pw[VDL2_SYNC_SKIP * g + u]);
+				v.sclk = 0;
+				vdl2_init_eval(v, ring, rs, env, chan_idx, idx0 + (uint64_t)(VDL2_SYNC_SKIP * g + first), mg[g], true, p0[g], sl[g]);
+				if(v.state & VDL2_ST_LOCKED) {
+					go = false;
+					resume = VDL2_SYNC_SKIP * g + first + 1;
+				} else {
+#pragma unroll
+					for(int u = 0; u < VDL2_SYNC_SKIP; u++)
+						if(u > first) vdl2_init_write(v, ring, rs, pw[VDL2_SYNC_SKIP * g + u]);
+					v.sclk = sclk_entry;
 				}
 			}
 		}

@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	v.cnt_sync = st[K2_CNT_SYNC * s + ch]; v.cnt_hdr_good = st[K2_CNT_HDR_GOOD * s + ch];
 	v.pure_run = st[K2_PURE_RUN * s + ch];
 	float *ring = &s_ring[tid];
+#pragma unroll 4
 	for(int i = 0; i < VDL2_SYNC_BUFLEN; i++) ring[i * BLOCK] = p.ring[(size_t)i * s + ch];
 
 	vdl2_k2_env env;
@@ -352,6 +353,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 		vdl2_demod_step_pm(v, ring, BLOCK, env, ch, p.dec_base + m, d.x, d.y, __ldg(&phs[o]), __ldg(&mgs[o]), false, 0.f, 0.f);
 	}
 
+#pragma unroll 4
 	for(int i = 0; i < VDL2_SYNC_BUFLEN; i++) p.ring[(size_t)i * s + ch] = ring[i * BLOCK];
 	st[K2_PREV_PHI * s + ch] = __float_as_uint(v.prev_phi); st[K2_PREV_DPHI * s + ch] = __float_as_uint(v.prev_dphi);
 	st[K2_DPHI * s + ch] = __float_as_uint(v.dphi); st[K2_PHERR0 * s + ch] = __float_as_uint(v.pherr0);

@@ -170,6 +170,7 @@ uint32_t hostsim_header_fix(uint32_t word, uint32_t *syndrome) {
 	return word ^ vdl2_header_error_pattern(s);
 }
 uint32_t hostsim_synd_weight(uint32_t s) { return vdl2_synd_weight(s); }
+float hostsim_unwrap_step(float unwrap, float step) { return vdl2_unwrap_step(unwrap, step); }
 uint16_t hostsim_crc16(const uint8_t *p, uint32_t n) { return vdl2_crc16(p, n); }
 void hostsim_tables(uint32_t rate, float *levels, float *sin_lut, float *cos_lut, float *A, float *B, float *lr_X, float *lr_denom, float *pr_phase) {
 	host_tables *h = new host_tables();

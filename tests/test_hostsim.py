@@ -96,3 +96,33 @@ def test_library_tables_match_oracle():
         assert d[0] == od
         # the pipelined K1 relies on nothing about A; but document the structure the strict design has
         assert A[1] == 2 * A[0] and A[2] == A[0]
+
+
+def test_fp32_unwrap_update_equals_the_double_arithmetic_of_the_reference():
+    """src/demod.c:137-141 updates `unwrap` in double and narrows; the kernels use an FP32-only TwoSum form.
+    Enumerate every value `unwrap` can take (<= 15 steps of +-2pi from 0) and check all transitions."""
+    import ctypes as C
+    L = hs.lib()
+    L.hostsim_unwrap_step.restype = C.c_float
+    L.hostsim_unwrap_step.argtypes = [C.c_float, C.c_float]
+    two_pi = np.float64(2.0) * np.float64(np.pi)
+    frontier, seen, n = {np.float32(0).tobytes()}, {np.float32(0).tobytes()}, 0
+    for depth in range(15):
+        nxt = set()
+        for b in frontier:
+            u = np.frombuffer(b, np.float32)[0]
+            assert L.hostsim_unwrap_step(u, np.float32(0.5)) == u          # no jump: unchanged
+            for step, sign in ((np.float32(3.2), -1.0), (np.float32(-3.2), 1.0)):   # step > pi: -2pi ; step < -pi: +2pi
+                want = np.float32(np.float64(u) + sign * two_pi)
+                got = np.float32(L.hostsim_unwrap_step(u, step))
+                assert got.tobytes() == want.tobytes(), (u, sign, got, want)
+                nxt.add(want.tobytes()); n += 1
+        frontier = nxt - seen
+        seen |= nxt
+    assert len(seen) == 77 and n == 138
+    # the jump thresholds: `errdiff > M_PI` with errdiff float, M_PI double
+    for x in (np.float32(np.pi), np.nextafter(np.float32(np.pi), np.float32(0)), np.nextafter(np.float32(np.pi), np.float32(4))):
+        jumped = L.hostsim_unwrap_step(np.float32(0), x) != 0
+        assert jumped == (np.float64(x) > np.pi)
+        jumped = L.hostsim_unwrap_step(np.float32(0), -x) != 0
+        assert jumped == (np.float64(-x) < -np.pi)
