@@ -180,6 +180,11 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # keep stdout clean for the single JSON line: libraries (NCCL prints its version banner there) write to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import dumpvdl2_b200 as vd
@@ -201,12 +206,13 @@ def main():
     g = vd.Vdl2Channels(FS, OVERSAMPLE, vd.FMT_U8, CENTER, my_freqs, max_chunk_bytes=CHUNK_BYTES, device=local_rank, flags=flags)
     stream = torch.cuda.current_stream()
 
-    # chunks resident in HBM (rank 0 is the ingest rank; others receive into a small rotating set of buffers)
+    # chunks resident in HBM on the ingest rank (rank 0).  With N > 1 every step's CPS chunks are broadcast in ONE
+    # NCCL call (bucket sized for launch latency: 4 MiB instead of 8 x 0.5 MiB) into a double-buffered receive
+    # area, then each rank demodulates its channel shard straight out of that buffer.
     if rank == 0:
         d_chunks = torch.from_numpy(chunks).cuda()
-    NB = 4
-    d_recv = [torch.empty(CHUNK_BYTES, dtype=torch.uint8, device="cuda") for _ in range(NB)]
-    h_chunks = [torch.from_numpy(chunks[i]).pin_memory() for i in range(n_chunks)]
+    h_chunks = torch.from_numpy(chunks).pin_memory()
+    d_recv = [torch.empty(CPS * CHUNK_BYTES, dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -215,38 +221,54 @@ def main():
 
     state = dict(chunk=0, bcast=0)
 
+    def next_indices():
+        idx = [(state["chunk"] + k) % n_chunks for k in range(CPS)]
+        state["chunk"] += CPS
+        return idx
+
+    def gather_rows(src, idx, dst):
+        """rows idx of src -> dst (flat), contiguous runs copied in one go"""
+        k = 0
+        while k < len(idx):
+            j = k
+            while j + 1 < len(idx) and idx[j + 1] == idx[j] + 1:
+                j += 1
+            dst[k * CHUNK_BYTES:(j + 1) * CHUNK_BYTES].copy_(src[idx[k]:idx[j] + 1].reshape(-1), non_blocking=True)
+            k = j + 1
+
     def step_device():
-        """one step, chunks already in HBM (N>1: NCCL broadcast of each chunk from rank 0)"""
-        for _ in range(CPS):
-            i = state["chunk"] % n_chunks
-            state["chunk"] += 1
-            if world == 1:
+        """one step, chunks already in HBM (N>1: one NCCL broadcast of the step's chunks from rank 0)"""
+        idx = next_indices()
+        if world == 1:
+            for i in idx:
                 g.submit_device(d_chunks[i].data_ptr(), CHUNK_BYTES, stream.cuda_stream)
-            else:
-                buf = d_recv[state["bcast"] % NB]
-                state["bcast"] += 1
-                g.wait_input_consumed(stream.cuda_stream)         # buffer reuse: K0 of the previous user has run
-                if rank == 0:
-                    buf.copy_(d_chunks[i], non_blocking=True)
-                dist.broadcast(buf, src=0)
-                g.submit_device(buf.data_ptr(), CHUNK_BYTES, stream.cuda_stream)
+        else:
+            buf = d_recv[state["bcast"] % 2]
+            state["bcast"] += 1
+            g.wait_input_consumed(stream.cuda_stream)              # every K0 that read this area has run
+            if rank == 0:
+                gather_rows(d_chunks, idx, buf)
+            dist.broadcast(buf, src=0)
+            for k in range(CPS):
+                g.submit_device(buf.data_ptr() + k * CHUNK_BYTES, CHUNK_BYTES, stream.cuda_stream)
         return g.flush_count()
 
     def step_host():
-        """one step through the public host-buffer entry point (process_buf_uchar)"""
-        for _ in range(CPS):
-            i = state["chunk"] % n_chunks
-            state["chunk"] += 1
-            if world == 1:
+        """one step through the public host-buffer entry point (process_buf_uchar); with N > 1 the ingest rank copies
+        the step's chunks host->device and broadcasts them, the other ranks receive"""
+        idx = next_indices()
+        if world == 1:
+            for i in idx:
                 g.process_buf_uchar(h_chunks[i].numpy())
-            else:
-                buf = d_recv[state["bcast"] % NB]
-                state["bcast"] += 1
-                g.wait_input_consumed(stream.cuda_stream)
-                if rank == 0:
-                    buf.copy_(h_chunks[i], non_blocking=True)     # host -> device on the ingest rank
-                dist.broadcast(buf, src=0)
-                g.submit_device(buf.data_ptr(), CHUNK_BYTES, stream.cuda_stream)
+        else:
+            buf = d_recv[state["bcast"] % 2]
+            state["bcast"] += 1
+            g.wait_input_consumed(stream.cuda_stream)
+            if rank == 0:
+                gather_rows(h_chunks, idx, buf)                    # pinned host -> device
+            dist.broadcast(buf, src=0)
+            for k in range(CPS):
+                g.submit_device(buf.data_ptr() + k * CHUNK_BYTES, CHUNK_BYTES, stream.cuda_stream)
         return g.flush_count()
 
     def timed(step_fn, steps, sample_clocks=False):
@@ -347,7 +369,10 @@ def main():
         )
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     barrier()
     g.close()
     if world > 1:
