@@ -397,7 +397,7 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	p1.n_ch = c->n_ch; p1.n_chp = c->n_chp; p1.dec = d_dec; p1.state = c->d_k1;
 	p1.lut = reinterpret_cast<const float4 *>(c->d_tab->lut);
 	p1.a0 = c->tab.t.A[0]; p1.a1 = c->tab.t.A[1]; p1.a2 = c->tab.t.A[2]; p1.b1 = c->tab.t.B[1]; p1.b2 = c->tab.t.B[2];
-	p1.one = 1.0f; p1.neg_one = -1.0f;
+	p1.one = 1.0f; p1.neg_one = -1.0f; p1.two = 2.0f;
 	KL(vdl2_launch_k1(&p1, (c->cfg.flags & VDL2GPU_FLAG_K1_SCALAR) ? 1 : 0, c->stream));
 	if(s.timed) CU(cudaEventRecord(s.tk[2], c->stream));
 	CU(cudaEventRecord(c->ev_k1_done[db], c->stream));

@@ -133,7 +133,7 @@ __device__ __forceinline__ u64 f2_pack(float lo, float hi) { u64 r; asm("mov.b64
 __device__ __forceinline__ float f2_lo(u64 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
 __device__ __forceinline__ float f2_hi(u64 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
 
-struct k1_packed_consts { u64 ONE, SGN, A0, A1, A2, B1, B2; };
+struct k1_packed_consts { u64 ONE, SGN, A0, A1, A2, B1, B2, TWO; };
 
 /* one input sample: s = {re, im, im, re}; returns the filtered (I,Q) pair */
 __device__ __forceinline__ u64 k1_packed_step(const float4 s, const float4 *s_lut, uint32_t &phi, const uint32_t dphi,
@@ -173,7 +173,7 @@ __device__ __forceinline__ u64 k1_packed_math(const float4 s, const float4 e, co
 
 #define K1P_TILE_GROUPS(OS) (640 / (OS))        /* 640 samples = 10 KB of float4 per tile: leaves room for K2's blocks on the same SM */
 
-template<int OS, int BLOCK, int BATCH>
+template<int OS, int BLOCK, int BATCH, bool SYM>
 __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_params p) {
 	constexpr int TG = K1P_TILE_GROUPS(OS);
 	__shared__ float4 s_lut[257];
@@ -189,7 +189,12 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	k1_packed_consts c;
 	c.ONE = f2_pack(p.one, p.one); c.SGN = f2_pack(p.neg_one, p.one);
 	c.A0 = f2_pack(p.a0, p.a0); c.A1 = f2_pack(p.a1, p.a1); c.A2 = f2_pack(p.a2, p.a2);
-	c.B1 = f2_pack(p.b1, p.b1); c.B2 = f2_pack(p.b2, p.b2);
+	c.B1 = f2_pack(p.b1, p.b1); c.B2 = f2_pack(p.b2, p.b2); c.TWO = f2_pack(p.two, p.two);
+	/* SYM: the feed-forward taps of this filter design are {A0, 2*A0, A0} (checked on the host).  A1*x[n-1] and
+	 * A2*x[n-2] are then exactly 2*(A0*x[n-1]) and A0*x[n-2], products the previous two steps already formed
+	 * (doubling is exact; no operand can be subnormal here), so two multiplies per sample go away:
+	 * t = fma(P1, 2, P2) rounds once, exactly like A1*x1 + A2*x2. */
+	u64 P1 = f2_mul(c.A0, x1), P2 = f2_mul(c.A0, x2);
 	__syncthreads();
 
 	uint32_t cnt = p.cnt0, m = 0, pos = 0;
@@ -205,6 +210,7 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	pos = head;
 	m = (p.cnt0 + head) / OS;
 	cnt = (p.cnt0 + head) % OS;
+	P1 = f2_mul(c.A0, x1); P2 = f2_mul(c.A0, x2);            /* after the head samples */
 	/* body: whole groups, staged through shared memory tile by tile */
 	const uint32_t n_groups = (p.n_pairs - pos) / OS;
 	for(uint32_t g0 = 0; g0 < n_groups; g0 += TG) {
@@ -245,8 +251,15 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 						}
 						if(k >= 0) {
 							const u64 x0 = X0[k];
-							const u64 t = f2_fma(f2_mul(c.A1, x1), c.ONE, f2_mul(c.A2, x2));
-							const u64 r = f2_fma(f2_mul(c.A0, x0), c.ONE, t);
+							u64 r;
+							if(SYM) {
+								const u64 P0 = f2_mul(c.A0, x0);
+								r = f2_fma(P0, c.ONE, f2_fma(P1, c.TWO, P2));
+								P2 = P1; P1 = P0;
+							} else {
+								const u64 t = f2_fma(f2_mul(c.A1, x1), c.ONE, f2_mul(c.A2, x2));
+								r = f2_fma(f2_mul(c.A0, x0), c.ONE, t);
+							}
 							const u64 u = f2_fma(f2_mul(c.B1, y1), c.ONE, f2_mul(c.B2, y2));
 							y0 = f2_fma(r, c.ONE, u);
 							x2 = x1; x1 = x0; y2 = y1; y1 = y0;
@@ -523,14 +536,15 @@ extern "C" int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, cudaStr
 	const uint32_t blocks = (p->n_ch + K1_BLOCK - 1) / K1_BLOCK;
 	static int variant = -1;
 	if(variant < 0) { const char *e = getenv("VDL2GPU_K1_VARIANT"); variant = e ? atoi(e) : 2; }
+	const bool sym = (p->a1 == 2.0f * p->a0) && (p->a2 == p->a0) && variant != 4;
 	if(!force_scalar && p->oversample == 20) {
-		if(variant == 0) k1_mix_iir_decimate_packed<20, K1_BLOCK, 0><<<blocks, K1_BLOCK, 0, st>>>(*p);
-		else if(variant == 1) k1_mix_iir_decimate_packed<20, K1_BLOCK, 5><<<blocks, K1_BLOCK, 0, st>>>(*p);
-		else if(variant == 3) k1_mix_iir_decimate_packed<20, K1_BLOCK, 20><<<blocks, K1_BLOCK, 0, st>>>(*p);
-		else k1_mix_iir_decimate_packed<20, K1_BLOCK, 10><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		if(variant == 0) k1_mix_iir_decimate_packed<20, K1_BLOCK, 0, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		else if(sym) k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		else k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
 	} else if(!force_scalar && p->oversample == 10) {
-		if(variant == 0) k1_mix_iir_decimate_packed<10, K1_BLOCK, 0><<<blocks, K1_BLOCK, 0, st>>>(*p);
-		else k1_mix_iir_decimate_packed<10, K1_BLOCK, 10><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		if(variant == 0) k1_mix_iir_decimate_packed<10, K1_BLOCK, 0, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		else if(sym) k1_mix_iir_decimate_packed<10, K1_BLOCK, 10, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		else k1_mix_iir_decimate_packed<10, K1_BLOCK, 10, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
 	} else k1_mix_iir_decimate_scalar<K1_BLOCK><<<blocks, K1_BLOCK, 0, st>>>(*p);
 	return (int)cudaGetLastError();
 }

@@ -15,7 +15,7 @@ typedef struct {
 	uint32_t *state;             /* [K1_NFIELDS][n_chp] */
 	const float4 *lut;           /* 257 x {cos, sin, dcos*2^-16, dsin*2^-16} */
 	float a0, a1, a2, b1, b2;
-	float one, neg_one;          /* run-time 1.0f / -1.0f (see k1_mix_iir_decimate_packed) */
+	float one, neg_one, two;     /* run-time 1.0f / -1.0f / 2.0f (see k1_mix_iir_decimate_packed) */
 } vdl2_k1_params;
 
 typedef struct {
