@@ -493,7 +493,8 @@ VDL2_HD void vdl2_demod_step_pm(vdl2_chan &v, float *ring, int rs, const vdl2_k2
 VDL2_HD void vdl2_walk_block(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env, uint32_t chan_idx, uint64_t idx0,
 		const float2 *dec, const float *phase, const float *mag, size_t stride) {
 	int resume = 0;
-	if(!(v.state & VDL2_ST_LOCKED) && vdl2_dec_state(v) != VDL2_DEC_IDLE && v.pure_run >= VDL2_PURE_NEEDED) {
+	if(!(v.state & VDL2_ST_LOCKED) && vdl2_dec_state(v) != VDL2_DEC_IDLE && v.pure_run >= VDL2_PURE_NEEDED
+			&& v.sclk >= 0 && v.sclk < VDL2_SYNC_SKIP) {      /* sclk can sit above SYNC_SKIP after a max_ppm veto */
 		const int first = (VDL2_SYNC_SKIP - 1) - v.sclk;                  /* offset of the first attempt in the block */
 		float ph[4][VDL2_PREAMBLE_SYMS], p0[4], sl[4], mg[4], pw[VDL2_WALK_BLOCK];
 #pragma unroll
@@ -519,7 +520,9 @@ VDL2_HD void vdl2_walk_block(vdl2_chan &v, float *ring, int rs, const vdl2_k2_en
 					if(u <= first) vdl2_init_write(v, ring, rs, pw[VDL2_SYNC_SKIP * g + u]);
 				v.sclk = 0;
 				vdl2_init_eval(v, ring, rs, env, chan_idx, idx0 + (uint64_t)(VDL2_SYNC_SKIP * g + first), mg[g], true, p0[g], sl[g]);
-				if(v.state & VDL2_ST_LOCKED) {
+				if((v.state & VDL2_ST_LOCKED) || v.sclk != 0) {
+					/* locked on a preamble, or the preamble was vetoed by max_ppm (src/demod.c:190-192 leaves the
+					 * sample clock at the sync point): the per-sample path takes over for the rest of the block */
 					go = false;
 					resume = VDL2_SYNC_SKIP * g + first + 1;
 				} else {

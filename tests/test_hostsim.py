@@ -46,6 +46,19 @@ def test_device_functions_on_host_match_oracle(name, use_pre):
     assert len(recs) == len(ob)
 
 
+def test_max_ppm_veto_in_blocked_walk():
+    """A vetoed preamble leaves the sample clock at the sync point (src/demod.c:179,190-192): the blocked walk
+    must fall back to the per-sample path there."""
+    c = dict(cases.case_mixed_s16()); c["max_ppm"] = 1.0
+    o = util.run_oracle(c, trace=True, dec_tap=True)
+    recs, ev, cnt = hs.k2k3(o.dec_samples(), c["freqs"], c["fs"], max_ppm=1.0)
+    got = sorted((r["channel"], r["burst_seq"], k, d, r["sync_dec_index"]) for r in recs for k, (d, _) in enumerate(r["frames"]))
+    want = sorted((f.channel, f.burst_seq, f.idx, f.data, f.sync_dec_index) for f in o.frames())
+    assert got == want and len(want) < 14
+    util.assert_events_equal(ev, o.events(), "hostsim max_ppm events")
+    assert any(e["kind"] == 1 and e["i"][3] == 0 for e in ev)
+
+
 def test_rs_decoder_matches_oracle_beyond_capacity():
     """Same result as the oracle (== Karn's decoder) for 0..7 errors incl. failures and miscorrections."""
     import ctypes as C
