@@ -73,6 +73,8 @@ def load_library():
     L.vdl2gpu_destroy.argtypes = [C.c_void_p]
     L.vdl2gpu_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.vdl2gpu_submit_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.vdl2gpu_submit_planar_s16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.vdl2gpu_serialize_raw_frame.argtypes = [C.POINTER(_Frame), C.c_char_p, C.c_void_p, C.c_size_t]
     L.vdl2gpu_wait_input_consumed.argtypes = [C.c_void_p, C.c_void_p]
     L.vdl2gpu_stream_wait.argtypes = [C.c_void_p, C.c_void_p]
     L.vdl2gpu_poll.argtypes = [C.c_void_p, _FRAME_CB, C.c_void_p]
@@ -112,6 +114,21 @@ class Frame:
     def __repr__(self):
         return (f"Frame(ch={self.channel} burst={self.burst_seq} idx={self.idx} len={len(self.data)} "
                 f"fcs_ok={self.fcs_ok} fec={self.num_fec_corrections} synd={self.synd_weight})")
+
+
+def serialize_raw_frame(frame, station_id=None, timestamp=(0, 0)):
+    """Frame -> one record of the reference's raw-frame archive format (see vdl2gpu_serialize_raw_frame)."""
+    L = load_library()
+    f = _Frame()
+    buf = (C.c_uint8 * max(len(frame.data), 1)).from_buffer_copy(frame.data or b"\0")
+    f.channel, f.freq, f.burst_seq, f.idx = frame.channel, frame.freq, frame.burst_seq, frame.idx
+    f.data, f.len = C.cast(buf, C.POINTER(C.c_uint8)), len(frame.data)
+    f.synd_weight, f.datalen_octets, f.num_fec_corrections = frame.synd_weight, frame.datalen_octets, frame.num_fec_corrections
+    f.frame_pwr_dbfs, f.nf_pwr_dbfs, f.ppm_error = frame.frame_pwr_dbfs, frame.nf_pwr_dbfs, frame.ppm_error
+    f.burst_timestamp.tv_sec, f.burst_timestamp.tv_usec = timestamp
+    out = (C.c_uint8 * 70000)()
+    n = _check(L, L.vdl2gpu_serialize_raw_frame(C.byref(f), station_id.encode() if station_id else None, out, 70000), "vdl2gpu_serialize_raw_frame")
+    return bytes(out[:n])
 
 
 class Vdl2Channels:
@@ -174,6 +191,12 @@ class Vdl2Channels:
 
     def submit(self, buf):
         return self._submit(buf, self.sample_fmt)
+
+    def submit_planar_s16(self, xi, xq):
+        """SDRplay-style hand-off: separate int16 I and Q arrays (src/sdrplay.c:72-134)."""
+        xi = np.ascontiguousarray(xi, dtype=np.int16); xq = np.ascontiguousarray(xq, dtype=np.int16)
+        assert xi.size == xq.size
+        _check(self.L, self.L.vdl2gpu_submit_planar_s16(self.h, xi.ctypes.data, xq.ctypes.data, xi.size), "vdl2gpu_submit_planar_s16")
 
     def submit_device(self, dev_ptr, nbytes, producer_stream=0):
         _check(self.L, self.L.vdl2gpu_submit_device(self.h, C.c_void_p(dev_ptr), nbytes, C.c_void_p(producer_stream)), "vdl2gpu_submit_device")

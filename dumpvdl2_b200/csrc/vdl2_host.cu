@@ -376,7 +376,7 @@ static int acquire_slot(vdl2gpu_ctx *c, chunk_slot **out) {
 	return VDL2GPU_OK;
 }
 
-static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t n_pairs) {
+static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t n_pairs, uint32_t k0_fmt = 0xFFFFFFFFu) {
 	const uint32_t os = c->cfg.oversample;
 	s.first_pair = c->total_pairs;
 	s.n_pairs = n_pairs;
@@ -388,7 +388,7 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	float2 *d_dec = c->d_dec2[db];
 	/* ---- front stage: K0, K1 ---- */
 	if(s.timed) CU(cudaEventRecord(s.tk[0], c->stream));
-	KL(vdl2_launch_k0(d_raw, n_pairs, c->cfg.sample_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->stream));
+	KL(vdl2_launch_k0(d_raw, n_pairs, k0_fmt == 0xFFFFFFFFu ? c->cfg.sample_fmt : k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->stream));
 	CU(cudaEventRecord(c->ev_input_consumed, c->stream));
 	if(s.timed) CU(cudaEventRecord(s.tk[1], c->stream));
 	if(c->chunk_seq >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_back_done[db], 0));   /* K2 of chunk c-2 has read this buffer */
@@ -446,6 +446,63 @@ extern "C" int vdl2gpu_submit(vdl2gpu_ctx *c, const void *iq, uint32_t len) {
 	memcpy(s->h_raw, iq, len);
 	CU(cudaMemcpyAsync(s->d_raw, s->h_raw, len, cudaMemcpyHostToDevice, c->stream));
 	return run_chain(c, *s, s->d_raw, n_pairs);
+}
+
+extern "C" int vdl2gpu_submit_planar_s16(vdl2gpu_ctx *c, const int16_t *xi, const int16_t *xq, uint32_t n_pairs) {
+	if(!c || ((!xi || !xq) && n_pairs)) return VDL2GPU_EINVAL;
+	if(c->cfg.sample_fmt != VDL2GPU_FMT_S16_LE) return VDL2GPU_EINVAL;
+	if(n_pairs == 0) return VDL2GPU_OK;
+	if((uint64_t)n_pairs * 4u > c->cfg.max_chunk_bytes) return VDL2GPU_ETOOBIG;
+	CU(cudaSetDevice(c->device));
+	chunk_slot *s;
+	int rc = acquire_slot(c, &s);
+	if(rc) return rc;
+	memcpy(s->h_raw, xi, (size_t)n_pairs * 2);
+	memcpy(s->h_raw + (size_t)n_pairs * 2, xq, (size_t)n_pairs * 2);
+	CU(cudaMemcpyAsync(s->d_raw, s->h_raw, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+	return run_chain(c, *s, s->d_raw, n_pairs, 2u);
+}
+
+/* src/fmtr-binary.c + src/output-file.c:181-189: one raw frame in the reference's archive format, i.e. a 2-octet
+ * big-endian length (its own two octets included) followed by the proto3 message dumpvdl2.raw_avlc_frame
+ * (proto/dumpvdl2.proto:25-48).  Files made of these records replay through an unmodified
+ * `dumpvdl2 --raw-frames-file` (src/input-raw_frames_file.c:33-75).  Returns the record size or a negative error. */
+static size_t pb_varint(uint8_t *o, uint64_t v) { size_t n = 0; do { uint8_t b = v & 0x7Fu; v >>= 7; o[n++] = (uint8_t)(b | (v ? 0x80u : 0u)); } while(v); return n; }
+static size_t pb_u32_field(uint8_t *o, int field, uint32_t v) { if(!v) return 0; size_t n = pb_varint(o, (uint64_t)field << 3); return n + pb_varint(o + n, v); }
+static size_t pb_i64_field(uint8_t *o, int field, int64_t v) { if(!v) return 0; size_t n = pb_varint(o, (uint64_t)field << 3); return n + pb_varint(o + n, (uint64_t)v); }
+static size_t pb_f32_field(uint8_t *o, int field, float v) { uint32_t u; memcpy(&u, &v, 4); if(!u) return 0; size_t n = pb_varint(o, ((uint64_t)field << 3) | 5u); memcpy(o + n, &u, 4); return n + 4; }
+
+extern "C" int vdl2gpu_serialize_raw_frame(const vdl2gpu_frame *f, const char *station_id, uint8_t *out, size_t cap) {
+	if(!f || !out || (f->len && !f->data)) return VDL2GPU_EINVAL;
+	uint8_t ts[24], md[96 + 256];
+	size_t nts = 0, nmd = 0;
+	nts += pb_i64_field(ts + nts, 1, (int64_t)f->burst_timestamp.tv_sec);
+	nts += pb_i64_field(ts + nts, 2, (int64_t)f->burst_timestamp.tv_usec);
+	size_t sl = station_id ? strlen(station_id) : 0;
+	if(sl > 255) sl = 255;                                          /* STATION_ID_LEN_MAX, src/dumpvdl2.h:193 */
+	if(sl) { nmd += pb_varint(md + nmd, (1u << 3) | 2u); nmd += pb_varint(md + nmd, sl); memcpy(md + nmd, station_id, sl); nmd += sl; }
+	nmd += pb_u32_field(md + nmd, 2, f->freq);
+	nmd += pb_u32_field(md + nmd, 3, f->synd_weight);
+	nmd += pb_u32_field(md + nmd, 4, f->datalen_octets);
+	nmd += pb_f32_field(md + nmd, 5, f->frame_pwr_dbfs);
+	nmd += pb_f32_field(md + nmd, 6, f->nf_pwr_dbfs);
+	nmd += pb_f32_field(md + nmd, 7, f->ppm_error);
+	nmd += pb_i64_field(md + nmd, 8, 1);                            /* metadata version, src/decode.c:177 */
+	nmd += pb_i64_field(md + nmd, 9, (int64_t)f->num_fec_corrections);
+	nmd += pb_i64_field(md + nmd, 10, (int64_t)f->idx);
+	nmd += pb_varint(md + nmd, (11u << 3) | 2u); nmd += pb_varint(md + nmd, nts); memcpy(md + nmd, ts, nts); nmd += nts;
+	uint8_t hdr[16];
+	size_t nh = pb_varint(hdr, (1u << 3) | 2u); nh += pb_varint(hdr + nh, nmd);
+	uint8_t dh[16];
+	size_t nd = f->len ? pb_varint(dh, (2u << 3) | 2u) : 0;
+	if(f->len) nd += pb_varint(dh + nd, f->len);
+	const size_t total = 2 + nh + nmd + nd + f->len;
+	if(total > 65536 || total > cap) return VDL2GPU_ETOOBIG;         /* OUT_BINARY_FRAME_LEN_MAX, src/output-file.h:26 */
+	uint8_t *o = out;
+	*o++ = (uint8_t)(total >> 8); *o++ = (uint8_t)total;
+	memcpy(o, hdr, nh); o += nh; memcpy(o, md, nmd); o += nmd;
+	memcpy(o, dh, nd); o += nd; if(f->len) memcpy(o, f->data, f->len);
+	return (int)total;
 }
 
 extern "C" int vdl2gpu_submit_device(vdl2gpu_ctx *c, const void *dev_iq, uint32_t len, void *producer_stream) {

@@ -32,10 +32,17 @@ __global__ void __launch_bounds__(256) k0_convert(const uint8_t *__restrict__ ra
 		uchar2 v = reinterpret_cast<const uchar2 *>(raw)[i];
 		re = __ldg(&levels[v.x]);
 		im = __ldg(&levels[v.y]);
-	} else {                                             /* src/demod.c:361-363 */
+	} else if(fmt == 1) {                                /* src/demod.c:361-363 */
 		short2 v = reinterpret_cast<const short2 *>(raw)[i];
 		re = __fdiv_rn((float)v.x, 32768.0f);
 		im = __fdiv_rn((float)v.y, 32768.0f);
+	} else {
+		/* planar cs16: n_pairs I values followed by n_pairs Q values, the shape the SDRplay APIs deliver
+		 * (src/sdrplay.c:72, src/sdrplay3.c callbacks); same arithmetic as the interleaved case, the
+		 * host-side interleave loop of src/sdrplay.c:95-121 is not needed */
+		const short *pl = reinterpret_cast<const short *>(raw);
+		re = __fdiv_rn((float)pl[i], 32768.0f);
+		im = __fdiv_rn((float)pl[n_pairs + i], 32768.0f);
 	}
 	out[i] = make_float4(re, im, im, re);
 }
@@ -539,6 +546,9 @@ extern "C" int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, cudaStr
 	const bool sym = (p->a1 == 2.0f * p->a0) && (p->a2 == p->a0) && variant != 4;
 	if(!force_scalar && p->oversample == 20) {
 		if(variant == 0) k1_mix_iir_decimate_packed<20, K1_BLOCK, 0, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		else if(sym && variant == 5) k1_mix_iir_decimate_packed<20, K1_BLOCK, 6, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		else if(sym && variant == 6) k1_mix_iir_decimate_packed<20, K1_BLOCK, 14, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		else if(sym && variant == 7) k1_mix_iir_decimate_packed<20, K1_BLOCK, 20, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
 		else if(sym) k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
 		else k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
 	} else if(!force_scalar && p->oversample == 10) {

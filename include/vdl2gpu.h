@@ -132,6 +132,10 @@ const char *vdl2gpu_last_error(void);
  * the caller may reuse `iq` as soon as the call returns.  Asynchronous: copies into a pinned staging ring,
  * enqueues H2D + kernels.  Blocks only when n_inflight chunks are pending (the reference's back-pressure). */
 int vdl2gpu_submit(vdl2gpu_ctx *ctx, const void *iq, uint32_t len);
+/* Ingest adaptor for front-ends that deliver I and Q as separate int16 arrays (SDRplay: src/sdrplay.c:72-134,
+ * src/sdrplay3.c): n_pairs values each; replaces the host-side interleave + process_buf_short.  The context must
+ * have been created with VDL2GPU_FMT_S16_LE. */
+int vdl2gpu_submit_planar_s16(vdl2gpu_ctx *ctx, const int16_t *xi, const int16_t *xq, uint32_t n_pairs);
 /* Same, but `dev_iq` already lives in this GPU's memory (e.g. the receive buffer of an NCCL broadcast).
  * `producer_stream` (cudaStream_t, may be NULL = legacy default stream) is the stream on which the buffer
  * was produced; the library orders its work after it.  The buffer may be overwritten once
@@ -150,6 +154,12 @@ int vdl2gpu_get_stats(vdl2gpu_ctx *ctx, vdl2gpu_stats *out);
 /* per-channel counters, 9 x uint64 per channel in the order: sync_good, hdr_crc_good, bursts, burst_err,
  * blocks_processed, blocks_fec_ok, msg_good, fcs_good, fcs_bad.  Implies a flush of device work. */
 int vdl2gpu_get_channel_counters(vdl2gpu_ctx *ctx, uint64_t *out, uint32_t n_channels);
+
+/* One frame in the reference's raw-frame archive format (2-octet big-endian record length + proto3
+ * dumpvdl2.raw_avlc_frame, proto/dumpvdl2.proto:25-48, as written by src/fmtr-binary.c + src/output-file.c:181-189):
+ * records written back to back replay through an unmodified `dumpvdl2 --raw-frames-file`.
+ * Returns the record size in octets, or a negative error.  Host-only helper (no device work). */
+int vdl2gpu_serialize_raw_frame(const vdl2gpu_frame *frame, const char *station_id, uint8_t *out, size_t cap);
 
 /* ---- introspection for parity tests / profiling ---- */
 /* tables the kernels use, computed by the library's own host code (restating src/demod.c:349-377,367-370,84-96) */

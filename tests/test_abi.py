@@ -66,3 +66,45 @@ def test_bad_config_is_rejected():
     cfg.sample_rate, cfg.oversample, cfg.n_channels = 2100000, 10, 1    # rate != 105000 * oversample
     cfg.freqs = f.ctypes.data_as(C.POINTER(C.c_uint32))
     assert L.vdl2gpu_create(C.byref(cfg), C.byref(h)) == -1
+
+
+def test_raw_frame_record_is_valid_dumpvdl2_protobuf():
+    """vdl2gpu_serialize_raw_frame writes the reference's archive record (proto/dumpvdl2.proto:25-48): parse it back
+    with the stock protobuf runtime against a descriptor mirroring that .proto."""
+    import struct
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    from dumpvdl2_b200 import api
+    fd = descriptor_pb2.FileDescriptorProto(name="dumpvdl2.proto", package="dumpvdl2", syntax="proto3")
+    md = fd.message_type.add(name="vdl2_msg_metadata")
+    T = descriptor_pb2.FieldDescriptorProto
+    for num, name, typ in ((1, "station_id", T.TYPE_STRING), (2, "frequency", T.TYPE_UINT32), (3, "synd_weight", T.TYPE_UINT32),
+                           (4, "datalen_octets", T.TYPE_UINT32), (5, "frame_pwr_dbfs", T.TYPE_FLOAT), (6, "nf_pwr_dbfs", T.TYPE_FLOAT),
+                           (7, "ppm_error", T.TYPE_FLOAT), (8, "version", T.TYPE_INT32), (9, "num_fec_corrections", T.TYPE_INT32),
+                           (10, "idx", T.TYPE_INT32)):
+        md.field.add(name=name, number=num, type=typ, label=T.LABEL_OPTIONAL)
+    ts = md.nested_type.add(name="timestamp")
+    ts.field.add(name="tv_sec", number=1, type=T.TYPE_INT64, label=T.LABEL_OPTIONAL)
+    ts.field.add(name="tv_usec", number=2, type=T.TYPE_INT64, label=T.LABEL_OPTIONAL)
+    md.field.add(name="burst_timestamp", number=11, type=T.TYPE_MESSAGE, label=T.LABEL_OPTIONAL, type_name=".dumpvdl2.vdl2_msg_metadata.timestamp")
+    fr = fd.message_type.add(name="raw_avlc_frame")
+    fr.field.add(name="metadata", number=1, type=T.TYPE_MESSAGE, label=T.LABEL_OPTIONAL, type_name=".dumpvdl2.vdl2_msg_metadata")
+    fr.field.add(name="data", number=2, type=T.TYPE_BYTES, label=T.LABEL_OPTIONAL)
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    Raw = message_factory.GetMessageClass(pool.FindMessageTypeByName("dumpvdl2.raw_avlc_frame"))
+
+    f = api.Frame()
+    f.channel, f.freq, f.burst_seq, f.idx = 3, 136975000, 7, 1
+    f.data = bytes(range(200)) + b"\x3e\xf9"
+    f.synd_weight, f.datalen_octets, f.num_fec_corrections = 1, 504, -2
+    f.frame_pwr_dbfs, f.nf_pwr_dbfs, f.ppm_error = -9.840581, 1.7991041, -0.070490792
+    rec = api.serialize_raw_frame(f, station_id="EPWA-1", timestamp=(1790000000, 123456))
+    (n,) = struct.unpack(">H", rec[:2])
+    assert n == len(rec)                      # the length counts its own two octets (src/output-file.c:181)
+    m = Raw.FromString(rec[2:])
+    assert m.data == f.data and m.metadata.station_id == "EPWA-1" and m.metadata.frequency == 136975000
+    assert (m.metadata.synd_weight, m.metadata.datalen_octets, m.metadata.version, m.metadata.num_fec_corrections, m.metadata.idx) == (1, 504, 1, -2, 1)
+    assert np.float32(m.metadata.frame_pwr_dbfs) == np.float32(-9.840581) and np.float32(m.metadata.ppm_error) == np.float32(-0.070490792)
+    assert (m.metadata.burst_timestamp.tv_sec, m.metadata.burst_timestamp.tv_usec) == (1790000000, 123456)
+    rec0 = api.serialize_raw_frame(f)         # no station id, zero timestamp: fields with default values are omitted
+    assert Raw.FromString(rec0[2:]).metadata.station_id == "" and Raw.FromString(rec0[2:]).metadata.HasField("burst_timestamp")

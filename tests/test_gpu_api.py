@@ -113,3 +113,16 @@ def test_two_contexts_are_independent():
         g2.submit(b2[k * c2["chunk"]:(k + 1) * c2["chunk"]])
     util.assert_frames_equal(g1.flush(), util.run_oracle(c1).frames(), "ctx 1")
     util.assert_frames_equal(g2.flush(), util.run_oracle(c2).frames(), "ctx 2")
+
+
+def test_planar_s16_ingest_equals_interleaved():
+    """SDRplay hand-off (separate I / Q arrays, src/sdrplay.c:72-134) through vdl2gpu_submit_planar_s16."""
+    c = cases.case_mixed_s16()
+    o = util.run_oracle(c)
+    g = _gpu(c)
+    iq = c["iq"].reshape(-1, 2)
+    step = c["chunk"] // 4
+    for k in range(0, iq.shape[0], step):
+        part = iq[k:k + step]
+        g.submit_planar_s16(part[:, 0].copy(), part[:, 1].copy())
+    util.assert_frames_equal(g.flush(), o.frames(), "planar cs16 ingest")
