@@ -63,7 +63,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -272,12 +272,17 @@ def main():
         return g.flush_count()
 
     def timed(step_fn, steps, sample_clocks=False):
+        # one sampler for the job (rank 0's GPU): eight concurrent nvidia-smi pollers contend for the driver lock.
+        # It is started BEFORE the barrier so that no rank enters the timed region late.
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+        if sample_clocks:
+            time.sleep(0.3)
         barrier()
         s0 = g.stats()
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sampler = ClockSampler(local_rank) if sample_clocks else None
-        if sampler:
-            sampler.start(); time.sleep(0.25)
         t0 = time.time()
         e0.record(stream)
         frames = 0
