@@ -735,29 +735,36 @@ VDL2_HD int vdl2_rs_verify(uint8_t *data, int fec_octets, const uint8_t *gexp, c
  * late error stay (the reference has already pushed them). */
 VDL2_HD int vdl2_burst_unstuff(vdl2_burst_work &w) {
 	const uint32_t total_bits = (8u * w.datalen_octets < w.datalen_bits) ? 8u * w.datalen_octets : w.datalen_bits;
-	uint32_t pos = 0;
+	uint32_t pos = 0, row = 0, col = 0, cur = 0;     /* input: corrected octets row by row, LSB first */
 	uint32_t out_base = 0;
 	for(;;) {
 		uint32_t j = 0;          /* bits of the candidate frame, flag prefix included */
+		uint32_t acc = 0;        /* output octet being assembled */
 		int ones = 0;
 		for(;;) {                /* one pass of bitstream_copy_next_frame, restarts folded in */
 			if(pos >= total_bits) break;
-			uint32_t o = pos >> 3;
-			uint32_t bit = (w.tab[o / VDL2_RS_K][o % VDL2_RS_K] >> (pos & 7u)) & 1u;
-			if(bit == 0 && ones == 5) { ones = 0; pos++; continue; }
-			if(bit == 1 && ++ones > 6) return w.status = VDL2_ERR_UNSTUFF;
-			uint32_t ob = out_base + (j >> 3);
-			if(ob >= sizeof(w.frames)) return w.status = VDL2_ERR_BITSTREAM;
-			if((j & 7u) == 0) w.frames[ob] = (uint8_t)bit;
-			else w.frames[ob] |= (uint8_t)(bit << (j & 7u));
+			if((pos & 7u) == 0) {
+				cur = w.tab[row][col];
+				if(++col == VDL2_RS_K) { col = 0; row++; }
+			}
+			const uint32_t bit = (cur >> (pos & 7u)) & 1u;
+			if(bit == 0 && ones == 5) { ones = 0; pos++; continue; }         /* stuffed zero */
+			if(bit == 1 && ++ones > 6) return w.status = VDL2_ERR_UNSTUFF;   /* seven ones */
+			acc |= bit << (j & 7u);
 			if(bit == 0) {
-				if(ones == 6) {
-					if(j == 7) { pos++; j = 0; ones = 0; continue; }       /* opening flag: restart */
+				if(ones == 6) {                                              /* 01111110 */
+					if(j == 7) { pos++; j = 0; acc = 0; ones = 0; continue; }    /* opening flag: restart */
 					if(j < 7) return w.status = VDL2_ERR_UNSTUFF;
 					j -= 7; pos++;
 					goto frame_done;
 				}
 				ones = 0;
+			}
+			if((j & 7u) == 7u) {
+				const uint32_t ob = out_base + (j >> 3);
+				if(ob >= sizeof(w.frames)) return w.status = VDL2_ERR_BITSTREAM;
+				w.frames[ob] = (uint8_t)acc;
+				acc = 0;
 			}
 			j++; pos++;
 		}

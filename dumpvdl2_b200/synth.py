@@ -129,7 +129,12 @@ def burst_bits(frames, corrupt_octets=None, header_bit_errors=()):
     corrupt_octets: optional list of (block_row, column, xor_value) applied after RS encoding;
     header_bit_errors: bit positions (0 = first transmitted) flipped in the 25-bit header.
     Returns (bits uint8 array, info dict)."""
-    payload = hdlc_payload_bits(frames)
+    return burst_bits_from_payload(hdlc_payload_bits(frames), corrupt_octets, header_bit_errors)
+
+
+def burst_bits_from_payload(payload, corrupt_octets=None, header_bit_errors=()):
+    """Same, from an arbitrary payload bit string ('0'/'1', transmission order): lets tests craft HDLC edge cases
+    (repeated flags, aborts, frames that are not whole octets, missing closing flag)."""
     datalen = len(payload)
     if datalen > 0x3FFF:
         raise ValueError("burst too long")
@@ -207,8 +212,9 @@ def modulate_burst(bits, up, ramp_up=4, ramp_down=2):
 class BurstSpec:
     """One burst to place in a stream."""
     def __init__(self, start_s, offset_hz, frames, power_dbfs=-20.0, freq_err_hz=0.0,
-                 corrupt_octets=None, header_bit_errors=()):
+                 corrupt_octets=None, header_bit_errors=(), payload=None):
         self.start_s, self.offset_hz, self.frames = start_s, offset_hz, frames
+        self.payload = payload          # raw payload bit string instead of frames (HDLC edge cases)
         self.power_dbfs, self.freq_err_hz = power_dbfs, freq_err_hz
         self.corrupt_octets, self.header_bit_errors = corrupt_octets, header_bit_errors
         self.info = None
@@ -227,7 +233,10 @@ def synth_stream(fs, duration_s, bursts, es_n0_db=None, noise_power=None, fmt="u
     n = int(round(duration_s * fs))
     x = np.zeros(n, np.complex64)
     for b in bursts:
-        bits, info = burst_bits(b.frames, b.corrupt_octets, b.header_bit_errors)
+        if b.payload is not None:
+            bits, info = burst_bits_from_payload(b.payload, b.corrupt_octets, b.header_bit_errors)
+        else:
+            bits, info = burst_bits(b.frames, b.corrupt_octets, b.header_bit_errors)
         b.info = info
         sig, first = modulate_burst(bits, up)
         a = 10.0 ** (b.power_dbfs / 20.0)
@@ -254,9 +263,9 @@ def synth_stream(fs, duration_s, bursts, es_n0_db=None, noise_power=None, fmt="u
     raise ValueError(fmt)
 
 
-def burst_duration_s(frames, ramp_up=4, ramp_down=2):
+def burst_duration_s(frames, ramp_up=4, ramp_down=2, payload=None):
     """On-air duration of the burst carrying `frames` (ramp + preamble + header/data symbols)."""
-    _, info = burst_bits(frames)
+    _, info = burst_bits_from_payload(payload) if payload is not None else burst_bits(frames)
     return (ramp_up + len(PREAMBLE_STEPS) + info["n_symbols"] + ramp_down) / SYMBOL_RATE
 
 

@@ -86,6 +86,40 @@ def case_fec():
     return _mk("fec", fs, "u8", [CENTER + o for o in offs], iq, bursts=bursts)
 
 
+def case_hdlc_edge():
+    """Crafted payloads (src/bitstream.c:109-150 corner cases, pinned by running the reference itself): repeated
+    flags, back-to-back flags, abort (seven ones), a frame that is not a whole number of octets after a good one,
+    a missing closing flag, trailing bits after the last flag, frames shorter than an AVLC header."""
+    fs = 2100000
+    rng = np.random.default_rng(31337)
+    F = "01111110"
+
+    def st(n):
+        return "".join(format(b, "08b")[::-1] for b in rng.integers(0, 256, n, dtype=np.uint8)).replace("11111", "111110")
+
+    def fr(n):
+        return "".join(format(b, "08b")[::-1] for b in synth.random_avlc_frame(rng, n)).replace("11111", "111110")
+    payloads = [
+        F + F + F + fr(40) + F,                          # repeated opening flags
+        F + fr(30) + F + F + fr(25) + F,                 # back-to-back flags between frames
+        F + fr(30) + F + st(10) + "1111111" + st(4) + F, # abort in the second frame: the first stays pushed
+        F + fr(22) + F + st(9) + "010" + F,              # second frame not octet aligned
+        F + fr(50),                                      # no closing flag
+        F + fr(35) + F + "0101",                         # trailing bits after the closing flag
+        F + st(3) + F + st(1) + F + fr(20) + F,          # frames shorter than an AVLC header
+        F + fr(270) + F + fr(260) + F,                   # three RS blocks
+        "0110" + F + fr(20) + F,                         # garbage before the opening flag (< 7 bits: error)
+        F + fr(12) + F + F,                              # trailing flag: zero-length last frame
+    ]
+    offs = [75e3 * k for k in range(-5, 6) if k != 0]
+    bursts, t = [], 0.02
+    for i, pl in enumerate(payloads):
+        bursts.append(synth.BurstSpec(t, offs[i], [], power_dbfs=-12.0, payload=pl))
+        t += synth.burst_duration_s(None, payload=pl) + 0.012
+    iq = synth.synth_stream(fs, t + 0.02, bursts, es_n0_db=32, fmt="u8", seed=31338)
+    return _mk("hdlc_edge", fs, "u8", [CENTER + o for o in offs], iq, bursts=bursts)
+
+
 def case_noisy():
     """Low SNR (Es/N0 19.5 dB): symbol errors, RS corrections and failures, false syncs on noise."""
     fs = 2100000
@@ -116,4 +150,5 @@ def case_replicas(n_slots=16, n_rep=4, duration=0.5, seed=0x56444C33, es_n0_db=2
     return _mk(f"replicas_{n_slots}x{n_rep}", fs, "u8", freqs, iq, chunk=524288, bursts=bursts)
 
 
-ALL_GOLDEN = {"wav": case_wav, "cfg2": case_cfg2, "mixed_s16": case_mixed_s16, "fec": case_fec, "noisy": case_noisy}
+ALL_GOLDEN = {"wav": case_wav, "cfg2": case_cfg2, "mixed_s16": case_mixed_s16, "fec": case_fec, "noisy": case_noisy,
+              "hdlc_edge": case_hdlc_edge}

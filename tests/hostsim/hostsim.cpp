@@ -158,6 +158,40 @@ int hostsim_k2k3(const float *dec /*[n_dec][n_ch][2]*/, uint32_t n_dec, uint32_t
 	return ovf;
 }
 
+/* K3 alone: `bits` = the burst after the preamble (header + payload + FEC, scrambled, one bit per byte) */
+int hostsim_k3(const uint8_t *bits, uint32_t nbits, uint32_t datalen_bits, uint8_t *frames_out, uint32_t cap, uint32_t *lens,
+		uint16_t *crcs, uint32_t max_frames, uint32_t *n_frames, int32_t *fec_corr, int8_t *rs_ret9) {
+	static host_tables *h = nullptr;
+	if(!h) { h = new host_tables(); make_tables(*h, 2100000); }
+	static vdl2_burst_slot slot;
+	static vdl2_burst_work w;
+	memset(&slot, 0, sizeof(slot));
+	for(uint32_t i = 0; i < nbits && i < VDL2_MAX_BURST_BITS; i++) slot.words[i >> 5] |= (uint32_t)(bits[i] & 1u) << (31u - (i & 31u));
+	vdl2_burst_geometry(w, datalen_bits, nbits);
+	memset(w.tab, 0, sizeof(w.tab));
+	if(w.status == VDL2_BURST_OK) {
+		vdl2_burst_unpack(w, slot.words, h->t.lfsr_words, 0, 1);
+		for(uint32_t r = 0; r < w.num_blocks; r++)
+			w.rs_ret[r] = vdl2_rs_verify(w.tab[r], (r == w.num_blocks - 1) ? (int)w.last_fec : 6, h->t.gf_exp, h->t.gf_log);
+		for(uint32_t r = 0; r < w.num_blocks; r++) {
+			int nfec = (r == w.num_blocks - 1) ? (int)w.last_fec : 6;
+			if(w.rs_ret[r] < 0) { w.status = VDL2_ERR_FEC_BAD; for(uint32_t q = r + 1; q < w.num_blocks; q++) w.rs_ret[q] = -128; break; }
+			if(w.rs_ret[r] > 0) w.fec_corr += w.rs_ret[r] - (6 - nfec);
+		}
+		if(w.status == VDL2_BURST_OK) vdl2_burst_unstuff(w);
+	}
+	*n_frames = w.n_frames; *fec_corr = w.fec_corr;
+	for(int r = 0; r < 9; r++) rs_ret9[r] = (int8_t)w.rs_ret[r];
+	uint32_t off = 0;
+	for(uint32_t k = 0; k < w.n_frames && k < max_frames; k++) {
+		if(off + w.flen[k] > cap) return -1;
+		memcpy(frames_out + off, w.frames + off, w.flen[k]);
+		lens[k] = w.flen[k]; crcs[k] = vdl2_crc16(w.frames + off, w.flen[k]);
+		off += w.flen[k];
+	}
+	return w.status;
+}
+
 /* stand-alone pieces for unit tests */
 int hostsim_rs_verify(uint8_t *block255, int fec_octets) {
 	static host_tables *h = nullptr;

@@ -89,3 +89,17 @@ def k2k3(dec, freqs, rate, max_ppm=0.0, trace=True, use_pre=True):
     events = [dict(channel=ev[k].channel, kind=ev[k].kind, dec_index=ev[k].dec_index, i=list(ev[k].i),
                    f=np.array(list(ev[k].f), np.float32)) for k in range(nev.value)]
     return recs, events, cnt
+
+
+def k3(bits, datalen_bits):
+    """Run the K3 device functions on one burst (scrambled bits incl. the 25 header bits)."""
+    b = np.ascontiguousarray(bits, np.uint8)
+    out = np.zeros(4096, np.uint8); lens = np.zeros(1100, np.uint32); crcs = np.zeros(1100, np.uint16)
+    n = C.c_uint32(0); corr = C.c_int32(0); rs = np.zeros(9, np.int8)
+    st = lib().hostsim_k3(b.ctypes.data_as(C.c_void_p), C.c_uint32(b.size), C.c_uint32(datalen_bits), out.ctypes.data_as(C.c_void_p),
+                          C.c_uint32(out.size), lens.ctypes.data_as(C.c_void_p), crcs.ctypes.data_as(C.c_void_p), C.c_uint32(1100),
+                          C.byref(n), C.byref(corr), rs.ctypes.data_as(C.c_void_p))
+    frames, off = [], 0
+    for k in range(n.value):
+        frames.append(bytes(out[off:off + lens[k]])); off += int(lens[k])
+    return st, frames, corr.value, rs, crcs[:n.value].copy()

@@ -17,7 +17,7 @@ def _samples(case):
 
 
 @pytest.mark.parametrize("use_pre", [True, False])
-@pytest.mark.parametrize("name", ["cfg2", "mixed_s16", "fec", "noisy", "wav"])
+@pytest.mark.parametrize("name", ["cfg2", "mixed_s16", "fec", "noisy", "wav", "hdlc_edge"])
 def test_device_functions_on_host_match_oracle(name, use_pre):
     c = cases.ALL_GOLDEN[name]()
     o = util.run_oracle(c, trace=True, dec_tap=True)
@@ -139,3 +139,52 @@ def test_fp32_unwrap_update_equals_the_double_arithmetic_of_the_reference():
         assert jumped == (np.float64(x) > np.pi)
         jumped = L.hostsim_unwrap_step(np.float32(0), -x) != 0
         assert jumped == (np.float64(-x) < -np.pi)
+
+
+def _flag():
+    return "01111110"
+
+
+def _stuffed(octets):
+    return "".join(format(b, "08b")[::-1] for b in octets).replace("11111", "111110")
+
+
+@pytest.mark.parametrize("trial", range(40))
+def test_burst_decoder_matches_oracle_on_hdlc_edge_cases(trial):
+    """K3 device functions (de-interleave, RS, HDLC unstuff, FCS) against the oracle's restatement of
+    src/decode.c:259-380 + src/bitstream.c:109-150 on crafted payloads: repeated / missing flags, aborts (seven
+    ones), frames that are not whole octets, zero-length frames, length cuts, multi-block and short-block bursts,
+    RS errors within and beyond capacity."""
+    from dumpvdl2_b200 import synth
+    rng = np.random.default_rng(1000 + trial)
+    pieces = [_flag()]
+    for _ in range(int(rng.integers(1, 5))):
+        body = _stuffed(rng.integers(0, 256, int(rng.integers(0, 120)), dtype=np.uint8))
+        kind = int(rng.integers(0, 10))
+        if kind == 0:
+            body += "1" * 7                                   # abort sequence
+        elif kind == 1:
+            body += "010"                                     # not a whole number of octets
+        elif kind == 2:
+            body = ""                                         # back-to-back flags
+        pieces.append(body)
+        pieces.append(_flag() * int(rng.integers(1, 3)))
+    payload = "".join(pieces)
+    if trial % 5 == 0:
+        payload = payload[:-int(rng.integers(1, 8))]          # closing flag cut short
+    if trial % 7 == 0:
+        payload = _flag() + _stuffed(rng.integers(0, 256, int(rng.integers(250, 900)), dtype=np.uint8)) + _flag()
+    corrupt = []
+    nblk = -(-(-(-len(payload) // 8)) // 249)
+    for _ in range(int(rng.integers(0, 5))):
+        corrupt.append((int(rng.integers(0, nblk)), int(rng.integers(0, 20)), int(rng.integers(1, 256))))
+    try:
+        bits, info = synth.burst_bits_from_payload(payload, corrupt_octets=corrupt)
+    except ValueError:
+        pytest.skip("payload too short for FEC")
+    descr = bits ^ synth.scrambler_sequence(len(bits))
+    st_o, fr_o, corr_o, rs_o = po.decode_burst_bits(descr[25:], info["datalen_bits"])
+    st_k, fr_k, corr_k, rs_k, crcs = hs.k3(bits, info["datalen_bits"])
+    assert (st_k, fr_k, corr_k) == (st_o, fr_o, corr_o), (st_k, st_o, len(fr_k), len(fr_o))
+    assert list(rs_k) == list(rs_o)
+    assert [int(c) for c in crcs] == [po.crc16(f) for f in fr_k]
