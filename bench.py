@@ -366,7 +366,14 @@ def main():
                                "served from shared memory so DRAM traffic is far lower and the kernel is FP32-issue bound",
                           kernel_share_of_step={k: v[0] / tot_k for k, v in kms.items()},
                           kernel_ms_per_launch={k: v[0] / max(v[1], 1) for k, v in kms.items()},
-                          measured="CUDA events on the library's stream inside the timed region (device-resident pass)"),
+                          measured="CUDA events on the library's stream inside the timed region (device-resident pass)",
+                          fp32_pipe=dict(
+                              achieved=(len(my_freqs) * CHUNK_PAIRS * 24.0 / (k1_ms_per_launch * 1e-3) / 1e12) if k1_ms_per_launch > 0 else None,
+                              peak=148 * 128 * 1.965e9 / 1e12, unit="T lane-ops/s",
+                              frac=(len(my_freqs) * CHUNK_PAIRS * 24.0 / (k1_ms_per_launch * 1e-3) / (148 * 128 * 1.965e9)) if k1_ms_per_launch > 0 else None,
+                              note="the bound that actually binds K1: 24 individually rounded FP32 operations per channel-sample "
+                                   "(12 packed FMUL2/FFMA2; contraction to FMA is not allowed by the bit-exactness contract) "
+                                   "against 148 SMs x 128 FP32 lanes x 1.965 GHz")),
             clocks=clocks,
             parity=dict(pool_overflows=int(d_dev["pool_overflows"] + d_e2e["pool_overflows"]), out_overflows=int(d_dev["out_overflows"] + d_e2e["out_overflows"]),
                         bursts_per_step=d_dev["bursts"] / K, fcs_good_per_step=d_dev["fcs_good"] / K, fcs_bad_per_step=d_dev["fcs_bad"] / K),
