@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvdl2gpu.so")
 FMT_U8, FMT_S16 = 0, 1
-FLAG_TRACE, FLAG_KEEP_DEC, FLAG_K1_SCALAR, FLAG_OVERLAP = 1, 2, 4, 8
+FLAG_TRACE, FLAG_KEEP_DEC, FLAG_K1_SCALAR, FLAG_NO_OVERLAP = 1, 2, 4, 8
 NUM_COUNTERS = 9
 COUNTER_NAMES = ["sync_good", "hdr_crc_good", "bursts", "burst_err", "blocks_processed",
                  "blocks_fec_ok", "msg_good", "fcs_good", "fcs_bad"]

@@ -56,11 +56,13 @@ struct vdl2gpu_ctx {
 	vdl2gpu_config cfg;
 	std::vector<uint32_t> freqs;
 	int device = 0;
-	/* `stream` (front) carries H2D + K0 + K1, `s_back` K2a/K2/K3.  By default they are the same stream.  With
-	 * VDL2GPU_FLAG_OVERLAP they differ and chunk c+1's front stage may run beside chunk c's back stage; measured on
-	 * B200 this gains little (K1 keeps the FP32 pipe ~65 % busy on its own) and is erratic, so it is opt-in */
+	/* `stream` (front) carries H2D + K0 + K1 of chunk c+1 while `s_back` carries K2a/K2/K3 of chunk c.  Both stages
+	 * are latency-bound with one warp per SM sub-partition at 16 k channels, so co-residency raises issue-slot use:
+	 * 12.1 -> 8.7 ms per chunk on B200.  This only works because every kernel of the chain requests the SAME
+	 * shared-memory carve-out (vdl2_kernels.cu): with per-kernel defaults the SMs drain to re-partition L1/shared
+	 * memory and the overlap is a 1.7x slow-down.  VDL2GPU_FLAG_NO_OVERLAP puts everything on one stream. */
 	cudaStream_t stream = nullptr, s_back = nullptr;
-	cudaEvent_t ev_k1_done[2] = { nullptr, nullptr }, ev_back_done[2] = { nullptr, nullptr };
+	cudaEvent_t ev_k1_done[2] = { nullptr, nullptr }, ev_back_done[2] = { nullptr, nullptr }, ev_k2a_done = nullptr;
 	uint64_t chunk_seq = 0;
 	cudaEvent_t ev_input_ready = nullptr, ev_input_consumed = nullptr;
 	uint32_t n_ch = 0, n_chp = 0, max_pairs = 0, max_dec = 0, n_slots = 0, out_cap = 0, event_cap = 0;
@@ -135,6 +137,7 @@ static int free_ctx(vdl2gpu_ctx *c) {
 	if(c->ev_input_ready) cudaEventDestroy(c->ev_input_ready);
 	if(c->ev_input_consumed) cudaEventDestroy(c->ev_input_consumed);
 	if(c->ev_drain) cudaEventDestroy(c->ev_drain);
+	if(c->ev_k2a_done) cudaEventDestroy(c->ev_k2a_done);
 	for(int i = 0; i < 2; i++) { if(c->ev_k1_done[i]) cudaEventDestroy(c->ev_k1_done[i]); if(c->ev_back_done[i]) cudaEventDestroy(c->ev_back_done[i]); }
 	if(c->s_back && c->s_back != c->stream) cudaStreamDestroy(c->s_back);
 	if(c->stream) cudaStreamDestroy(c->stream);
@@ -176,9 +179,16 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	make_tables(c->tab, cfg->sample_rate);
 	memset(&c->stats, 0, sizeof(c->stats));
 
-	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-	if(cfg->flags & VDL2GPU_FLAG_OVERLAP) CU(cudaStreamCreateWithFlags(&c->s_back, cudaStreamNonBlocking));
-	else c->s_back = c->stream;
+	{
+		int lo = 0, hi = 0;
+		CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));      /* lo = least priority (numerically largest) */
+		const char *pe = getenv("VDL2GPU_PRIO");
+		const int prio = pe ? atoi(pe) : 0;
+		CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio == 1 ? hi : lo));
+		if(cfg->flags & VDL2GPU_FLAG_NO_OVERLAP) c->s_back = c->stream;
+		else CU(cudaStreamCreateWithPriority(&c->s_back, cudaStreamNonBlocking, prio == 2 ? hi : lo));
+	}
+	CU(cudaEventCreateWithFlags(&c->ev_k2a_done, cudaEventDisableTiming));
 	for(int i = 0; i < 2; i++) {
 		CU(cudaEventCreateWithFlags(&c->ev_k1_done[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&c->ev_back_done[i], cudaEventDisableTiming));
@@ -392,6 +402,9 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	CU(cudaEventRecord(c->ev_input_consumed, c->stream));
 	if(s.timed) CU(cudaEventRecord(s.tk[1], c->stream));
 	if(c->chunk_seq >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_back_done[db], 0));   /* K2 of chunk c-2 has read this buffer */
+	/* K1 (one warp per SM sub-partition, latency-bound) pairs well with the equally latency-bound walker K2 and K3 of
+	 * the previous chunk, but not with K2a, a full-occupancy issue-bound pass: let K2a of chunk c-1 finish first */
+	if(c->chunk_seq >= 1 && c->s_back != c->stream) CU(cudaStreamWaitEvent(c->stream, c->ev_k2a_done, 0));
 	vdl2_k1_params p1;
 	p1.samples = c->d_samples; p1.n_pairs = n_pairs; p1.oversample = os; p1.cnt0 = c->decim_cnt;
 	p1.n_ch = c->n_ch; p1.n_chp = c->n_chp; p1.dec = d_dec; p1.state = c->d_k1;
@@ -409,6 +422,8 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	p2.state = c->d_k2; p2.ring = c->d_ring; p2.tables = c->d_tab; p2.max_ppm = c->cfg.max_ppm; p2.s27 = c->tab.s27;
 	p2.pool = c->d_pool; p2.free_list = c->d_free; p2.ready = c->d_ready; p2.ctl = c->d_ctl;
 	p2.events = c->d_events; p2.event_cap = c->event_cap; p2.trace = (c->cfg.flags & VDL2GPU_FLAG_TRACE) ? 1u : 0u;
+	KL(vdl2_launch_k2a(&p2, c->s_back));
+	CU(cudaEventRecord(c->ev_k2a_done, c->s_back));
 	KL(vdl2_launch_k2(&p2, c->s_back));
 	CU(cudaEventRecord(c->ev_back_done[db], c->s_back));
 	if(s.timed) CU(cudaEventRecord(s.tk[4], c->s_back));

@@ -529,6 +529,14 @@ __global__ void k_rs_verify(uint8_t *blocks, const int32_t *fec_octets, uint32_t
 /* ------------------------------------------------------------------------------------------------
  * launch stubs
  * ---------------------------------------------------------------------------------------------- */
+/* One shared-memory carve-out for every kernel of the chain, so that an SM never has to drain to re-partition
+ * its L1/shared memory when kernels of two chunks are resident together (VDL2GPU_FLAG_OVERLAP). */
+template<typename K> static void vdl2_set_carveout(K kernel) {
+	static const char *ev = getenv("VDL2GPU_CARVEOUT");
+	const int pct = ev ? atoi(ev) : 100;          /* default: maximum shared memory, the same for every kernel */
+	if(pct >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 #define K1_BLOCK 32
 #define K2_BLOCK 32
 
@@ -542,7 +550,12 @@ extern "C" int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, cudaStr
 	if(p->n_pairs == 0 || p->n_ch == 0) return 0;
 	const uint32_t blocks = (p->n_ch + K1_BLOCK - 1) / K1_BLOCK;
 	static int variant = -1;
-	if(variant < 0) { const char *e = getenv("VDL2GPU_K1_VARIANT"); variant = e ? atoi(e) : 2; }
+	if(variant < 0) {
+		const char *e = getenv("VDL2GPU_K1_VARIANT"); variant = e ? atoi(e) : 2;
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, true>);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, false>);
+		vdl2_set_carveout(k0_convert);
+	}
 	const bool sym = (p->a1 == 2.0f * p->a0) && (p->a2 == p->a0) && variant != 4;
 	if(!force_scalar && p->oversample == 20) {
 		if(variant == 0) k1_mix_iir_decimate_packed<20, K1_BLOCK, 0, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
@@ -559,19 +572,32 @@ extern "C" int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, cudaStr
 	return (int)cudaGetLastError();
 }
 
+extern "C" int vdl2_launch_k2a(const vdl2_k2_params *p, cudaStream_t st) {
+	if(p->n_dec == 0 || p->n_ch == 0) return 0;
+	const uint32_t n_elems = p->n_dec * p->n_chp;
+	const uint32_t hist = VDL2_SYNC_BUFLEN * p->n_chp;
+	static bool once = false;
+	if(!once) { once = true; vdl2_set_carveout(k2a_phase_mag); }
+	k2a_phase_mag<<<(n_elems + 255u) / 256u, 256, 0, st>>>(p->dec, p->phase + hist, p->mag, n_elems);
+	return (int)cudaGetLastError();
+}
+
 extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
 	if(p->n_dec == 0 || p->n_ch == 0) return 0;
 	const uint32_t blocks = (p->n_ch + K2_BLOCK - 1) / K2_BLOCK;
-	const uint32_t n_elems = p->n_dec * p->n_chp;
 	const uint32_t hist = VDL2_SYNC_BUFLEN * p->n_chp;
-	k2a_phase_mag<<<(n_elems + 255u) / 256u, 256, 0, st>>>(p->dec, p->phase + hist, p->mag, n_elems);
-	int e = (int)cudaGetLastError();
-	if(e) return e;
 	static int variant = -1;
-	if(variant < 0) { const char *ev = getenv("VDL2GPU_K2_VARIANT"); variant = ev ? atoi(ev) : 1; }
+	if(variant < 0) {
+		const char *ev = getenv("VDL2GPU_K2_VARIANT"); variant = ev ? atoi(ev) : 1;
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true>);
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, false>);
+		vdl2_set_carveout(k_copy_rows);
+		vdl2_set_carveout(k3_burst_fec);
+		vdl2_set_carveout(k_chunk_finish);
+	}
 	if(variant == 0) k2_sync_slice<K2_BLOCK, false><<<blocks, K2_BLOCK, 0, st>>>(*p);
 	else k2_sync_slice<K2_BLOCK, true><<<blocks, K2_BLOCK, 0, st>>>(*p);
-	e = (int)cudaGetLastError();
+	int e = (int)cudaGetLastError();
 	if(e) return e;
 	/* history for the next chunk: rows [n_dec, n_dec+160) -> [0, 160) */
 	if(p->n_dec >= VDL2_SYNC_BUFLEN) {

@@ -57,6 +57,7 @@ extern "C" {
 #endif
 int vdl2_launch_k0(const void *raw, uint32_t n_pairs, uint32_t fmt, const float *levels, float *out4, cudaStream_t st);
 int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, cudaStream_t st);
+int vdl2_launch_k2a(const vdl2_k2_params *p, cudaStream_t st);
 int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st);
 int vdl2_launch_k3(const vdl2_k3_params *p, uint32_t grid, cudaStream_t st);
 int vdl2_launch_k4(const uint8_t *frames, const uint32_t *offsets, const uint32_t *lens, uint32_t n, uint16_t *out, cudaStream_t st);

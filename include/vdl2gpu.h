@@ -50,7 +50,7 @@ enum {
 	VDL2GPU_FLAG_TRACE = 1u << 0,        /* record sync/header/burst events (debug, parity tests) */
 	VDL2GPU_FLAG_KEEP_DEC = 1u << 1,     /* keep the decimated samples of the last chunk readable (parity tests) */
 	VDL2GPU_FLAG_K1_SCALAR = 1u << 2,    /* use the plain per-sample K1 kernel instead of the pipelined one */
-	VDL2GPU_FLAG_OVERLAP = 1u << 3       /* experimental: K0/K1 of chunk c+1 on a second stream beside K2/K3 of chunk c */
+	VDL2GPU_FLAG_NO_OVERLAP = 1u << 3    /* one stream: do not run K0/K1 of chunk c+1 beside K2/K3 of chunk c (profiling) */
 };
 
 typedef struct {

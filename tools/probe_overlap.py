@@ -7,7 +7,7 @@ chunks, offs, _ = bench.make_stream(2.0)
 freqs = bench.channel_freqs(offs, 16384)
 d_chunks = torch.from_numpy(chunks).cuda()
 st = torch.cuda.current_stream()
-for name, flags, dev in (("serial host", 0, False), ("overlap host", vd.FLAG_OVERLAP, False), ("overlap device", vd.FLAG_OVERLAP, True), ("serial device", 0, True)):
+for name, flags, dev in (("serial host", vd.FLAG_NO_OVERLAP, False), ("overlap host", 0, False), ("overlap device", 0, True), ("serial device", vd.FLAG_NO_OVERLAP, True)):
     g = vd.Vdl2Channels(bench.FS, bench.OVERSAMPLE, vd.FMT_U8, bench.CENTER, freqs, max_chunk_bytes=bench.CHUNK_BYTES, flags=flags)
     def run(n):
         for i in range(n):

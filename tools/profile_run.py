@@ -16,7 +16,7 @@ a = ap.parse_args()
 chunks, offs, _ = bench.make_stream(1.0)
 freqs = bench.channel_freqs(offs, a.channels)
 g = vd.Vdl2Channels(bench.FS, bench.OVERSAMPLE, vd.FMT_U8, bench.CENTER, freqs, max_chunk_bytes=bench.CHUNK_BYTES,
-                    flags=vd.FLAG_K1_SCALAR if a.k1_scalar else 0)
+                    flags=(vd.FLAG_K1_SCALAR if a.k1_scalar else 0) | vd.FLAG_NO_OVERLAP)
 g.enable_timing(True)
 n = 0
 for i in range(a.chunks):
