@@ -251,7 +251,7 @@ def main():
             dist.broadcast(buf, src=0)
             for k in range(CPS):
                 g.submit_device(buf.data_ptr() + k * CHUNK_BYTES, CHUNK_BYTES, stream.cuda_stream)
-        return g.flush_count()
+        return g.poll_count()
 
     def step_host():
         """one step through the public host-buffer entry point (process_buf_uchar); with N > 1 the ingest rank copies
@@ -269,7 +269,7 @@ def main():
             dist.broadcast(buf, src=0)
             for k in range(CPS):
                 g.submit_device(buf.data_ptr() + k * CHUNK_BYTES, CHUNK_BYTES, stream.cuda_stream)
-        return g.flush_count()
+        return g.poll_count()
 
     def timed(step_fn, steps, sample_clocks=False):
         # one sampler for the job (rank 0's GPU): eight concurrent nvidia-smi pollers contend for the driver lock.
@@ -287,7 +287,8 @@ def main():
         e0.record(stream)
         frames = 0
         for _ in range(steps):
-            frames += step_fn()
+            frames += step_fn()          # submits + non-blocking harvest: the pipeline stays full across steps
+        frames += g.flush_count()       # everything submitted is processed and its frames are on the host
         g.stream_wait(stream.cuda_stream)
         e1.record(stream)
         barrier()
@@ -303,9 +304,11 @@ def main():
 
     for _ in range(W):
         step_device()
+    g.flush_count()
     ms_dev, frames_dev, d_dev, clocks, wall_dev = timed(step_device, K, sample_clocks=True)
     for _ in range(2):
         step_host()
+    g.flush_count()
     ms_e2e, frames_e2e, d_e2e, _, wall_e2e = timed(step_host, K)
 
     # Per-kernel durations for the roofline.  The production pipeline runs K0/K1 of chunk c+1 beside K2/K3 of chunk c
@@ -317,6 +320,7 @@ def main():
                         flags=flags | vd.FLAG_NO_OVERLAP)
     for _ in range(2):
         step_device()
+    g.flush_count()
     g.enable_timing(True)
     k0 = g.kernel_ms()
     ms_serial, _, _, _, _ = timed(step_device, max(2, K // 2))

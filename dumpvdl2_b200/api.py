@@ -224,6 +224,10 @@ class Vdl2Channels:
         out, self._frames = self._frames, []
         return out
 
+    def poll_count(self):
+        """Like poll() but only counts frames (no Python object per frame)."""
+        return _check(self.L, self.L.vdl2gpu_poll(self.h, C.cast(None, _FRAME_CB), None), "vdl2gpu_poll")
+
     def flush_count(self):
         """Like flush() but only counts frames (no Python object per frame)."""
         return _check(self.L, self.L.vdl2gpu_flush(self.h, C.cast(None, _FRAME_CB), None), "vdl2gpu_flush")
