@@ -179,15 +179,10 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	make_tables(c->tab, cfg->sample_rate);
 	memset(&c->stats, 0, sizeof(c->stats));
 
-	{
-		int lo = 0, hi = 0;
-		CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));      /* lo = least priority (numerically largest) */
-		const char *pe = getenv("VDL2GPU_PRIO");
-		const int prio = pe ? atoi(pe) : 0;
-		CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio == 1 ? hi : lo));
-		if(cfg->flags & VDL2GPU_FLAG_NO_OVERLAP) c->s_back = c->stream;
-		else CU(cudaStreamCreateWithPriority(&c->s_back, cudaStreamNonBlocking, prio == 2 ? hi : lo));
-	}
+	/* equal (default) priorities: raising either stage's priority slowed the pair down (tools/probe_overlap.py) */
+	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	if(cfg->flags & VDL2GPU_FLAG_NO_OVERLAP) c->s_back = c->stream;
+	else CU(cudaStreamCreateWithFlags(&c->s_back, cudaStreamNonBlocking));
 	CU(cudaEventCreateWithFlags(&c->ev_k2a_done, cudaEventDisableTiming));
 	for(int i = 0; i < 2; i++) {
 		CU(cudaEventCreateWithFlags(&c->ev_k1_done[i], cudaEventDisableTiming));
