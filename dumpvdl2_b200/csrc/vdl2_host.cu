@@ -171,6 +171,11 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	c->cfg.max_chunk_bytes = max_bytes;
 	c->max_pairs = max_bytes / (cfg->sample_fmt == VDL2GPU_FMT_S16_LE ? 4u : 2u);
 	c->max_dec = c->max_pairs / cfg->oversample + 2;
+	if((uint64_t)(c->max_dec + VDL2_SYNC_BUFLEN) * c->n_chp >= (1ull << 32)) {
+		snprintf(g_last_error, sizeof(g_last_error), "%u channels x %u decimated samples per chunk exceed the 32-bit element index of the kernels; "
+				"use a smaller max_chunk_bytes or shard the channels", c->n_ch, c->max_dec);
+		return VDL2GPU_ETOOBIG;
+	}
 	c->n_slots = std::max(256u, 3u * c->n_ch);
 	c->out_cap = std::max(4u << 20, c->n_ch * 512u);
 	const uint32_t n_inflight = cfg->n_inflight ? cfg->n_inflight : 4u;
