@@ -554,6 +554,13 @@ extern "C" int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, cudaStr
 		const char *e = getenv("VDL2GPU_K1_VARIANT"); variant = e ? atoi(e) : 2;
 		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, true>);
 		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, false>);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK, 0, false>);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK, 10, true>);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK, 10, false>);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK, 0, false>);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<13, K1_BLOCK, 10, true>);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<13, K1_BLOCK, 10, false>);
+		vdl2_set_carveout(k1_mix_iir_decimate_scalar<K1_BLOCK>);
 		vdl2_set_carveout(k0_convert);
 	}
 	const bool sym = (p->a1 == 2.0f * p->a0) && (p->a2 == p->a0) && variant != 4;
@@ -568,6 +575,9 @@ extern "C" int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, cudaStr
 		if(variant == 0) k1_mix_iir_decimate_packed<10, K1_BLOCK, 0, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
 		else if(sym) k1_mix_iir_decimate_packed<10, K1_BLOCK, 10, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
 		else k1_mix_iir_decimate_packed<10, K1_BLOCK, 10, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
+	} else if(!force_scalar && p->oversample == 13 && variant != 0) {      /* 1.365 Msps (Mirics, src/mirics.h:23) */
+		if(sym) k1_mix_iir_decimate_packed<13, K1_BLOCK, 10, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		else k1_mix_iir_decimate_packed<13, K1_BLOCK, 10, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
 	} else k1_mix_iir_decimate_scalar<K1_BLOCK><<<blocks, K1_BLOCK, 0, st>>>(*p);
 	return (int)cudaGetLastError();
 }

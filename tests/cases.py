@@ -60,6 +60,21 @@ def case_mixed_s16():
     return _mk("mixed_s16", fs, "s16", [CENTER + o for o in offs], iq, chunk=4 * 33331, bursts=bursts)
 
 
+def case_mirics_os13():
+    """1.365 Msps cs16 (Mirics front-end rate, src/mirics.h:23: oversample 13): a decimation factor without a
+    specialised K1, i.e. the generic per-sample kernel in production use; centre channel + offsets, odd chunks."""
+    fs = 1365000
+    offs = [0.0, -125e3, 100e3, 300e3]
+    rng = np.random.default_rng(1365)
+    bursts = []
+    for i, o in enumerate(offs):
+        for k in range(2):
+            bursts.append(synth.BurstSpec(0.015 + 0.05 * i + 0.22 * k, o, synth.random_frames(rng), power_dbfs=-13.0,
+                                          freq_err_hz=float(rng.uniform(-200, 200))))
+    iq = synth.synth_stream(fs, 0.5, bursts, es_n0_db=26, fmt="s16", seed=1366)
+    return _mk("mirics_os13", fs, "s16", [CENTER + o for o in offs], iq, chunk=4 * 50001, bursts=bursts)
+
+
 def case_fec():
     """RS error correction, header bit errors, multi-block and short-last-block bursts (paths no reference
     fixture pins; pinned here by running the reference itself)."""
@@ -151,4 +166,4 @@ def case_replicas(n_slots=16, n_rep=4, duration=0.5, seed=0x56444C33, es_n0_db=2
 
 
 ALL_GOLDEN = {"wav": case_wav, "cfg2": case_cfg2, "mixed_s16": case_mixed_s16, "fec": case_fec, "noisy": case_noisy,
-              "hdlc_edge": case_hdlc_edge}
+              "hdlc_edge": case_hdlc_edge, "mirics_os13": case_mirics_os13}

@@ -51,7 +51,7 @@ def test_tables_match_oracle():
     assert t["lr_denom"][0] == d
 
 
-@pytest.mark.parametrize("name", ["cfg2", "mixed_s16", "wav"])
+@pytest.mark.parametrize("name", ["cfg2", "mixed_s16", "wav", "mirics_os13"])
 @pytest.mark.parametrize("scalar", [False, True])
 def test_k1_decimated_samples_bit_exact(name, scalar, oracle_runs):
     c, o = oracle_runs(name)

@@ -17,7 +17,7 @@ def _samples(case):
 
 
 @pytest.mark.parametrize("use_pre", [True, False])
-@pytest.mark.parametrize("name", ["cfg2", "mixed_s16", "fec", "noisy", "wav", "hdlc_edge"])
+@pytest.mark.parametrize("name", ["cfg2", "mixed_s16", "fec", "noisy", "wav", "hdlc_edge", "mirics_os13"])
 def test_device_functions_on_host_match_oracle(name, use_pre):
     c = cases.ALL_GOLDEN[name]()
     o = util.run_oracle(c, trace=True, dec_tap=True)
