@@ -109,7 +109,6 @@ struct vdl2_k2_env {
 	vdl2_event_rec *events;
 	uint32_t event_cap;
 	uint32_t trace;
-	uint32_t *cnt_bursts;        /* per-channel counter plane */
 };
 
 VDL2_HD uint32_t vdl2_dec_state(const vdl2_chan &v) { return (v.state >> VDL2_DEC_SHIFT) & 3u; }

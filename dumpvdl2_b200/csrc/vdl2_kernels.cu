@@ -3,11 +3,12 @@
  *
  *   K0  k0_convert            raw cu8/cs16 -> float samples        src/demod.c:339-365
  *   K1  k1_mix_iir_decimate   NCO mix + 2-pole IIR + decimate      src/demod.c:58-79,200-203,288-337
+ *   K2a k2a_phase_mag         atan2 / hypot of every decimated sample  src/demod.c:232,238,256
  *   K2  k2_sync_slice         preamble sync, D8PSK slicing, header src/demod.c:105-198,222-286; src/decode.c:198-258
  *   K3  k3_burst_fec          descramble, de-interleave, RS, HDLC  src/decode.c:259-380; src/rs.c; src/libfec; src/bitstream.c
  *   K4  (inside K3)           AVLC FCS residue per frame           src/crc.c:21-64
  *
- * Unit of parallelism: K0 sample; K1/K2 one thread per VDL2 channel (32 channels per warp, the sample
+ * Unit of parallelism: K0, K2a element; K1/K2 one thread per VDL2 channel (32 channels per warp, the sample
  * stream is broadcast to the warp from shared memory); K3 one thread block per burst.
  * No tensor cores: there is no dense contraction on this path.  Built with -fmad=false; all float
  * arithmetic additionally goes through explicit round-to-nearest intrinsics / PTX.
@@ -353,7 +354,6 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	env.max_ppm = p.max_ppm; env.s27 = p.s27;
 	env.pool = p.pool; env.free_list = p.free_list; env.ready = p.ready; env.ctl = p.ctl;
 	env.events = reinterpret_cast<vdl2_event_rec *>(p.events); env.event_cap = p.event_cap; env.trace = p.trace;
-	env.cnt_bursts = nullptr;
 
 	const float2 *dec = p.dec + ch;
 	const float *phs = p.phase + (size_t)VDL2_SYNC_BUFLEN * s + ch;      /* row 0 of phs = first sample of this chunk */
@@ -530,7 +530,7 @@ __global__ void k_rs_verify(uint8_t *blocks, const int32_t *fec_octets, uint32_t
  * launch stubs
  * ---------------------------------------------------------------------------------------------- */
 /* One shared-memory carve-out for every kernel of the chain, so that an SM never has to drain to re-partition
- * its L1/shared memory when kernels of two chunks are resident together (VDL2GPU_FLAG_OVERLAP). */
+ * its L1/shared memory when kernels of two chunks are resident together (the default two-stream pipeline, see vdl2_host.cu). */
 template<typename K> static void vdl2_set_carveout(K kernel) {
 	static const char *ev = getenv("VDL2GPU_CARVEOUT");
 	const int pct = ev ? atoi(ev) : 100;          /* default: maximum shared memory, the same for every kernel */

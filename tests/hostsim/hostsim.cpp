@@ -76,7 +76,7 @@ int hostsim_k2k3(const float *dec /*[n_dec][n_ch][2]*/, uint32_t n_dec, uint32_t
 	vdl2_k2_env env;
 	env.pr_phase = h->t.pr_phase; env.lr_X = h->t.lr_X; env.lr_denom = h->t.lr_denom; env.max_ppm = max_ppm; env.s27 = h->s27;
 	env.pool = pool.data(); env.free_list = free_list.data(); env.ready = ready.data(); env.ctl = &ctl;
-	env.events = events; env.event_cap = event_cap; env.trace = events != nullptr; env.cnt_bursts = nullptr;
+	env.events = events; env.event_cap = event_cap; env.trace = events != nullptr;
 	std::vector<vdl2_chan> chans(n_ch);
 	std::vector<float> rings((size_t)n_ch * VDL2_SYNC_BUFLEN, 0.f);
 	for(uint32_t ch = 0; ch < n_ch; ch++) vdl2_chan_init(chans[ch], freqs[ch]);
