@@ -179,17 +179,37 @@ __device__ __forceinline__ u64 k1_packed_math(const float4 s, const float4 e, co
 	return y0;
 }
 
+/* TMA (bulk asynchronous copy) staging of the sample stream: one elected lane asks the copy engine for the next
+ * tile (cp.async.bulk global -> shared, completion counted in bytes on an mbarrier) while the warp works on the
+ * current one; two tiles in flight hide the L2 round trip completely.  SASS: UBLKCP + SYNCS. */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_tile(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			:: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+			:: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 #define K1P_TILE_GROUPS(OS) (640 / (OS))        /* 640 samples = 10 KB of float4 per tile: leaves room for K2's blocks on the same SM */
 
 template<int OS, int BLOCK, int BATCH, bool SYM>
 __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_params p) {
 	constexpr int TG = K1P_TILE_GROUPS(OS);
 	__shared__ float4 s_lut[257];
-	__shared__ float4 s_tile[TG * OS];
+	__shared__ __align__(128) float4 s_tiles[2][TG * OS];
+	__shared__ __align__(8) uint64_t s_bar[2];
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ch = blockIdx.x * BLOCK + tid;
 	const bool active = ch < p.n_ch;
 	for(uint32_t i = tid; i < 257; i += BLOCK) s_lut[i] = p.lut[i];
+	if(tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
 	float xr1 = 0, xr2 = 0, xi1 = 0, xi2 = 0, yr1 = 0, yr2 = 0, yi1 = 0, yi2 = 0;
 	uint32_t phi = 0, dphi = 0;
 	if(active) k1_load_state(p, ch, xr1, xr2, xi1, xi2, yr1, yr2, yi1, yi2, phi, dphi);
@@ -221,11 +241,18 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	P1 = f2_mul(c.A0, x1); P2 = f2_mul(c.A0, x2);            /* after the head samples */
 	/* body: whole groups, staged through shared memory tile by tile */
 	const uint32_t n_groups = (p.n_pairs - pos) / OS;
-	for(uint32_t g0 = 0; g0 < n_groups; g0 += TG) {
+	const uint32_t n_tiles = (n_groups + TG - 1) / TG;
+	/* prologue: the first two tiles are requested at once; tile t lands in buffer t & 1, its mbarrier phase is (t >> 1) & 1 */
+	if(tid == 0) {
+		for(uint32_t t = 0; t < 2 && t < n_tiles; t++) {
+			const uint32_t ngt = min((uint32_t)TG, n_groups - t * TG);
+			tma_load_tile(s_tiles[t], p.samples + pos + (size_t)t * TG * OS, ngt * OS * (uint32_t)sizeof(float4), &s_bar[t]);
+		}
+	}
+	for(uint32_t g0 = 0, tile = 0; g0 < n_groups; g0 += TG, tile++) {
 		const uint32_t ng = min((uint32_t)TG, n_groups - g0);
-		__syncthreads();
-		for(uint32_t i = tid; i < ng * OS; i += BLOCK) s_tile[i] = p.samples[pos + i];
-		__syncthreads();
+		const float4 *s_tile = s_tiles[tile & 1u];
+		mbar_wait(&s_bar[tile & 1u], (tile >> 1) & 1u);
 		if(active) {
 			for(uint32_t g = 0; g < ng; g++) {
 				const float4 *sp = &s_tile[g * OS];
@@ -280,6 +307,11 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 		}
 		m += ng;
 		pos += ng * OS;
+		__syncthreads();                                           /* every lane is done with this buffer */
+		if(tid == 0 && tile + 2 < n_tiles) {
+			const uint32_t ngn = min((uint32_t)TG, n_groups - (tile + 2) * TG);
+			tma_load_tile(s_tiles[tile & 1u], p.samples + pos + (size_t)TG * OS, ngn * OS * (uint32_t)sizeof(float4), &s_bar[tile & 1u]);
+		}
 	}
 	/* tail: fewer than OS samples left */
 	if(active) {
