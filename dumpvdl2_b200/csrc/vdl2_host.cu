@@ -430,7 +430,7 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	vdl2_k3_params p3;
 	p3.pool = c->d_pool; p3.free_list = c->d_free; p3.ready = c->d_ready; p3.ctl = c->d_ctl; p3.tables = c->d_tab;
 	p3.out = s.d_out; p3.out_cap = c->out_cap; p3.n_chp = c->n_chp; p3.counters = c->d_counters;
-	KL(vdl2_launch_k3(&p3, 148u * 8u, c->s_back));
+	KL(vdl2_launch_k3(&p3, 148u * 16u, c->s_back));      /* 16 resident blocks per SM (11.4 KB shared memory each): ~1.5 bursts per block per chunk at the bench traffic */
 	if(s.timed) CU(cudaEventRecord(s.tk[5], c->s_back));
 	CU(cudaEventRecord(s.done, c->s_back));
 	c->chunk_seq++;
