@@ -642,19 +642,34 @@ VDL2_HD void vdl2_burst_unpack(vdl2_burst_work &w, const uint32_t *words, const 
 /* RS(255,249) errors-and-erasures decoder, one block per caller.  src/rs.c:32-49 ->
  * src/libfec/decode_rs.h:71-298 (Karn): syndromes by Horner, erasure-seeded Berlekamp-Massey, Chien search
  * with early exit, failure iff deg(lambda) != number of roots, Forney.  Polynomial (not log) form. */
-VDL2_HD int vdl2_rs_verify(uint8_t *data, int fec_octets, const uint8_t *gexp, const uint8_t *glog) {
+/* rootmul[i][x] = x * alpha^(120+i): the six syndrome recurrences of decode_rs.h:82-93 become one table look-up per
+ * symbol and root, and run interleaved (six independent Horner chains) */
+VDL2_HD void vdl2_rs_build_rootmul(uint8_t *rootmul, const uint8_t *gexp, const uint8_t *glog, uint32_t tid, uint32_t nthr) {
+	for(uint32_t k = tid; k < 6u * 256u; k += nthr) {
+		const uint32_t i = k >> 8, x = k & 255u;
+		rootmul[k] = x ? gexp[(uint32_t)glog[x] + 120u + i] : (uint8_t)0;
+	}
+}
+
+VDL2_HD int vdl2_rs_verify(uint8_t *data, int fec_octets, const uint8_t *gexp, const uint8_t *glog, const uint8_t *rootmul) {
 	enum { NR = VDL2_RS_N - VDL2_RS_K, FCR = 120 };
 	if(fec_octets == 0) return 0;
 	const int no_eras = NR - fec_octets;
 	uint8_t S[NR];
 	int any = 0;
-	for(int i = 0; i < NR; i++) {
-		uint8_t acc = data[0];
-		const int lr = FCR + i;                       /* log of the root */
-		for(int j = 1; j < VDL2_RS_N; j++)
-			acc = (uint8_t)((acc ? gexp[glog[acc] + lr] : 0) ^ data[j]);
-		S[i] = acc;
-		any |= acc;
+	{
+		uint32_t s0 = data[0], s1 = s0, s2 = s0, s3 = s0, s4 = s0, s5 = s0;
+		for(int j = 1; j < VDL2_RS_N; j++) {
+			const uint32_t d = data[j];
+			s0 = rootmul[s0] ^ d;
+			s1 = rootmul[256 + s1] ^ d;
+			s2 = rootmul[512 + s2] ^ d;
+			s3 = rootmul[768 + s3] ^ d;
+			s4 = rootmul[1024 + s4] ^ d;
+			s5 = rootmul[1280 + s5] ^ d;
+		}
+		S[0] = (uint8_t)s0; S[1] = (uint8_t)s1; S[2] = (uint8_t)s2; S[3] = (uint8_t)s3; S[4] = (uint8_t)s4; S[5] = (uint8_t)s5;
+		any = (int)(s0 | s1 | s2 | s3 | s4 | s5);
 	}
 	if(!any) return 0;
 	uint8_t lambda[NR + 1] = { 1, 0, 0, 0, 0, 0, 0 };
@@ -694,14 +709,24 @@ VDL2_HD int vdl2_rs_verify(uint8_t *data, int fec_octets, const uint8_t *gexp, c
 	int deg = 0;
 	for(int i = 0; i <= NR; i++) if(lambda[i]) deg = i;
 	int root[NR], loc[NR], count = 0;
-	for(int i = 1; i <= 255; i++) {
-		uint8_t q = 1;
-		for(int j = deg; j > 0; j--)
-			if(lambda[j]) q ^= gexp[(glog[lambda[j]] + i * j) % 255];
-		if(q != 0) continue;
-		root[count] = i;
-		loc[count] = i - 1;
-		if(++count == deg) break;
+	{
+		/* Chien search, decode_rs.h:216-239: reg[j] = log(lambda_j) + i*j mod 255, advanced by j per step */
+		int reg[NR + 1];
+		for(int j = 1; j <= NR; j++) reg[j] = lambda[j] ? (int)glog[lambda[j]] : -1;
+		for(int i = 1; i <= 255; i++) {
+			uint8_t q = 1;
+			for(int j = deg; j > 0; j--) {
+				if(reg[j] >= 0) {
+					reg[j] += j;
+					if(reg[j] >= 255) reg[j] -= 255;
+					q ^= gexp[reg[j]];
+				}
+			}
+			if(q != 0) continue;
+			root[count] = i;
+			loc[count] = i - 1;
+			if(++count == deg) break;
+		}
 	}
 	if(deg != count) return -1;
 	const int deg_omega = deg - 1;
@@ -781,7 +806,21 @@ VDL2_HD int vdl2_burst_unstuff(vdl2_burst_work &w) {
 	return VDL2_BURST_OK;
 }
 
-/* K4: AVLC FCS residue, src/crc.c:21-64 (reflected 0x1021), bitwise */
+/* K4: AVLC FCS residue, src/crc.c:21-64 (reflected 0x1021): byte-wise with a 256-entry table built by
+ * vdl2_crc16_build_table (the same table the reference carries as a literal), or bitwise without one */
+VDL2_HD void vdl2_crc16_build_table(uint16_t *table, uint32_t tid, uint32_t nthr) {
+	for(uint32_t b = tid; b < 256u; b += nthr) {
+		uint32_t c = b;
+		for(int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1u) ? 0x8408u : 0u);
+		table[b] = (uint16_t)c;
+	}
+}
+VDL2_HD uint16_t vdl2_crc16_tab(const uint8_t *p, uint32_t len, const uint16_t *table) {
+	uint32_t crc = 0xFFFFu;
+	for(uint32_t n = 0; n < len; n++) crc = (crc >> 8) ^ table[(crc ^ p[n]) & 0xFFu];
+	return (uint16_t)crc;
+}
+
 VDL2_HD uint16_t vdl2_crc16(const uint8_t *p, uint32_t len) {
 	uint32_t crc = 0xFFFFu;
 	for(uint32_t n = 0; n < len; n++) {

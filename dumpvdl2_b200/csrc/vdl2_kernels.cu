@@ -433,12 +433,18 @@ __global__ void __launch_bounds__(K3_BLOCK) k3_burst_fec(vdl2_k3_params p) {
 	__shared__ vdl2_burst_work w;
 	__shared__ uint8_t s_gexp[512];
 	__shared__ uint8_t s_glog[256];
+	__shared__ uint8_t s_rootmul[6 * 256];
+	__shared__ uint16_t s_crctab[256];
 	__shared__ uint16_t s_foff[VDL2_MAX_FRAMES];
 	__shared__ uint32_t s_out_off;
 	const uint32_t tid = threadIdx.x;
 	for(uint32_t i = tid; i < 512; i += K3_BLOCK) s_gexp[i] = p.tables->gf_exp[i];
 	for(uint32_t i = tid; i < 256; i += K3_BLOCK) s_glog[i] = p.tables->gf_log[i];
 	const uint32_t n_ready = p.ctl->n_ready;
+	if(blockIdx.x >= n_ready) return;                         /* nothing for this block: skip the table set-up */
+	__syncthreads();
+	vdl2_rs_build_rootmul(s_rootmul, s_gexp, s_glog, tid, K3_BLOCK);
+	vdl2_crc16_build_table(s_crctab, tid, K3_BLOCK);
 	for(uint32_t b = blockIdx.x; b < n_ready; b += gridDim.x) {
 		__syncthreads();
 		const uint32_t slot_idx = p.ready[b];
@@ -451,7 +457,7 @@ __global__ void __launch_bounds__(K3_BLOCK) k3_burst_fec(vdl2_k3_params p) {
 			__syncthreads();
 			if(tid < w.num_blocks) {
 				int nfec = (tid == w.num_blocks - 1) ? (int)w.last_fec : (VDL2_RS_N - VDL2_RS_K);
-				w.rs_ret[tid] = vdl2_rs_verify(w.tab[tid], nfec, s_gexp, s_glog);
+				w.rs_ret[tid] = vdl2_rs_verify(w.tab[tid], nfec, s_gexp, s_glog, s_rootmul);
 			}
 			__syncthreads();
 			if(tid == 0) {
@@ -472,7 +478,7 @@ __global__ void __launch_bounds__(K3_BLOCK) k3_burst_fec(vdl2_k3_params p) {
 			}
 			__syncthreads();
 			for(uint32_t k = tid; k < w.n_frames; k += K3_BLOCK)          /* K4 */
-				w.fcrc[k] = vdl2_crc16(&w.frames[s_foff[k]], w.flen[k]);
+				w.fcrc[k] = vdl2_crc16_tab(&w.frames[s_foff[k]], w.flen[k], s_crctab);
 		}
 		__syncthreads();
 		/* record -> host-mapped output region */
@@ -553,9 +559,12 @@ __global__ void k_rs_verify(uint8_t *blocks, const int32_t *fec_octets, uint32_t
 	__shared__ uint8_t s_glog[256];
 	for(uint32_t i = threadIdx.x; i < 512; i += blockDim.x) s_gexp[i] = tables->gf_exp[i];
 	for(uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_glog[i] = tables->gf_log[i];
+	__shared__ uint8_t s_rootmul[6 * 256];
+	__syncthreads();
+	vdl2_rs_build_rootmul(s_rootmul, s_gexp, s_glog, threadIdx.x, blockDim.x);
 	__syncthreads();
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i < n) ret[i] = vdl2_rs_verify(blocks + (size_t)i * VDL2_RS_N, fec_octets[i], s_gexp, s_glog);
+	if(i < n) ret[i] = vdl2_rs_verify(blocks + (size_t)i * VDL2_RS_N, fec_octets[i], s_gexp, s_glog, s_rootmul);
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -15,6 +15,19 @@ struct float2 { float x, y; };
 typedef float2 float2x;
 #include "vdl2_core.cuh"
 
+static const uint8_t *rootmul_table(const host_tables *h) {
+	static uint8_t tab[6 * 256];
+	static bool ready = false;
+	if(!ready) { vdl2_rs_build_rootmul(tab, h->t.gf_exp, h->t.gf_log, 0, 1); ready = true; }
+	return tab;
+}
+static const uint16_t *crc_table() {
+	static uint16_t tab[256];
+	static bool ready = false;
+	if(!ready) { vdl2_crc16_build_table(tab, 0, 1); ready = true; }
+	return tab;
+}
+
 extern "C" {
 
 /* K1 restated on the host exactly as the scalar kernel does it (table form of the NCO) */
@@ -119,7 +132,7 @@ int hostsim_k2k3(const float *dec /*[n_dec][n_ch][2]*/, uint32_t n_dec, uint32_t
 				vdl2_burst_unpack(*w, slot->words, h->t.lfsr_words, 0, 1);
 				for(uint32_t r = 0; r < w->num_blocks; r++) {
 					int nfec = (r == w->num_blocks - 1) ? (int)w->last_fec : 6;
-					w->rs_ret[r] = vdl2_rs_verify(w->tab[r], nfec, h->t.gf_exp, h->t.gf_log);
+					w->rs_ret[r] = vdl2_rs_verify(w->tab[r], nfec, h->t.gf_exp, h->t.gf_log, rootmul_table(h));
 				}
 				for(uint32_t r = 0; r < w->num_blocks; r++) {
 					int nfec = (r == w->num_blocks - 1) ? (int)w->last_fec : 6;
@@ -129,7 +142,7 @@ int hostsim_k2k3(const float *dec /*[n_dec][n_ch][2]*/, uint32_t n_dec, uint32_t
 				}
 				if(w->status == VDL2_BURST_OK) vdl2_burst_unstuff(*w);
 				uint32_t off = 0;
-				for(uint32_t k = 0; k < w->n_frames; k++) { w->fcrc[k] = vdl2_crc16(&w->frames[off], w->flen[k]); off += w->flen[k]; }
+				for(uint32_t k = 0; k < w->n_frames; k++) { w->fcrc[k] = vdl2_crc16_tab(&w->frames[off], w->flen[k], crc_table()); off += w->flen[k]; }
 			}
 			uint32_t rec_bytes = (uint32_t)((sizeof(vdl2_burst_record) + 4u * w->n_frames + w->frame_bytes + 15u) & ~15u);
 			if(*out_used + rec_bytes > out_cap) { delete w; delete h; return -1; }
@@ -172,7 +185,7 @@ int hostsim_k3(const uint8_t *bits, uint32_t nbits, uint32_t datalen_bits, uint8
 	if(w.status == VDL2_BURST_OK) {
 		vdl2_burst_unpack(w, slot.words, h->t.lfsr_words, 0, 1);
 		for(uint32_t r = 0; r < w.num_blocks; r++)
-			w.rs_ret[r] = vdl2_rs_verify(w.tab[r], (r == w.num_blocks - 1) ? (int)w.last_fec : 6, h->t.gf_exp, h->t.gf_log);
+			w.rs_ret[r] = vdl2_rs_verify(w.tab[r], (r == w.num_blocks - 1) ? (int)w.last_fec : 6, h->t.gf_exp, h->t.gf_log, rootmul_table(h));
 		for(uint32_t r = 0; r < w.num_blocks; r++) {
 			int nfec = (r == w.num_blocks - 1) ? (int)w.last_fec : 6;
 			if(w.rs_ret[r] < 0) { w.status = VDL2_ERR_FEC_BAD; for(uint32_t q = r + 1; q < w.num_blocks; q++) w.rs_ret[q] = -128; break; }
@@ -186,7 +199,7 @@ int hostsim_k3(const uint8_t *bits, uint32_t nbits, uint32_t datalen_bits, uint8
 	for(uint32_t k = 0; k < w.n_frames && k < max_frames; k++) {
 		if(off + w.flen[k] > cap) return -1;
 		memcpy(frames_out + off, w.frames + off, w.flen[k]);
-		lens[k] = w.flen[k]; crcs[k] = vdl2_crc16(w.frames + off, w.flen[k]);
+		lens[k] = w.flen[k]; crcs[k] = vdl2_crc16_tab(w.frames + off, w.flen[k], crc_table());
 		off += w.flen[k];
 	}
 	return w.status;
@@ -196,7 +209,7 @@ int hostsim_k3(const uint8_t *bits, uint32_t nbits, uint32_t datalen_bits, uint8
 int hostsim_rs_verify(uint8_t *block255, int fec_octets) {
 	static host_tables *h = nullptr;
 	if(!h) { h = new host_tables(); memset(h, 0, sizeof(*h)); make_gf(h->t); }
-	return vdl2_rs_verify(block255, fec_octets, h->t.gf_exp, h->t.gf_log);
+	return vdl2_rs_verify(block255, fec_octets, h->t.gf_exp, h->t.gf_log, rootmul_table(h));
 }
 uint32_t hostsim_header_fix(uint32_t word, uint32_t *syndrome) {
 	uint32_t s = vdl2_header_syndrome(word);
