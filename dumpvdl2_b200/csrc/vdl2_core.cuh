@@ -101,6 +101,7 @@ struct vdl2_k2_env {
 	const float *lr_X;           /* 16 */
 	float lr_denom;
 	float max_ppm;
+	const uint32_t *unwrap_lut;  /* vdl2_tables::unwrap_lut (shared memory on the device) */
 	uint32_t s27;                /* first 27 scrambler output bits, first bit in bit 26 */
 	vdl2_burst_slot *pool;
 	int32_t *free_list;
@@ -223,14 +224,35 @@ VDL2_HD float vdl2_unwrap_step(float unwrap, float step) {
  * The N evaluations share nothing; interleaving them in one instruction stream gives the N-fold instruction
  * level parallelism a single warp per SM sub-partition needs to hide the FP32/FP64 pipeline latency.
  * Every evaluation performs exactly the reference's operations in the reference's order. */
-template<int N>
+/* the same update through the transition table (vdl2_tables::unwrap_lut): `row` is the byte offset of the current
+ * state's row; one 8-byte look-up gives the next row and the next value.  Bit-identical to vdl2_unwrap_step by
+ * construction (the table is built with the reference's double arithmetic) and checked state by state in
+ * tests/test_hostsim.py. */
+VDL2_HD float vdl2_unwrap_lut_step(const uint32_t *lut, uint32_t &row, float step) {
+	const uint32_t off = row + ((step >= VDL2_PI_F_ABOVE) ? 8u : 0u) + ((step <= -VDL2_PI_F_ABOVE) ? 16u : 0u);
+#ifdef __CUDA_ARCH__
+	const uint2 e = *reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(lut) + off);
+	row = e.x;
+	return __uint_as_float(e.y);
+#else
+	const uint32_t *e = lut + (off >> 2);
+	float val;
+	row = e[0];
+	memcpy(&val, &e[1], 4);
+	return val;
+#endif
+}
+
+template<int N, bool LUT>
 VDL2_HD void vdl2_metric_core_n(const float (*ph)[VDL2_PREAMBLE_SYMS], const float *pr_phase, const float *lr_X,
-		float lr_denom, float *p0_out, float *slope_out) {
+		float lr_denom, const uint32_t *unwrap_lut, float *p0_out, float *slope_out) {
 	float err[N][VDL2_PREAMBLE_SYMS];
 	float unwrap[N], prev[N], mean[N], slope[N], p0[N];
+	uint32_t row[N];
 #pragma unroll
 	for(int k = 0; k < N; k++) {
 		unwrap[k] = 0.f;
+		row[k] = 0u;
 		prev[k] = F_SUB(ph[k][0], pr_phase[0]);
 		mean[k] = prev[k];
 		err[k][0] = prev[k];
@@ -242,7 +264,8 @@ VDL2_HD void vdl2_metric_core_n(const float (*ph)[VDL2_PREAMBLE_SYMS], const flo
 			float cur = F_SUB(ph[k][i], pr_phase[i]);
 			float step = F_SUB(cur, prev[k]);
 			prev[k] = cur;
-			unwrap[k] = vdl2_unwrap_step(unwrap[k], step);
+			if(LUT) unwrap[k] = vdl2_unwrap_lut_step(unwrap_lut, row[k], step);
+			else unwrap[k] = vdl2_unwrap_step(unwrap[k], step);
 			err[k][i] = F_ADD(cur, unwrap[k]);
 			mean[k] = F_ADD(mean[k], err[k][i]);
 		}
@@ -273,7 +296,7 @@ VDL2_HD void vdl2_metric_core_n(const float (*ph)[VDL2_PREAMBLE_SYMS], const flo
 
 VDL2_HD float vdl2_metric_core(const float *ph, const float *pr_phase, const float *lr_X, float lr_denom, float *slope_out) {
 	float p0;
-	vdl2_metric_core_n<1>(reinterpret_cast<const float (*)[VDL2_PREAMBLE_SYMS]>(ph), pr_phase, lr_X, lr_denom, &p0, slope_out);
+	vdl2_metric_core_n<1, false>(reinterpret_cast<const float (*)[VDL2_PREAMBLE_SYMS]>(ph), pr_phase, lr_X, lr_denom, nullptr, &p0, slope_out);
 	return p0;
 }
 
@@ -489,6 +512,7 @@ VDL2_HD void vdl2_demod_step_pm(vdl2_chan &v, float *ring, int rs, const vdl2_k2
  *   generic anything else (the 150 samples after a reset, the sample after a burst): the per-sample step.
  * All three produce exactly what twelve calls of vdl2_demod_step_pm would. */
 #define VDL2_WALK_BLOCK 12
+template<bool LUT>
 VDL2_HD void vdl2_walk_block(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env, uint32_t chan_idx, uint64_t idx0,
 		const float2 *dec, const float *phase, const float *mag, size_t stride) {
 	int resume = 0;
@@ -506,7 +530,7 @@ VDL2_HD void vdl2_walk_block(vdl2_chan &v, float *ring, int rs, const vdl2_k2_en
 		}
 #pragma unroll
 		for(int t = 0; t < VDL2_WALK_BLOCK; t++) pw[t] = VDL2_LDG(phase + (ptrdiff_t)t * (ptrdiff_t)stride);
-		vdl2_metric_core_n<4>(ph, env.pr_phase, env.lr_X, env.lr_denom, p0, sl);
+		vdl2_metric_core_n<4, LUT>(ph, env.pr_phase, env.lr_X, env.lr_denom, env.unwrap_lut, p0, sl);
 		/* the block is four groups of SYNC_SKIP samples; in each the attempt falls on local offset `first`,
 		 * and the sample clock is back at its entry value at every group boundary */
 		const int sclk_entry = v.sclk;

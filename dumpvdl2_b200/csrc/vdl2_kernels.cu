@@ -348,14 +348,16 @@ __global__ void __launch_bounds__(256) k_copy_rows(const float *__restrict__ src
 	if(i < n) dst[i] = src[i];
 }
 
-template<int BLOCK, bool BLOCKED>
+template<int BLOCK, bool BLOCKED, bool LUT>
 __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	__shared__ float s_ring[VDL2_SYNC_BUFLEN * BLOCK];
 	__shared__ float s_consts[33];
+	__shared__ __align__(8) uint32_t s_unwrap[LUT ? VDL2_UNWRAP_STATES * 6 : 2];
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ch = blockIdx.x * BLOCK + tid;
 	if(tid < 16) { s_consts[tid] = p.tables->pr_phase[tid]; s_consts[16 + tid] = p.tables->lr_X[tid]; }
 	if(tid == 0) s_consts[32] = p.tables->lr_denom;
+	if(LUT) for(uint32_t i = tid; i < VDL2_UNWRAP_STATES * 6; i += BLOCK) s_unwrap[i] = p.tables->unwrap_lut[i];
 	__syncthreads();
 	if(ch >= p.n_ch) return;
 	const uint32_t s = p.n_chp;
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 
 	vdl2_k2_env env;
 	env.pr_phase = s_consts; env.lr_X = s_consts + 16; env.lr_denom = s_consts[32];
-	env.max_ppm = p.max_ppm; env.s27 = p.s27;
+	env.max_ppm = p.max_ppm; env.s27 = p.s27; env.unwrap_lut = s_unwrap;
 	env.pool = p.pool; env.free_list = p.free_list; env.ready = p.ready; env.ctl = p.ctl;
 	env.events = reinterpret_cast<vdl2_event_rec *>(p.events); env.event_cap = p.event_cap; env.trace = p.trace;
 
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 #pragma unroll 1
 		for(; m + VDL2_WALK_BLOCK <= p.n_dec; m += VDL2_WALK_BLOCK) {
 			const size_t o = (size_t)m * s;
-			vdl2_walk_block(v, ring, BLOCK, env, ch, p.dec_base + m, dec + o, phs + o, mgs + o, s);
+			vdl2_walk_block<LUT>(v, ring, BLOCK, env, ch, p.dec_base + m, dec + o, phs + o, mgs + o, s);
 		}
 	}
 #pragma unroll 1
@@ -639,15 +641,17 @@ extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
 	const uint32_t hist = VDL2_SYNC_BUFLEN * p->n_chp;
 	static int variant = -1;
 	if(variant < 0) {
-		const char *ev = getenv("VDL2GPU_K2_VARIANT"); variant = ev ? atoi(ev) : 1;
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true>);
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, false>);
+		const char *ev = getenv("VDL2GPU_K2_VARIANT"); variant = ev ? atoi(ev) : 2;
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, true>);
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, false>);
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, false, false>);
 		vdl2_set_carveout(k_copy_rows);
 		vdl2_set_carveout(k3_burst_fec);
 		vdl2_set_carveout(k_chunk_finish);
 	}
-	if(variant == 0) k2_sync_slice<K2_BLOCK, false><<<blocks, K2_BLOCK, 0, st>>>(*p);
-	else k2_sync_slice<K2_BLOCK, true><<<blocks, K2_BLOCK, 0, st>>>(*p);
+	if(variant == 0) k2_sync_slice<K2_BLOCK, false, false><<<blocks, K2_BLOCK, 0, st>>>(*p);          /* per-sample walk */
+	else if(variant == 1) k2_sync_slice<K2_BLOCK, true, false><<<blocks, K2_BLOCK, 0, st>>>(*p);     /* blocked, TwoSum unwrap */
+	else k2_sync_slice<K2_BLOCK, true, true><<<blocks, K2_BLOCK, 0, st>>>(*p);                       /* blocked, table unwrap (default) */
 	int e = (int)cudaGetLastError();
 	if(e) return e;
 	/* history for the next chunk: rows [n_dec, n_dec+160) -> [0, 160) */

@@ -122,6 +122,38 @@ static inline void make_gf(vdl2_tables &t) {
 	for(int e = 255; e < 512; e++) t.gf_exp[e] = t.gf_exp[e - 255];
 }
 
+/* src/demod.c:137-141: `unwrap -= 2.0f * M_PI` / `unwrap += 2.0f * M_PI` is double arithmetic narrowed on store.
+ * Breadth-first enumeration of the values reachable within the 15 steps one got_sync evaluation can take; the
+ * transition table replaces the arithmetic in the K2 walk.  Returns the number of states (77), 0 on overflow. */
+static inline int make_unwrap_lut(vdl2_tables &t) {
+	float vals[VDL2_UNWRAP_STATES];
+	int depth[VDL2_UNWRAP_STATES], next[VDL2_UNWRAP_STATES][3];
+	int n = 1;
+	vals[0] = 0.f; depth[0] = 0;
+	for(int head = 0; head < n; head++) {
+		next[head][0] = head;
+		for(int j = 1; j <= 2; j++) {
+			next[head][j] = 0;                              /* transitions out of a depth-15 state are never taken */
+			if(depth[head] >= 15) continue;
+			const float nv = (float)((double)vals[head] + (j == 1 ? -1.0 : 1.0) * (2.0f * M_PI));
+			int k = 0;
+			while(k < n && memcmp(&vals[k], &nv, 4) != 0) k++;
+			if(k == n) {
+				if(n == VDL2_UNWRAP_STATES) return 0;
+				vals[n] = nv; depth[n] = depth[head] + 1; n++;
+			}
+			next[head][j] = k;
+		}
+	}
+	memset(t.unwrap_lut, 0, sizeof(t.unwrap_lut));
+	for(int s = 0; s < n; s++)
+		for(int j = 0; j < 3; j++) {
+			t.unwrap_lut[s * 6 + j * 2] = (uint32_t)next[s][j] * 24u;
+			memcpy(&t.unwrap_lut[s * 6 + j * 2 + 1], &vals[next[s][j]], 4);
+		}
+	return n;
+}
+
 static inline void make_tables(host_tables &h, uint32_t rate) {
 	memset(&h, 0, sizeof(h));
 	make_levels(h.t.levels);
@@ -130,6 +162,7 @@ static inline void make_tables(host_tables &h, uint32_t rate) {
 	make_sync_consts(h.t);
 	make_lfsr(h);
 	make_gf(h.t);
+	make_unwrap_lut(h.t);
 }
 
 

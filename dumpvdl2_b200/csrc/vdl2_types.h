@@ -37,6 +37,7 @@
 /* 25 header bits + 8 * (2048 data + 54 fec octets) + up to 2 spare bits of the last symbol */
 #define VDL2_MAX_BURST_BITS (25 + 8 * (2048 + 54) + 2)
 #define VDL2_MAX_BURST_WORDS ((VDL2_MAX_BURST_BITS + 31) / 32)     /* 527 */
+#define VDL2_UNWRAP_STATES 80
 #define VDL2_MAX_FRAMES 1032                     /* >= 16384 bits / 16 */
 
 /* burst decoder status; names follow the statsd counters of src/decode.c:204-369 */
@@ -142,6 +143,10 @@ typedef struct {
 	uint32_t lfsr_words[1056];   /* scrambler output, bit i at words[i/32] >> (31 - i%32), 33792 bits (period 32767 wraps) */
 	uint8_t gf_exp[512];         /* src/libfec/init_rs.h:48-58, doubled to skip the modulo */
 	uint8_t gf_log[256];
+	/* got_sync's `unwrap` accumulator (src/demod.c:137-141) as a finite automaton: it only takes the values reachable
+	 * from 0 by at most 15 steps of fl32((double)u -/+ 2pi) (77 of them).  Row r (24 bytes) = three {next row byte
+	 * offset, value bits of the next state} pairs: +0 no wrap, +8 step > pi (u -= 2pi), +16 step < -pi (u += 2pi). */
+	uint32_t unwrap_lut[VDL2_UNWRAP_STATES * 6];
 } vdl2_tables;
 
 #endif

@@ -87,7 +87,7 @@ int hostsim_k2k3(const float *dec /*[n_dec][n_ch][2]*/, uint32_t n_dec, uint32_t
 	memset(&ctl, 0, sizeof(ctl));
 	ctl.free_top = (int32_t)n_slots;
 	vdl2_k2_env env;
-	env.pr_phase = h->t.pr_phase; env.lr_X = h->t.lr_X; env.lr_denom = h->t.lr_denom; env.max_ppm = max_ppm; env.s27 = h->s27;
+	env.pr_phase = h->t.pr_phase; env.lr_X = h->t.lr_X; env.lr_denom = h->t.lr_denom; env.max_ppm = max_ppm; env.s27 = h->s27; env.unwrap_lut = h->t.unwrap_lut;
 	env.pool = pool.data(); env.free_list = free_list.data(); env.ready = ready.data(); env.ctl = &ctl;
 	env.events = events; env.event_cap = event_cap; env.trace = events != nullptr;
 	std::vector<vdl2_chan> chans(n_ch);
@@ -113,8 +113,12 @@ int hostsim_k2k3(const float *dec /*[n_dec][n_ch][2]*/, uint32_t n_dec, uint32_t
 			if(use_pre) {                     /* the kernel's blocked walk */
 				for(; m + VDL2_WALK_BLOCK <= n; m += VDL2_WALK_BLOCK) {
 					const size_t o = (size_t)(base + m) * n_ch + ch;
-					vdl2_walk_block(chans[ch], &rings[(size_t)ch * VDL2_SYNC_BUFLEN], 1, env, ch, base + m,
-							reinterpret_cast<const float2 *>(dec2 + o), &phase[o + (size_t)VDL2_SYNC_BUFLEN * n_ch], &mag[o], n_ch);
+					if(use_pre == 2)              /* unwrap through the transition table */
+						vdl2_walk_block<true>(chans[ch], &rings[(size_t)ch * VDL2_SYNC_BUFLEN], 1, env, ch, base + m,
+								reinterpret_cast<const float2 *>(dec2 + o), &phase[o + (size_t)VDL2_SYNC_BUFLEN * n_ch], &mag[o], n_ch);
+					else
+						vdl2_walk_block<false>(chans[ch], &rings[(size_t)ch * VDL2_SYNC_BUFLEN], 1, env, ch, base + m,
+								reinterpret_cast<const float2 *>(dec2 + o), &phase[o + (size_t)VDL2_SYNC_BUFLEN * n_ch], &mag[o], n_ch);
 				}
 			}
 			for(; m < n; m++) {
@@ -218,6 +222,14 @@ uint32_t hostsim_header_fix(uint32_t word, uint32_t *syndrome) {
 }
 uint32_t hostsim_synd_weight(uint32_t s) { return vdl2_synd_weight(s); }
 float hostsim_unwrap_step(float unwrap, float step) { return vdl2_unwrap_step(unwrap, step); }
+int hostsim_unwrap_lut(uint32_t *out /*[VDL2_UNWRAP_STATES * 6]*/) {
+	vdl2_tables *t = new vdl2_tables();
+	int n = make_unwrap_lut(*t);
+	memcpy(out, t->unwrap_lut, sizeof(t->unwrap_lut));
+	delete t;
+	return n;
+}
+float hostsim_unwrap_lut_step(const uint32_t *lut, uint32_t *row, float step) { return vdl2_unwrap_lut_step(lut, *row, step); }
 uint16_t hostsim_crc16(const uint8_t *p, uint32_t n) { return vdl2_crc16(p, n); }
 void hostsim_tables(uint32_t rate, float *levels, float *sin_lut, float *cos_lut, float *A, float *B, float *lr_X, float *lr_denom, float *pr_phase) {
 	host_tables *h = new host_tables();

@@ -16,7 +16,7 @@ def _samples(case):
     return po.levels_u8()[b]
 
 
-@pytest.mark.parametrize("use_pre", [True, False])
+@pytest.mark.parametrize("use_pre", [2, 1, 0], ids=["blocked_lut", "blocked", "per_sample"])
 @pytest.mark.parametrize("name", ["cfg2", "mixed_s16", "fec", "noisy", "wav", "hdlc_edge", "mirics_os13"])
 def test_device_functions_on_host_match_oracle(name, use_pre):
     c = cases.ALL_GOLDEN[name]()
@@ -51,7 +51,12 @@ def test_max_ppm_veto_in_blocked_walk():
     must fall back to the per-sample path there."""
     c = dict(cases.case_mixed_s16()); c["max_ppm"] = 1.0
     o = util.run_oracle(c, trace=True, dec_tap=True)
-    recs, ev, cnt = hs.k2k3(o.dec_samples(), c["freqs"], c["fs"], max_ppm=1.0)
+    for mode in (1, 2):
+        _check_veto(c, o, mode)
+
+
+def _check_veto(c, o, mode):
+    recs, ev, cnt = hs.k2k3(o.dec_samples(), c["freqs"], c["fs"], max_ppm=1.0, use_pre=mode)
     got = sorted((r["channel"], r["burst_seq"], k, d, r["sync_dec_index"]) for r in recs for k, (d, _) in enumerate(r["frames"]))
     want = sorted((f.channel, f.burst_seq, f.idx, f.data, f.sync_dec_index) for f in o.frames())
     assert got == want and len(want) < 14
@@ -139,6 +144,49 @@ def test_fp32_unwrap_update_equals_the_double_arithmetic_of_the_reference():
         assert jumped == (np.float64(x) > np.pi)
         jumped = L.hostsim_unwrap_step(np.float32(0), -x) != 0
         assert jumped == (np.float64(-x) < -np.pi)
+
+
+def test_unwrap_transition_table_equals_the_double_arithmetic_of_the_reference():
+    """The K2 walk replaces the arithmetic by a 77-state transition table built at start-up (vdl2_tables_host.h):
+    every row must hold exactly fl32((double)u -/+ 2pi) for its state, and walking the table along random step
+    sequences must give the same values as the arithmetic form."""
+    import ctypes as C
+    L = hs.lib()
+    lut = np.zeros(80 * 6, np.uint32)
+    n = L.hostsim_unwrap_lut(lut.ctypes.data_as(C.c_void_p))
+    assert n == 77
+    two_pi = np.float64(2.0) * np.float64(np.pi)
+    rows = lut.reshape(80, 3, 2)
+    vals = {}                                  # state -> value, from the rows pointing at it
+    assert rows[0, 0, 0] == 0 and rows[0, 0, 1] == 0
+    vals[0] = np.float32(0)
+    depth = {0: 0}
+    order = [0]
+    for s in order:                            # breadth first, like the builder
+        u = vals[s]
+        assert rows[s, 0, 0] == s * 24 and rows[s, 0, 1:].view(np.float32)[0].tobytes() == u.tobytes()
+        if depth[s] >= 15:
+            continue
+        for j, sign in ((1, -1.0), (2, 1.0)):
+            want = np.float32(np.float64(u) + sign * two_pi)
+            nxt = int(rows[s, j, 0]) // 24
+            assert rows[s, j, 0] % 24 == 0 and nxt < n
+            assert rows[s, j, 1:].view(np.float32)[0].tobytes() == want.tobytes(), (s, j)
+            if nxt not in vals:
+                vals[nxt] = want; depth[nxt] = depth[s] + 1; order.append(nxt)
+            assert vals[nxt].tobytes() == want.tobytes()
+    assert len(vals) == 77
+    L.hostsim_unwrap_step.restype = C.c_float
+    L.hostsim_unwrap_step.argtypes = [C.c_float, C.c_float]
+    L.hostsim_unwrap_lut_step.restype = C.c_float
+    L.hostsim_unwrap_lut_step.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_float]
+    rng = np.random.default_rng(77)
+    for trial in range(300):
+        row, u = C.c_uint32(0), np.float32(0)
+        for step in rng.uniform(-6.2, 6.2, 15).astype(np.float32):
+            u = np.float32(L.hostsim_unwrap_step(u, step))
+            got = np.float32(L.hostsim_unwrap_lut_step(lut.ctypes.data_as(C.c_void_p), C.byref(row), step))
+            assert got.tobytes() == u.tobytes()
 
 
 def _flag():
