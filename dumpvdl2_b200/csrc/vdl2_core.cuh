@@ -578,6 +578,122 @@ VDL2_HD void vdl2_walk_block(vdl2_chan &v, float *ring, int rs, const vdl2_k2_en
 	}
 }
 
+/* The blocked walk with the sync attempts fed from the phase RING instead of the phase plane.
+ *
+ * With ring_pos = P at block entry (the slot of the sample before the block), local sample t is written to slot
+ * P+1+t, and the attempt on local sample e reads, in the reference, the slots of samples e-150+10i (i = 0..15) after
+ * samples 0..e were written.  Those writes only replace samples <= e-160, which the attempt does not read, so every
+ * sample < 0 can be read from the ring BEFORE the block is applied, and samples >= 0 (i = 15 always, i = 14 for
+ * e >= 10) are the block's own inputs pw[].  This holds for any ring content, so the 150 samples after a reset take
+ * the same path; per block the walk then needs 12 phase + 4 magnitude values from global memory instead of 80, and
+ * they are requested one block ahead (`pf`), so no load latency is exposed.
+ * pf carries the next block's inputs: pw[0..11], and mg[] for the attempt offsets predicted from this block's
+ * `first` (the sample clock returns to the same value every 12 samples while searching). */
+struct vdl2_walk_pref {
+	float pw[VDL2_WALK_BLOCK];
+	float mg[4];
+	int first;
+	int valid;
+};
+
+VDL2_HD void vdl2_walk_tail(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env, uint32_t chan_idx, uint64_t idx0,
+		const float2 *dec, const float *phase, const float *mag, size_t stride, int resume) {
+	int t = resume;
+	while(t < VDL2_WALK_BLOCK) {
+		if((v.state & VDL2_ST_LOCKED) && vdl2_dec_state(v) != VDL2_DEC_IDLE) {
+			const int tsym = t + (VDL2_SPS - 1) - v.sclk;                  /* sample on which ++sclk reaches SPS */
+			if(tsym >= VDL2_WALK_BLOCK) { v.sclk += VDL2_WALK_BLOCK - t; break; }
+			const float2 d = VDL2_LDG(dec + (ptrdiff_t)tsym * (ptrdiff_t)stride);
+			const float phi = VDL2_LDG(phase + (ptrdiff_t)tsym * (ptrdiff_t)stride);
+			v.sclk = 0;
+			vdl2_symbol(v, env, chan_idx, idx0 + (uint64_t)tsym, d.x, d.y, phi);
+			t = tsym + 1;
+		} else {
+			const float2 d = VDL2_LDG(dec + (ptrdiff_t)t * (ptrdiff_t)stride);
+			const float phi = VDL2_LDG(phase + (ptrdiff_t)t * (ptrdiff_t)stride);
+			const float mgt = VDL2_LDG(mag + (ptrdiff_t)t * (ptrdiff_t)stride);
+			vdl2_demod_step_pm(v, ring, rs, env, chan_idx, idx0 + (uint64_t)t, d.x, d.y, phi, mgt, false, 0.f, 0.f);
+			t++;
+		}
+	}
+}
+
+VDL2_HD void vdl2_walk_block_ring(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env, uint32_t chan_idx, uint64_t idx0,
+		const float2 *dec, const float *phase, const float *mag, size_t stride, vdl2_walk_pref &pf, bool has_next) {
+	const bool fast = !(v.state & VDL2_ST_LOCKED) && vdl2_dec_state(v) != VDL2_DEC_IDLE && v.sclk >= 0 && v.sclk < VDL2_SYNC_SKIP;
+	const int first = fast ? (VDL2_SYNC_SKIP - 1) - v.sclk : 0;          /* offset of the first attempt in the block */
+	float pw[VDL2_WALK_BLOCK], mg[4];
+	const bool have_pw = pf.valid != 0, have_mg = pf.valid != 0 && pf.first == first;
+#pragma unroll
+	for(int t = 0; t < VDL2_WALK_BLOCK; t++) pw[t] = pf.pw[t];
+#pragma unroll
+	for(int j = 0; j < 4; j++) mg[j] = pf.mg[j];
+	if(!have_pw && fast) {
+#pragma unroll
+		for(int t = 0; t < VDL2_WALK_BLOCK; t++) pw[t] = VDL2_LDG(phase + (ptrdiff_t)t * (ptrdiff_t)stride);
+	}
+	if(!have_mg && fast) {
+#pragma unroll
+		for(int j = 0; j < 4; j++) mg[j] = VDL2_LDG(mag + (ptrdiff_t)(first + VDL2_SYNC_SKIP * j) * (ptrdiff_t)stride);
+	}
+	/* request the next block's inputs now; they arrive while this block is evaluated */
+	if(has_next) {
+#pragma unroll
+		for(int t = 0; t < VDL2_WALK_BLOCK; t++) pf.pw[t] = VDL2_LDG(phase + (ptrdiff_t)(VDL2_WALK_BLOCK + t) * (ptrdiff_t)stride);
+#pragma unroll
+		for(int j = 0; j < 4; j++) pf.mg[j] = VDL2_LDG(mag + (ptrdiff_t)(VDL2_WALK_BLOCK + first + VDL2_SYNC_SKIP * j) * (ptrdiff_t)stride);
+		pf.first = first;
+		pf.valid = 1;
+	} else {
+		pf.valid = 0;
+	}
+	int resume = 0;
+	if(fast) {
+		float ph[4][VDL2_PREAMBLE_SYMS], p0[4], sl[4];
+#pragma unroll
+		for(int j = 0; j < 4; j++) {
+			/* slot of sample e-150 with e = first + 3j: P + 1 + e - 150 == P + e + 11 (mod 160) */
+			int idx = v.ring_pos + first + VDL2_SYNC_SKIP * j + 11;
+			if(idx >= VDL2_SYNC_BUFLEN) idx -= VDL2_SYNC_BUFLEN;
+#pragma unroll
+			for(int i = 0; i < VDL2_PREAMBLE_SYMS - 1; i++) {
+				ph[j][i] = ring[idx * rs];
+				idx += VDL2_SPS;
+				if(idx >= VDL2_SYNC_BUFLEN) idx -= VDL2_SYNC_BUFLEN;
+			}
+			/* i = 15 is the attempt's own sample, one of the block's inputs */
+			ph[j][15] = (first == 0) ? pw[VDL2_SYNC_SKIP * j] : ((first == 1) ? pw[VDL2_SYNC_SKIP * j + 1] : pw[VDL2_SYNC_SKIP * j + 2]);
+		}
+		/* i = 14 of the last attempt is sample first - 1: still the ring for first == 0, else pw[0] / pw[1] */
+		if(first == 1) ph[3][14] = pw[0];
+		else if(first == 2) ph[3][14] = pw[1];
+		vdl2_metric_core_n<4, true>(ph, env.pr_phase, env.lr_X, env.lr_denom, env.unwrap_lut, p0, sl);
+		const int sclk_entry = v.sclk;
+		bool go = true;
+#pragma unroll
+		for(int g = 0; g < 4; g++) {
+			if(go) {
+#pragma unroll
+				for(int u = 0; u < VDL2_SYNC_SKIP; u++)
+					if(u <= first) vdl2_init_write(v, ring, rs, pw[VDL2_SYNC_SKIP * g + u]);
+				v.sclk = 0;
+				vdl2_init_eval(v, ring, rs, env, chan_idx, idx0 + (uint64_t)(VDL2_SYNC_SKIP * g + first), mg[g], true, p0[g], sl[g]);
+				if((v.state & VDL2_ST_LOCKED) || v.sclk != 0) {
+					go = false;                      /* locked, or vetoed by max_ppm: the per-sample path takes over */
+					resume = VDL2_SYNC_SKIP * g + first + 1;
+				} else {
+#pragma unroll
+					for(int u = 0; u < VDL2_SYNC_SKIP; u++)
+						if(u > first) vdl2_init_write(v, ring, rs, pw[VDL2_SYNC_SKIP * g + u]);
+					v.sclk = sclk_entry;
+				}
+			}
+		}
+		if(go) resume = VDL2_WALK_BLOCK;
+	}
+	vdl2_walk_tail(v, ring, rs, env, chan_idx, idx0, dec, phase, mag, stride, resume);
+}
+
 /* same, computing phase and magnitude in place (host simulation, unit tests) */
 VDL2_HD void vdl2_demod_step(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env,
 		uint32_t chan_idx, uint64_t dec_index, float re, float im) {

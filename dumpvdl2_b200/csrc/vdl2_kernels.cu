@@ -348,16 +348,18 @@ __global__ void __launch_bounds__(256) k_copy_rows(const float *__restrict__ src
 	if(i < n) dst[i] = src[i];
 }
 
-template<int BLOCK, bool BLOCKED, bool LUT>
+/* MODE: 0 sync attempts from the phase plane, TwoSum unwrap; 1 phase plane, table unwrap; 2 phase ring + inputs
+ * requested one block ahead, table unwrap (default) */
+template<int BLOCK, bool BLOCKED, int MODE>
 __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	__shared__ float s_ring[VDL2_SYNC_BUFLEN * BLOCK];
 	__shared__ float s_consts[33];
-	__shared__ __align__(8) uint32_t s_unwrap[LUT ? VDL2_UNWRAP_STATES * 6 : 2];
+	__shared__ __align__(8) uint32_t s_unwrap[MODE ? VDL2_UNWRAP_STATES * 6 : 2];
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ch = blockIdx.x * BLOCK + tid;
 	if(tid < 16) { s_consts[tid] = p.tables->pr_phase[tid]; s_consts[16 + tid] = p.tables->lr_X[tid]; }
 	if(tid == 0) s_consts[32] = p.tables->lr_denom;
-	if(LUT) for(uint32_t i = tid; i < VDL2_UNWRAP_STATES * 6; i += BLOCK) s_unwrap[i] = p.tables->unwrap_lut[i];
+	if(MODE) for(uint32_t i = tid; i < VDL2_UNWRAP_STATES * 6; i += BLOCK) s_unwrap[i] = p.tables->unwrap_lut[i];
 	__syncthreads();
 	if(ch >= p.n_ch) return;
 	const uint32_t s = p.n_chp;
@@ -394,10 +396,25 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	const float *mgs = p.mag + ch;
 	uint32_t m = 0;
 	if(BLOCKED) {
+		if(MODE == 2) {
+			vdl2_walk_pref pf;
+			pf.valid = 0; pf.first = 0;
+#pragma unroll
+			for(int t = 0; t < VDL2_WALK_BLOCK; t++) pf.pw[t] = 0.f;
+#pragma unroll
+			for(int j = 0; j < 4; j++) pf.mg[j] = 0.f;
 #pragma unroll 1
-		for(; m + VDL2_WALK_BLOCK <= p.n_dec; m += VDL2_WALK_BLOCK) {
-			const size_t o = (size_t)m * s;
-			vdl2_walk_block<LUT>(v, ring, BLOCK, env, ch, p.dec_base + m, dec + o, phs + o, mgs + o, s);
+			for(; m + VDL2_WALK_BLOCK <= p.n_dec; m += VDL2_WALK_BLOCK) {
+				const size_t o = (size_t)m * s;
+				vdl2_walk_block_ring(v, ring, BLOCK, env, ch, p.dec_base + m, dec + o, phs + o, mgs + o, s, pf,
+						m + 2 * VDL2_WALK_BLOCK <= p.n_dec);
+			}
+		} else {
+#pragma unroll 1
+			for(; m + VDL2_WALK_BLOCK <= p.n_dec; m += VDL2_WALK_BLOCK) {
+				const size_t o = (size_t)m * s;
+				vdl2_walk_block<MODE == 1>(v, ring, BLOCK, env, ch, p.dec_base + m, dec + o, phs + o, mgs + o, s);
+			}
 		}
 	}
 #pragma unroll 1
@@ -641,17 +658,19 @@ extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
 	const uint32_t hist = VDL2_SYNC_BUFLEN * p->n_chp;
 	static int variant = -1;
 	if(variant < 0) {
-		const char *ev = getenv("VDL2GPU_K2_VARIANT"); variant = ev ? atoi(ev) : 2;
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, true>);
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, false>);
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, false, false>);
+		const char *ev = getenv("VDL2GPU_K2_VARIANT"); variant = ev ? atoi(ev) : 3;
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 2>);
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 1>);
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 0>);
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, false, 0>);
 		vdl2_set_carveout(k_copy_rows);
 		vdl2_set_carveout(k3_burst_fec);
 		vdl2_set_carveout(k_chunk_finish);
 	}
-	if(variant == 0) k2_sync_slice<K2_BLOCK, false, false><<<blocks, K2_BLOCK, 0, st>>>(*p);          /* per-sample walk */
-	else if(variant == 1) k2_sync_slice<K2_BLOCK, true, false><<<blocks, K2_BLOCK, 0, st>>>(*p);     /* blocked, TwoSum unwrap */
-	else k2_sync_slice<K2_BLOCK, true, true><<<blocks, K2_BLOCK, 0, st>>>(*p);                       /* blocked, table unwrap (default) */
+	if(variant == 0) k2_sync_slice<K2_BLOCK, false, 0><<<blocks, K2_BLOCK, 0, st>>>(*p);              /* per-sample walk */
+	else if(variant == 1) k2_sync_slice<K2_BLOCK, true, 0><<<blocks, K2_BLOCK, 0, st>>>(*p);         /* blocked, phase plane, TwoSum unwrap */
+	else if(variant == 2) k2_sync_slice<K2_BLOCK, true, 1><<<blocks, K2_BLOCK, 0, st>>>(*p);         /* blocked, phase plane, table unwrap */
+	else k2_sync_slice<K2_BLOCK, true, 2><<<blocks, K2_BLOCK, 0, st>>>(*p);                          /* blocked, phase ring, inputs one block ahead */
 	int e = (int)cudaGetLastError();
 	if(e) return e;
 	/* history for the next chunk: rows [n_dec, n_dec+160) -> [0, 160) */

@@ -110,7 +110,16 @@ int hostsim_k2k3(const float *dec /*[n_dec][n_ch][2]*/, uint32_t n_dec, uint32_t
 		uint32_t n = n_dec - base < 1024 ? n_dec - base : 1024;
 		for(uint32_t ch = 0; ch < n_ch; ch++) {
 			uint32_t m = 0;
-			if(use_pre) {                     /* the kernel's blocked walk */
+			if(use_pre == 3) {                /* the kernel's ring walk, inputs requested one block ahead */
+				vdl2_walk_pref pf;
+				memset(&pf, 0, sizeof(pf));
+				for(; m + VDL2_WALK_BLOCK <= n; m += VDL2_WALK_BLOCK) {
+					const size_t o = (size_t)(base + m) * n_ch + ch;
+					vdl2_walk_block_ring(chans[ch], &rings[(size_t)ch * VDL2_SYNC_BUFLEN], 1, env, ch, base + m,
+							reinterpret_cast<const float2 *>(dec2 + o), &phase[o + (size_t)VDL2_SYNC_BUFLEN * n_ch], &mag[o], n_ch,
+							pf, m + 2 * VDL2_WALK_BLOCK <= n);
+				}
+			} else if(use_pre) {              /* the kernel's blocked walk on the phase plane */
 				for(; m + VDL2_WALK_BLOCK <= n; m += VDL2_WALK_BLOCK) {
 					const size_t o = (size_t)(base + m) * n_ch + ch;
 					if(use_pre == 2)              /* unwrap through the transition table */

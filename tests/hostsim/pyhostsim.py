@@ -83,7 +83,7 @@ def k2k3(dec, freqs, rate, max_ppm=0.0, trace=True, use_pre=True):
     rc = lib().hostsim_k2k3(d.ctypes.data_as(C.c_void_p), C.c_uint32(n_dec), C.c_uint32(n_ch), f.ctypes.data_as(C.c_void_p),
                             C.c_uint32(rate), C.c_float(max_ppm), out.ctypes.data_as(C.c_void_p), C.c_uint32(out.size),
                             C.byref(used), C.byref(nrec), C.cast(ev, C.c_void_p) if trace else None, C.c_uint32(cap), C.byref(nev),
-                            cnt.ctypes.data_as(C.c_void_p), C.c_int(int(use_pre)))       # 0 per-sample walk, 1 blocked walk, 2 blocked walk with the unwrap table
+                            cnt.ctypes.data_as(C.c_void_p), C.c_int(int(use_pre)))       # 0 per-sample, 1 blocked, 2 blocked + unwrap table, 3 ring walk
     assert rc == 0, f"hostsim pool overflow / error {rc}"
     recs = parse_records(out, used.value)
     events = [dict(channel=ev[k].channel, kind=ev[k].kind, dec_index=ev[k].dec_index, i=list(ev[k].i),
