@@ -658,7 +658,7 @@ extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
 	const uint32_t hist = VDL2_SYNC_BUFLEN * p->n_chp;
 	static int variant = -1;
 	if(variant < 0) {
-		const char *ev = getenv("VDL2GPU_K2_VARIANT"); variant = ev ? atoi(ev) : 3;
+		const char *ev = getenv("VDL2GPU_K2_VARIANT"); variant = ev ? atoi(ev) : 2;
 		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 2>);
 		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 1>);
 		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 0>);
