@@ -135,6 +135,30 @@ def case_hdlc_edge():
     return _mk("hdlc_edge", fs, "u8", [CENTER + o for o in offs], iq, bursts=bursts)
 
 
+def case_maxlen():
+    """Size corners of src/decode.c:45-48,124-133,222-297 on the air: the longest transmission the header can carry
+    within the reference's limit (2047 octets, 9 RS blocks, 54 FEC octets), a burst whose last block is full
+    (3 x 249 octets) and one whose last block is too short to carry FEC octets (249 + 2)."""
+    fs = 2100000
+    rng = np.random.default_rng(2047)
+    F = "01111110"
+
+    def fr(n):
+        return "".join(format(b, "08b")[::-1] for b in synth.random_avlc_frame(rng, n)).replace("11111", "111110")
+
+    def fill(frames, n_octets):
+        pl = F + F.join(fr(n) for n in frames) + F
+        assert len(pl) <= 8 * n_octets
+        return (pl + F * 64)[:8 * n_octets]              # pad with flags up to the exact transmission length
+    payloads = [(fill([240] * 8, 2047), 100e3), (fill([240, 240, 230], 747), -100e3), (fill([235], 251), -100e3)]
+    bursts, t = [], {100e3: 0.02, -100e3: 0.02}
+    for pl, off in payloads:
+        bursts.append(synth.BurstSpec(t[off], off, [], power_dbfs=-12.0, payload=pl))
+        t[off] += synth.burst_duration_s(None, payload=pl) + 0.015
+    iq = synth.synth_stream(fs, max(t.values()) + 0.02, bursts, es_n0_db=32, fmt="u8", seed=2048)
+    return _mk("maxlen", fs, "u8", [CENTER + 100e3, CENTER - 100e3], iq, chunk=524288, bursts=bursts)
+
+
 def case_noisy():
     """Low SNR (Es/N0 19.5 dB): symbol errors, RS corrections and failures, false syncs on noise."""
     fs = 2100000
@@ -166,4 +190,4 @@ def case_replicas(n_slots=16, n_rep=4, duration=0.5, seed=0x56444C33, es_n0_db=2
 
 
 ALL_GOLDEN = {"wav": case_wav, "cfg2": case_cfg2, "mixed_s16": case_mixed_s16, "fec": case_fec, "noisy": case_noisy,
-              "hdlc_edge": case_hdlc_edge, "mirics_os13": case_mirics_os13}
+              "hdlc_edge": case_hdlc_edge, "mirics_os13": case_mirics_os13, "maxlen": case_maxlen}

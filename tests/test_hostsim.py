@@ -236,3 +236,30 @@ def test_burst_decoder_matches_oracle_on_hdlc_edge_cases(trial):
     assert (st_k, fr_k, corr_k) == (st_o, fr_o, corr_o), (st_k, st_o, len(fr_k), len(fr_o))
     assert list(rs_k) == list(rs_o)
     assert [int(c) for c in crcs] == [po.crc16(f) for f in fr_k]
+
+
+@pytest.mark.parametrize("n_octets", [1, 2, 3, 4, 30, 31, 32, 67, 68, 69, 248, 249, 250, 251, 252, 279, 280, 317, 498, 499, 747,
+                                      1245, 1992, 1993, 1994, 2022, 2023, 2040, 2046, 2047])
+def test_burst_decoder_block_geometry_edges(n_octets):
+    """Block geometry corners of src/decode.c:124-133,222-297: last-block lengths around the FEC-octet thresholds
+    (2|3, 30|31, 67|68), exact multiples of 249, and the maximum transmission length (9 blocks, 2047 octets),
+    each with a couple of corrupted octets in the first and the last block."""
+    from dumpvdl2_b200 import synth
+    rng = np.random.default_rng(5000 + n_octets)
+    body = _flag() + _stuffed(rng.integers(0, 256, max(0, n_octets - 4), dtype=np.uint8)) + _flag()
+    payload = (body + _flag() * 300)[:n_octets * 8]           # pad with flags, cut to the exact transmission length
+    nblk = -(-n_octets // 249)
+    last_len = n_octets - (nblk - 1) * 249
+    corrupt = [(0, int(rng.integers(0, min(249, n_octets))), 0x55)]
+    if last_len > 2:
+        corrupt.append((nblk - 1, int(rng.integers(0, last_len)), 0xAA))
+    try:
+        bits, info = synth.burst_bits_from_payload(payload, corrupt_octets=corrupt)
+    except ValueError:
+        pytest.skip("no FEC octets for this length")
+    assert info["datalen_bits"] == n_octets * 8
+    descr = bits ^ synth.scrambler_sequence(len(bits))
+    st_o, fr_o, corr_o, rs_o = po.decode_burst_bits(descr[25:], info["datalen_bits"])
+    st_k, fr_k, corr_k, rs_k, crcs = hs.k3(bits, info["datalen_bits"])
+    assert (st_k, fr_k, corr_k) == (st_o, fr_o, corr_o), (st_k, st_o, len(fr_k), len(fr_o))
+    assert list(rs_k) == list(rs_o) and sum(int(r) != -128 for r in rs_k) == nblk
