@@ -263,3 +263,47 @@ def test_burst_decoder_block_geometry_edges(n_octets):
     st_k, fr_k, corr_k, rs_k, crcs = hs.k3(bits, info["datalen_bits"])
     assert (st_k, fr_k, corr_k) == (st_o, fr_o, corr_o), (st_k, st_o, len(fr_k), len(fr_o))
     assert list(rs_k) == list(rs_o) and sum(int(r) != -128 for r in rs_k) == nblk
+
+
+def test_burst_decoder_fuzz_random_payloads():
+    """Random transmissions (any bit length 17..16383, random content with a sprinkling of flags, 0..8 corrupted octets
+    anywhere in the code words): K3's device functions must return exactly the oracle's status, frames, correction
+    count, per-block RS results and FCS residues."""
+    from dumpvdl2_b200 import synth
+    rng = np.random.default_rng(0xF0B8)
+    done = 0
+    for trial in range(160):
+        nbits = int(rng.integers(17, 0x4000)) if trial % 3 else int(rng.integers(17, 700))
+        if trial % 2:                                        # well-formed: stuffed frames between flags, cut to nbits
+            payload = _flag()
+            while len(payload) < nbits:
+                payload += _stuffed(rng.integers(0, 256, int(rng.integers(0, 300)), dtype=np.uint8)) + _flag() * int(rng.integers(1, 3))
+            if trial % 4 == 1:
+                payload = payload[:nbits]                    # cut anywhere
+            else:
+                nbits = len(payload) if len(payload) < 0x4000 else nbits
+                payload = payload[:nbits]
+        else:                                                # raw noise with a few flags dropped in
+            bits01 = rng.integers(0, 2, nbits, dtype=np.uint8)
+            payload = "".join("01"[b] for b in bits01)
+            for _ in range(int(rng.integers(0, 6))):
+                at = int(rng.integers(0, max(1, nbits - 8)))
+                payload = payload[:at] + _flag() + payload[at + 8:]
+        n_oct = -(-nbits // 8)
+        nblk = -(-n_oct // 249)
+        corrupt = [(int(rng.integers(0, nblk)), int(rng.integers(0, 255)), int(rng.integers(1, 256)))
+                   for _ in range(int(rng.integers(0, 9)) if trial % 3 == 1 else 0)]
+        last_len = n_oct - (nblk - 1) * 249
+        corrupt = [(r, c, x) for (r, c, x) in corrupt if not (r == nblk - 1 and last_len <= c < 249)]   # keep to transmitted octets
+        try:
+            bits, info = synth.burst_bits_from_payload(payload, corrupt_octets=corrupt)
+        except ValueError:
+            continue
+        descr = bits ^ synth.scrambler_sequence(len(bits))
+        st_o, fr_o, corr_o, rs_o = po.decode_burst_bits(descr[25:], info["datalen_bits"])
+        st_k, fr_k, corr_k, rs_k, crcs = hs.k3(bits, info["datalen_bits"])
+        assert (st_k, fr_k, corr_k) == (st_o, fr_o, corr_o), (trial, nbits, st_k, st_o, len(fr_k), len(fr_o))
+        assert list(rs_k) == list(rs_o), (trial, list(rs_k), list(rs_o))
+        assert [int(c) for c in crcs] == [po.crc16(f) for f in fr_k]
+        done += 1
+    assert done > 140
