@@ -65,6 +65,52 @@ def test_oracle_matches_live_reference_on_replicas(flavour):
             assert a.num_fec_corrections == b["num_fec_corrections"]
 
 
+@pytest.mark.skipif(po.ref_binary("strict") is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_matches_live_reference_on_fuzzed_payloads():
+    """Differential fuzz of the burst decoder against the reference itself: transmissions whose payloads are random
+    bits, or stuffed frames cut at a random bit, some with corrupted code words and header bits, modulated and run
+    through oracle/_ref (unmodified src/decode.c, bitstream.c, rs.c) and through the restatement."""
+    from dumpvdl2_b200 import synth
+    rng = np.random.default_rng(0x7E7E)
+    F = "01111110"
+
+    def stuffed(n):
+        return "".join(format(b, "08b")[::-1] for b in rng.integers(0, 256, n, dtype=np.uint8)).replace("11111", "111110")
+    fs, offs = 2100000, [100e3, -100e3]
+    bursts, t = [], [0.02, 0.02]
+    for k in range(18):
+        nbits = int(rng.integers(40, 5000))
+        if k % 3 == 0:
+            pl = "".join("01"[b] for b in rng.integers(0, 2, nbits, dtype=np.uint8))
+        else:
+            pl = F
+            while len(pl) < nbits:
+                pl += stuffed(int(rng.integers(0, 200))) + F * int(rng.integers(1, 3))
+            if k % 3 == 1:
+                pl = pl[:nbits]
+        n_oct = -(-len(pl) // 8)
+        nblk = -(-n_oct // 249)
+        corrupt = [(int(rng.integers(0, nblk)), int(rng.integers(0, min(249, n_oct - (nblk - 1) * 249))), int(rng.integers(1, 256)))
+                   for _ in range(int(rng.integers(0, 5)) if k % 2 else 0)]
+        hdr = (int(rng.integers(0, 25)),) if k % 5 == 4 else ()
+        ch = k % 2
+        try:
+            synth.burst_bits_from_payload(pl, corrupt)
+        except ValueError:
+            continue
+        bursts.append(synth.BurstSpec(t[ch], offs[ch], [], power_dbfs=-12.0, payload=pl, corrupt_octets=corrupt, header_bit_errors=hdr))
+        t[ch] += synth.burst_duration_s(None, payload=pl) + 0.012
+    iq = synth.synth_stream(fs, max(t) + 0.02, bursts, es_n0_db=32, fmt="u8", seed=0x7E7F)
+    c = cases._mk("fuzz", fs, "u8", [cases.CENTER + o for o in offs], iq, chunk=524288, bursts=bursts)
+    with tempfile.NamedTemporaryFile(suffix=".cu8") as tf:
+        tf.write(c["iq"].tobytes()); tf.flush()
+        ref, _ = po.run_ref(tf.name, po.FMT_U8, c["oversample"], c["centerfreq"], c["freqs"], flavour="strict", chunk=c["chunk"])
+    fr = sorted(util.run_oracle(c).frames(), key=lambda f: f.key())
+    assert len(fr) == len(ref) and len(fr) > 20
+    for a, b in zip(fr, ref):
+        assert (a.channel, a.idx, a.data, a.num_fec_corrections, a.synd_weight) == (b["channel"], b["idx"], b["data"], b["num_fec_corrections"], b["synd_weight"])
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference sources not mounted")
 def test_tables_against_reference_literals():
     src = open("/root/reference/src/decode.c").read()
