@@ -159,6 +159,29 @@ def case_maxlen():
     return _mk("maxlen", fs, "u8", [CENTER + 100e3, CENTER - 100e3], iq, chunk=524288, bursts=bursts)
 
 
+def case_stress():
+    """Impairments the goldens do not carry (CPU-only differential case, not a golden): carrier offsets up to
+    +-900 Hz (beyond and within the sync range), powers from -45 dBFS to clipping, bursts following each other
+    after 0.3-2 ms (the sample after a burst, the 150 samples after a reset), two bursts overlapping on one
+    channel, cu8 quantisation at low level."""
+    fs = 2100000
+    offs = [-150e3, -75e3, 50e3, 125e3, 300e3, -425e3]
+    rng = np.random.default_rng(4711)
+    bursts = []
+    for i, o in enumerate(offs):
+        t = 0.005 + 0.003 * i
+        for k in range(5):
+            fr = synth.random_frames(rng, lo=11, hi=120)
+            pw = float(rng.choice([-45.0, -30.0, -18.0, -9.0, -2.0, 1.5]))
+            bursts.append(synth.BurstSpec(t, o, fr, power_dbfs=pw, freq_err_hz=float(rng.uniform(-900, 900))))
+            gap = float(rng.choice([0.0003, 0.001, 0.002, 0.015]))
+            t += synth.burst_duration_s(fr) + gap
+            if k == 3 and i % 2 == 0:
+                t -= 0.004                                # the next burst starts before this one has ended
+    iq = synth.synth_stream(fs, 0.6, bursts, noise_power=10 ** (-38 / 10), fmt="u8", seed=4712)
+    return _mk("stress", fs, "u8", [CENTER + o for o in offs], iq, chunk=2 * 77777, bursts=bursts)
+
+
 def case_noisy():
     """Low SNR (Es/N0 19.5 dB): symbol errors, RS corrections and failures, false syncs on noise."""
     fs = 2100000

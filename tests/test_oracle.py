@@ -66,6 +66,22 @@ def test_oracle_matches_live_reference_on_replicas(flavour):
 
 
 @pytest.mark.skipif(po.ref_binary("strict") is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_matches_live_reference_on_stress_stream():
+    """Demodulator-side differential: carrier offsets, clipping / very weak bursts, back-to-back and overlapping
+    bursts (cases.case_stress) - frames and printed metadata identical to the strictly compiled reference."""
+    c = cases.case_stress()
+    with tempfile.NamedTemporaryFile(suffix=".cu8") as tf:
+        tf.write(c["iq"].tobytes()); tf.flush()
+        ref, _ = po.run_ref(tf.name, po.FMT_U8, c["oversample"], c["centerfreq"], c["freqs"], flavour="strict", chunk=c["chunk"])
+    fr = sorted(util.run_oracle(c).frames(), key=lambda f: f.key())
+    assert len(fr) == len(ref) and len(fr) > 15, (len(fr), len(ref))
+    for a, b in zip(fr, ref):
+        assert (a.channel, a.idx, a.data, a.num_fec_corrections, a.synd_weight) == (b["channel"], b["idx"], b["data"], b["num_fec_corrections"], b["synd_weight"])
+        assert abs(a.frame_pwr_dbfs - b["frame_pwr_dbfs"]) < 2e-3 and abs(a.nf_pwr_dbfs - b["nf_pwr_dbfs"]) < 2e-3
+        assert abs(a.ppm_error - b["ppm_error"]) < 2e-3
+
+
+@pytest.mark.skipif(po.ref_binary("strict") is None, reason="oracle/_ref not built (needs /root/reference)")
 def test_oracle_matches_live_reference_on_fuzzed_payloads():
     """Differential fuzz of the burst decoder against the reference itself: transmissions whose payloads are random
     bits, or stuffed frames cut at a random bit, some with corrupted code words and header bits, modulated and run
