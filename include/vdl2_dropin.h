@@ -27,8 +27,14 @@
 #include <sys/time.h>
 
 #ifdef VDL2_DROPIN_USE_REFERENCE_HEADERS
+#ifdef __cplusplus
+extern "C" {                           /* the reference's headers are plain C */
+#endif
 #include "dumpvdl2.h"
 #include "output-common.h"
+#ifdef __cplusplus
+}
+#endif
 #else
 /* ---- layout mirrors (interface declarations; field order and types as in the reference) ---- */
 typedef struct {                       /* src/dumpvdl2.h:290-293 */

@@ -58,3 +58,21 @@ def test_dropin_harness_reproduces_reference_output(name):
         assert int(a["synd"]) == b["synd_weight"] and int(a["datalen"]) == b["datalen_octets"] and int(a["fec"]) == b["num_fec_corrections"]
         for k, g in (("pwr", "frame_pwr_dbfs"), ("nf", "nf_pwr_dbfs"), ("ppm", "ppm_error")):
             assert float(a[k]) == float(f"{b[g]:.9g}"), (k, a[k], b[g])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference sources not mounted")
+def test_shim_compiles_against_the_reference_headers():
+    """INTEGRATION.md build mode -DVDL2_DROPIN_USE_REFERENCE_HEADERS: the shim translation unit compiles with the
+    reference's own dumpvdl2.h / output-common.h in place of the layout mirrors (glib / libacars stubbed as for the
+    oracle build), i.e. every replaced symbol has exactly the reference's prototype."""
+    from dumpvdl2_b200 import build as b
+    with tempfile.TemporaryDirectory() as td:
+        cmd = [b._nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-fmad=false",
+               "-DVDL2_DROPIN_USE_REFERENCE_HEADERS", "-I/root/reference/src", "-I" + os.path.join(ROOT, "oracle", "ref_shim"),
+               "-I" + os.path.join(ROOT, "include"), "-I" + b.CSRC, "-Xcompiler", "-fPIC", "-c",
+               os.path.join(b.CSRC, "vdl2_dropin.cu"), "-o", os.path.join(td, "dropin.o")]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        syms = subprocess.run(["nm", "--defined-only", os.path.join(td, "dropin.o")], capture_output=True, text=True).stdout
+        for s in ("vdl2_channel_init", "process_buf_uchar", "process_buf_short", "process_samples", "rs_verify", "rs_init", "sbuf"):
+            assert f" {s}\n" in syms or f" {s}" in syms.split(), s
