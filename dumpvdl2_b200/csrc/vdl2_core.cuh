@@ -596,6 +596,12 @@ struct vdl2_walk_pref {
 	int valid;
 };
 
+/* offset of the first sync attempt in a block entered with this state (0 when the block will not take the fast path) */
+VDL2_HD int vdl2_walk_first(const vdl2_chan &v) {
+	const bool fast = !(v.state & VDL2_ST_LOCKED) && vdl2_dec_state(v) != VDL2_DEC_IDLE && v.sclk >= 0 && v.sclk < VDL2_SYNC_SKIP;
+	return fast ? (VDL2_SYNC_SKIP - 1) - v.sclk : 0;
+}
+
 VDL2_HD void vdl2_walk_tail(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env, uint32_t chan_idx, uint64_t idx0,
 		const float2 *dec, const float *phase, const float *mag, size_t stride, int resume) {
 	int t = resume;

@@ -350,8 +350,18 @@ __global__ void __launch_bounds__(256) k_copy_rows(const float *__restrict__ src
 	if(i < n) dst[i] = src[i];
 }
 
-/* MODE: 0 sync attempts from the phase plane, TwoSum unwrap; 1 phase plane, table unwrap; 2 phase ring + inputs
- * requested one block ahead, table unwrap (default) */
+/* 4-byte asynchronous global->shared copies (LDGSTS): completion is tracked per thread by commit/wait groups, not
+ * by the register scoreboards, so a look-ahead built on them cannot alias with its own consumer. */
+__device__ __forceinline__ void k2_cp_async4(float *smem_dst, const float *gsrc) {
+	const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void k2_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void k2_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+/* MODE: 0 sync attempts from the phase plane, TwoSum unwrap; 1 phase plane, table unwrap (default); 2 phase ring,
+ * block inputs loaded one block ahead into registers; 3 phase ring, block inputs staged one block ahead in shared
+ * memory by cp.async (experimental, VDL2GPU_K2_VARIANT=4: written at the end of round 1, not yet run on hardware) */
 template<int BLOCK, bool BLOCKED, int MODE>
 __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	__shared__ float s_ring[VDL2_SYNC_BUFLEN * BLOCK];
@@ -398,7 +408,48 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	const float *mgs = p.mag + ch;
 	uint32_t m = 0;
 	if(BLOCKED) {
-		if(MODE == 2) {
+		if(MODE == 3) {
+			/* stage[buf][k][lane]: k = 0..11 the block's phases, 12..15 the magnitudes at the predicted attempt offsets */
+			__shared__ float s_stage[2 * 16 * BLOCK];
+			float *stg = s_stage + tid;
+			int first_cur = 0;                                   /* attempt offset the buffer about to be consumed was staged for */
+			uint32_t b = 0;
+			if(m + VDL2_WALK_BLOCK <= p.n_dec) {
+				const int f0 = vdl2_walk_first(v);
+#pragma unroll
+				for(int t = 0; t < VDL2_WALK_BLOCK; t++) k2_cp_async4(stg + t * BLOCK, phs + (size_t)t * s);
+#pragma unroll
+				for(int j = 0; j < 4; j++) k2_cp_async4(stg + (12 + j) * BLOCK, mgs + (size_t)(f0 + VDL2_SYNC_SKIP * j) * s);
+				k2_cp_async_commit();
+				first_cur = f0;
+			}
+#pragma unroll 1
+			for(; m + VDL2_WALK_BLOCK <= p.n_dec; m += VDL2_WALK_BLOCK, b ^= 1u) {
+				const size_t o = (size_t)m * s;
+				k2_cp_async_wait_all();
+				vdl2_walk_pref pf;
+				const float *cur = stg + b * 16 * BLOCK;
+#pragma unroll
+				for(int t = 0; t < VDL2_WALK_BLOCK; t++) pf.pw[t] = cur[t * BLOCK];
+#pragma unroll
+				for(int j = 0; j < 4; j++) pf.mg[j] = cur[(12 + j) * BLOCK];
+				pf.first = first_cur; pf.valid = 1;
+				if(m + 2 * VDL2_WALK_BLOCK <= p.n_dec) {             /* next block's inputs into the other buffer */
+					const int fn = vdl2_walk_first(v);                /* prediction: the attempt offset repeats every block */
+					float *nxt = stg + (b ^ 1u) * 16 * BLOCK;
+					const float *ph_n = phs + o + (size_t)VDL2_WALK_BLOCK * s;
+					const float *mg_n = mgs + o + (size_t)VDL2_WALK_BLOCK * s;
+#pragma unroll
+					for(int t = 0; t < VDL2_WALK_BLOCK; t++) k2_cp_async4(nxt + t * BLOCK, ph_n + (size_t)t * s);
+#pragma unroll
+					for(int j = 0; j < 4; j++) k2_cp_async4(nxt + (12 + j) * BLOCK, mg_n + (size_t)(fn + VDL2_SYNC_SKIP * j) * s);
+					first_cur = fn;
+				}
+				k2_cp_async_commit();
+				vdl2_walk_block_ring(v, ring, BLOCK, env, ch, p.dec_base + m, dec + o, phs + o, mgs + o, s, pf, false);
+			}
+			k2_cp_async_wait_all();
+		} else if(MODE == 2) {
 			vdl2_walk_pref pf;
 			pf.valid = 0; pf.first = 0;
 #pragma unroll
@@ -661,6 +712,7 @@ extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
 	static int variant = -1;
 	if(variant < 0) {
 		const char *ev = getenv("VDL2GPU_K2_VARIANT"); variant = ev ? atoi(ev) : 2;
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 3>);
 		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 2>);
 		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 1>);
 		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 0>);
@@ -672,7 +724,8 @@ extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
 	if(variant == 0) k2_sync_slice<K2_BLOCK, false, 0><<<blocks, K2_BLOCK, 0, st>>>(*p);              /* per-sample walk */
 	else if(variant == 1) k2_sync_slice<K2_BLOCK, true, 0><<<blocks, K2_BLOCK, 0, st>>>(*p);         /* blocked, phase plane, TwoSum unwrap */
 	else if(variant == 2) k2_sync_slice<K2_BLOCK, true, 1><<<blocks, K2_BLOCK, 0, st>>>(*p);         /* blocked, phase plane, table unwrap */
-	else k2_sync_slice<K2_BLOCK, true, 2><<<blocks, K2_BLOCK, 0, st>>>(*p);                          /* blocked, phase ring, inputs one block ahead */
+	else if(variant == 3) k2_sync_slice<K2_BLOCK, true, 2><<<blocks, K2_BLOCK, 0, st>>>(*p);         /* blocked, phase ring, inputs one block ahead (registers) */
+	else k2_sync_slice<K2_BLOCK, true, 3><<<blocks, K2_BLOCK, 0, st>>>(*p);                          /* blocked, phase ring, inputs one block ahead (cp.async staging) */
 	int e = (int)cudaGetLastError();
 	if(e) return e;
 	/* history for the next chunk: rows [n_dec, n_dec+160) -> [0, 160) */

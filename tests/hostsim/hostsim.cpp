@@ -110,7 +110,35 @@ int hostsim_k2k3(const float *dec /*[n_dec][n_ch][2]*/, uint32_t n_dec, uint32_t
 		uint32_t n = n_dec - base < 1024 ? n_dec - base : 1024;
 		for(uint32_t ch = 0; ch < n_ch; ch++) {
 			uint32_t m = 0;
-			if(use_pre == 3) {                /* the kernel's ring walk, inputs requested one block ahead */
+			if(use_pre == 4) {                /* the kernel's staged ring walk (MODE 3): same control flow, the cp.async copies done at once */
+				float stage[2][16];
+				int first_cur = 0;
+				uint32_t b = 0;
+				const float *phs = &phase[((size_t)base + VDL2_SYNC_BUFLEN) * n_ch + ch];
+				const float *mgs = &mag[(size_t)base * n_ch + ch];
+				if(m + VDL2_WALK_BLOCK <= n) {
+					const int f0 = vdl2_walk_first(chans[ch]);
+					for(int t = 0; t < VDL2_WALK_BLOCK; t++) stage[0][t] = phs[(size_t)t * n_ch];
+					for(int j = 0; j < 4; j++) stage[0][12 + j] = mgs[(size_t)(f0 + VDL2_SYNC_SKIP * j) * n_ch];
+					first_cur = f0;
+				}
+				for(; m + VDL2_WALK_BLOCK <= n; m += VDL2_WALK_BLOCK, b ^= 1u) {
+					const size_t o = (size_t)(base + m) * n_ch + ch;
+					vdl2_walk_pref pf;
+					for(int t = 0; t < VDL2_WALK_BLOCK; t++) pf.pw[t] = stage[b][t];
+					for(int j = 0; j < 4; j++) pf.mg[j] = stage[b][12 + j];
+					pf.first = first_cur; pf.valid = 1;
+					if(m + 2 * VDL2_WALK_BLOCK <= n) {
+						const int fn = vdl2_walk_first(chans[ch]);
+						const float *ph_n = phs + (size_t)(m + VDL2_WALK_BLOCK) * n_ch, *mg_n = mgs + (size_t)(m + VDL2_WALK_BLOCK) * n_ch;
+						for(int t = 0; t < VDL2_WALK_BLOCK; t++) stage[b ^ 1u][t] = ph_n[(size_t)t * n_ch];
+						for(int j = 0; j < 4; j++) stage[b ^ 1u][12 + j] = mg_n[(size_t)(fn + VDL2_SYNC_SKIP * j) * n_ch];
+						first_cur = fn;
+					}
+					vdl2_walk_block_ring(chans[ch], &rings[(size_t)ch * VDL2_SYNC_BUFLEN], 1, env, ch, base + m,
+							reinterpret_cast<const float2 *>(dec2 + o), &phase[o + (size_t)VDL2_SYNC_BUFLEN * n_ch], &mag[o], n_ch, pf, false);
+				}
+			} else if(use_pre == 3) {         /* the kernel's ring walk, inputs requested one block ahead */
 				vdl2_walk_pref pf;
 				memset(&pf, 0, sizeof(pf));
 				for(; m + VDL2_WALK_BLOCK <= n; m += VDL2_WALK_BLOCK) {
