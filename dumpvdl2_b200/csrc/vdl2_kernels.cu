@@ -723,9 +723,9 @@ extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
 	}
 	if(variant == 0) k2_sync_slice<K2_BLOCK, false, 0><<<blocks, K2_BLOCK, 0, st>>>(*p);              /* per-sample walk */
 	else if(variant == 1) k2_sync_slice<K2_BLOCK, true, 0><<<blocks, K2_BLOCK, 0, st>>>(*p);         /* blocked, phase plane, TwoSum unwrap */
-	else if(variant == 2) k2_sync_slice<K2_BLOCK, true, 1><<<blocks, K2_BLOCK, 0, st>>>(*p);         /* blocked, phase plane, table unwrap */
 	else if(variant == 3) k2_sync_slice<K2_BLOCK, true, 2><<<blocks, K2_BLOCK, 0, st>>>(*p);         /* blocked, phase ring, inputs one block ahead (registers) */
-	else k2_sync_slice<K2_BLOCK, true, 3><<<blocks, K2_BLOCK, 0, st>>>(*p);                          /* blocked, phase ring, inputs one block ahead (cp.async staging) */
+	else if(variant == 4) k2_sync_slice<K2_BLOCK, true, 3><<<blocks, K2_BLOCK, 0, st>>>(*p);         /* blocked, phase ring, inputs one block ahead (cp.async staging) */
+	else k2_sync_slice<K2_BLOCK, true, 1><<<blocks, K2_BLOCK, 0, st>>>(*p);                          /* default (2, or any unknown value): blocked, phase plane, table unwrap */
 	int e = (int)cudaGetLastError();
 	if(e) return e;
 	/* history for the next chunk: rows [n_dec, n_dec+160) -> [0, 160) */
