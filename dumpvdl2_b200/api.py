@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvdl2gpu.so")
 FMT_U8, FMT_S16 = 0, 1
-FLAG_TRACE, FLAG_KEEP_DEC, FLAG_K1_SCALAR, FLAG_NO_OVERLAP = 1, 2, 4, 8
+FLAG_TRACE, FLAG_KEEP_DEC, FLAG_K1_SCALAR, FLAG_NO_OVERLAP, FLAG_NO_GRAPH = 1, 2, 4, 8, 16
 NUM_COUNTERS = 9
 COUNTER_NAMES = ["sync_good", "hdr_crc_good", "bursts", "burst_err", "blocks_processed",
                  "blocks_fec_ok", "msg_good", "fcs_good", "fcs_bad"]
@@ -32,7 +32,7 @@ class _Config(C.Structure):
     _fields_ = [("sample_rate", C.c_uint32), ("oversample", C.c_uint32), ("sample_fmt", C.c_uint32),
                 ("centerfreq", C.c_uint32), ("n_channels", C.c_uint32), ("freqs", C.POINTER(C.c_uint32)),
                 ("max_ppm", C.c_float), ("max_chunk_bytes", C.c_uint32), ("device", C.c_int32),
-                ("flags", C.c_uint32), ("n_inflight", C.c_uint32), ("reserved", C.c_uint32 * 5)]
+                ("flags", C.c_uint32), ("n_inflight", C.c_uint32), ("n_streams", C.c_uint32), ("reserved", C.c_uint32 * 4)]
 
 
 class _Frame(C.Structure):
@@ -48,7 +48,7 @@ class _Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("chunks_submitted", "chunks_completed", "iq_samples", "dec_samples", "demod_sync_good",
                  "decoder_crc_good", "bursts", "burst_errors", "blocks_processed", "blocks_fec_ok", "msg_good",
-                 "fcs_good", "fcs_bad", "pool_overflows", "out_overflows", "kernel_launches", "out_bytes")] + [("reserved", C.c_uint64 * 3)]
+                 "fcs_good", "fcs_bad", "pool_overflows", "out_overflows", "kernel_launches", "out_bytes", "graph_launches")] + [("reserved", C.c_uint64 * 2)]
 
 
 class _Event(C.Structure):
@@ -92,6 +92,18 @@ def load_library():
     L.vdl2gpu_launch_convert.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.vdl2gpu_launch_fcs_crc16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.vdl2gpu_launch_rs_verify.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.vdl2gpu_stage_device_bytes.restype = C.c_size_t
+    L.vdl2gpu_stage_device_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    L.vdl2gpu_stage_row_stride.restype = C.c_uint32
+    L.vdl2gpu_stage_row_stride.argtypes = [C.c_uint32]
+    L.vdl2gpu_stage_create.argtypes = [C.POINTER(_Config), C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.vdl2gpu_stage_destroy.argtypes = [C.c_void_p]
+    L.vdl2gpu_stage_levels.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.vdl2gpu_launch_mix_iir_decimate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p]
+    L.vdl2gpu_launch_sync_slice.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.vdl2gpu_launch_burst_fec.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.vdl2gpu_parse_records.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, _FRAME_CB, C.c_void_p]
+    L.vdl2gpu_stage_read_events.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     _LIB = L
     return L
 
@@ -131,12 +143,50 @@ def serialize_raw_frame(frame, station_id=None, timestamp=(0, 0)):
     return bytes(out[:n])
 
 
+def frame_from_c(f):
+    """vdl2gpu_frame (ctypes) -> Frame"""
+    o = Frame()
+    o.channel, o.freq, o.burst_seq, o.idx = f.channel, f.freq, f.burst_seq, f.idx
+    o.data = C.string_at(f.data, f.len) if f.len else b""
+    o.synd_weight, o.datalen_octets, o.num_fec_corrections = f.synd_weight, f.datalen_octets, f.num_fec_corrections
+    o.frame_pwr_dbfs, o.nf_pwr_dbfs, o.ppm_error = f.frame_pwr_dbfs, f.nf_pwr_dbfs, f.ppm_error
+    o.frame_pwr, o.mag_nf = f.frame_pwr, f.mag_nf
+    o.sync_dec_index = f.sync_dec_index
+    o.burst_timestamp = f.burst_timestamp.tv_sec + 1e-6 * f.burst_timestamp.tv_usec
+    o.fcs_ok = bool(f.fcs_ok)
+    return o
+
+
+def make_config(sample_rate, oversample, sample_fmt, centerfreq, freqs, max_ppm=0.0, flags=0):
+    """(vdl2gpu_config, the freqs array it points at) for the stage stubs"""
+    fr = np.ascontiguousarray(freqs, dtype=np.uint32)
+    cfg = _Config()
+    cfg.sample_rate, cfg.oversample, cfg.sample_fmt, cfg.centerfreq = sample_rate, oversample, sample_fmt, centerfreq
+    cfg.n_channels = int(fr.size)
+    cfg.freqs = fr.ctypes.data_as(C.POINTER(C.c_uint32))
+    cfg.max_ppm, cfg.flags, cfg.device = max_ppm, flags, -1
+    return cfg, fr
+
+
+def parse_records(region_bytes, decimated_rate):
+    """host copy of a vdl2gpu_launch_burst_fec region -> [Frame]"""
+    L = load_library()
+    out = []
+    cb = _FRAME_CB(lambda fp, _u: out.append(frame_from_c(fp.contents)))
+    buf = np.frombuffer(region_bytes, np.uint8)
+    _check(L, L.vdl2gpu_parse_records(buf.ctypes.data, buf.size, decimated_rate, cb, None), "vdl2gpu_parse_records")
+    return out
+
+
 class Vdl2Channels:
     """N VDL2 channels demodulated from one IQ stream on one B200."""
 
     def __init__(self, sample_rate, oversample, sample_fmt, centerfreq, freqs, max_ppm=0.0,
-                 max_chunk_bytes=1 << 20, device=-1, flags=0, n_inflight=4):
+                 max_chunk_bytes=1 << 20, device=-1, flags=0, n_inflight=4, n_streams=1):
+        """n_streams > 1: independent-streams mode, channels [s*C, (s+1)*C) demodulate stream s; process_buf_* then take
+        the S per-stream buffers back to back."""
         self.L = load_library()
+        self.n_streams = int(n_streams)
         self.freqs = np.ascontiguousarray(freqs, dtype=np.uint32)
         self.n_channels = int(self.freqs.size)
         self.sample_fmt = sample_fmt
@@ -145,6 +195,7 @@ class Vdl2Channels:
         cfg.n_channels = self.n_channels
         cfg.freqs = self.freqs.ctypes.data_as(C.POINTER(C.c_uint32))
         cfg.max_ppm, cfg.max_chunk_bytes, cfg.device, cfg.flags, cfg.n_inflight = max_ppm, max_chunk_bytes, device, flags, n_inflight
+        cfg.n_streams = self.n_streams
         self.h = C.c_void_p()
         _check(self.L, self.L.vdl2gpu_create(C.byref(cfg), C.byref(self.h)), "vdl2gpu_create")
         self._frames = []
@@ -162,17 +213,7 @@ class Vdl2Channels:
             pass
 
     def _on_frame(self, fp, _user):
-        f = fp.contents
-        o = Frame()
-        o.channel, o.freq, o.burst_seq, o.idx = f.channel, f.freq, f.burst_seq, f.idx
-        o.data = C.string_at(f.data, f.len) if f.len else b""
-        o.synd_weight, o.datalen_octets, o.num_fec_corrections = f.synd_weight, f.datalen_octets, f.num_fec_corrections
-        o.frame_pwr_dbfs, o.nf_pwr_dbfs, o.ppm_error = f.frame_pwr_dbfs, f.nf_pwr_dbfs, f.ppm_error
-        o.frame_pwr, o.mag_nf = f.frame_pwr, f.mag_nf
-        o.sync_dec_index = f.sync_dec_index
-        o.burst_timestamp = f.burst_timestamp.tv_sec + 1e-6 * f.burst_timestamp.tv_usec
-        o.fcs_ok = bool(f.fcs_ok)
-        self._frames.append(o)
+        self._frames.append(frame_from_c(fp.contents))
 
     # ---- the reference's entry points for this path ----
     def process_buf_uchar(self, buf):
@@ -187,7 +228,9 @@ class Vdl2Channels:
         if fmt != self.sample_fmt:
             raise Vdl2GpuError("sample format differs from the one the channels were created with")
         b = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
-        _check(self.L, self.L.vdl2gpu_submit(self.h, b.ctypes.data, b.size), "vdl2gpu_submit")
+        if b.size % self.n_streams:
+            raise Vdl2GpuError("buffer size is not a multiple of n_streams")
+        _check(self.L, self.L.vdl2gpu_submit(self.h, b.ctypes.data, b.size // self.n_streams), "vdl2gpu_submit")
 
     def submit(self, buf):
         return self._submit(buf, self.sample_fmt)
@@ -267,7 +310,7 @@ class Vdl2Channels:
         _check(self.L, self.L.vdl2gpu_enable_timing(self.h, 1 if on else 0), "vdl2gpu_enable_timing")
 
     def kernel_ms(self):
-        ms = (C.c_double * 4)()
-        n = (C.c_uint64 * 4)()
+        ms = (C.c_double * 5)()
+        n = (C.c_uint64 * 5)()
         _check(self.L, self.L.vdl2gpu_get_kernel_ms(self.h, ms, n), "vdl2gpu_get_kernel_ms")
-        return dict(K0=(ms[0], n[0]), K1=(ms[1], n[1]), K2=(ms[2], n[2]), K3=(ms[3], n[3]))
+        return dict(K0=(ms[0], n[0]), K1=(ms[1], n[1]), K2a=(ms[2], n[2]), K2=(ms[3], n[3]), K3=(ms[4], n[4]))

@@ -1,0 +1,127 @@
+/*
+ * vdl2_fastmath.cuh — (float)atan2((double)im, (double)re) and hypotf() of a decimated sample without the
+ * general-purpose libm routines.
+ *
+ * The reference obtains a sample's phase as `atan2(im, re)` in double and narrows it to float on store
+ * (src/demod.c:232,256).  What the demodulator consumes is therefore fl32(atan2(im, re)): any evaluation of
+ * atan2 whose error is far below half a float ulp yields the same float, unless the true value lies within that
+ * error of a float rounding boundary (a midpoint between two floats).  vdl2_phase_fast evaluates atan2 in
+ * double with a short argument reduction (9 break points k/8, one division, a degree-5 polynomial in t^2:
+ * ~22 FP64 operations instead of the ~65 of the libdevice routine) and reports, Ziv style, whether its result
+ * is too close to a rounding boundary to be trusted; the caller then falls back to the full routine (about one
+ * sample in a million).  The float returned without the fall-back flag is the correctly rounded one.
+ *
+ * Error budget (relative to the final result r; the guard used is 2^-44, 16x the bound):
+ *   t = num/den      num, den exact in double (|c| <= 1 has 4 significant bits, the floats 24);
+ *                    two Newton steps on a >= 2^-18 reciprocal seed: |dt/t| <= 2^-51
+ *   atan(t)          |t| <= 1/16 (+2^-20 slack from the approximate selection of k); the series is cut after
+ *                    t^11/11: truncation <= t^12/13 <= 2^-51.7 relative to t; evaluation error <= 2^-51
+ *   A_k + atan(t)    table entry rounded to nearest: 2^-54 absolute (values < 1), sum 2^-53 relative
+ *   pi/2 - r, pi - r two-term constants (hi + lo), no cancellation (r <= pi/4 resp. pi/2): 2^-52 relative
+ *   total            < 2^-48 relative to |r| >= ~1e-30 (smaller results and non-finite inputs take the slow path)
+ */
+#ifndef VDL2_FASTMATH_CUH
+#define VDL2_FASTMATH_CUH
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define VDL2_FM_HD __host__ __device__ __forceinline__
+#else
+#define VDL2_FM_HD static inline
+#endif
+
+/* {atan(k/8), k/8} for k = 0..8, atan correctly rounded to double (generated with mpmath at 200 bits) */
+#define VDL2_ATAN_TABLE_INIT { \
+	0.0, 0.0, \
+	0x1.fd5ba9aac2f6ep-4, 0.125, \
+	0x1.f5b75f92c80ddp-3, 0.25, \
+	0x1.6f61941e4def1p-2, 0.375, \
+	0x1.dac670561bb4fp-2, 0.5, \
+	0x1.1e00babdefeb4p-1, 0.625, \
+	0x1.4978fa3269ee1p-1, 0.75, \
+	0x1.700a7c5784634p-1, 0.875, \
+	0x1.921fb54442d18p-1, 1.0 }
+#define VDL2_ATAN_TABLE_DOUBLES 18
+
+#define VDL2_PI_HI 0x1.921fb54442d18p+1
+#define VDL2_PI_LO 0x1.1a62633145c07p-53
+#define VDL2_PIO2_HI 0x1.921fb54442d18p+0
+#define VDL2_PIO2_LO 0x1.1a62633145c07p-54
+
+VDL2_FM_HD double vdl2_fm_rcp_seed(double d) {
+#if defined(__CUDA_ARCH__)
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));      /* MUFU.RCP64H: ~20 good bits */
+	return r;
+#else
+	return (double)(1.0f / (float)d);                          /* any seed good to 2^-18 gives the same bounds */
+#endif
+}
+
+VDL2_FM_HD double vdl2_fm_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+	return __fma_rn(a, b, c);
+#else
+	return fma(a, b, c);
+#endif
+}
+
+/* Returns fl32(atan2(im, re)) and clears *slow, or sets *slow when the caller must use the full routine:
+ * non-finite / zero / extreme inputs, or a result within 2^-44 (relative) of a float rounding boundary.
+ * `tab` points at VDL2_ATAN_TABLE_DOUBLES doubles initialised with VDL2_ATAN_TABLE_INIT (shared memory on the device). */
+VDL2_FM_HD float vdl2_phase_fast(float re, float im, const double *tab, int *slow) {
+	const float ax = fabsf(re), ay = fabsf(im);
+	const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+	/* comparisons are false for NaN (fmaxf/fminf drop a NaN operand, so both components are tested); zero, infinite
+	 * or extreme magnitudes and component ratios below 1e-6 (other than an exact zero) leave the fast path */
+	if(!(ax <= 1.0e30f && ay <= 1.0e30f && mx >= 1.0e-30f && (mn >= mx * 1.0e-6f || mn == 0.0f))) { *slow = 1; return 0.0f; }
+	/* break point: k = round(8 * mn/mx) from an approximate quotient (any neighbour would do) */
+#if defined(__CUDA_ARCH__)
+	const float q = __fmul_rn(mn, __frcp_rn(mx));
+	const uint32_t k = __float_as_uint(__fmaf_rn(q, 8.0f, 12582912.0f)) & 15u;
+#else
+	const float q = mn / mx;
+	float kf = q * 8.0f + 12582912.0f;
+	uint32_t kb; memcpy(&kb, &kf, 4);
+	const uint32_t k = kb & 15u;
+#endif
+	const double A = tab[2 * k], c = tab[2 * k + 1];
+	const double dmx = (double)mx, dmn = (double)mn;
+	const double num = vdl2_fm_fma(-c, dmx, dmn);          /* exact */
+	const double den = vdl2_fm_fma(c, dmn, dmx);           /* exact */
+	double r = vdl2_fm_rcp_seed(den);
+	r = vdl2_fm_fma(r, vdl2_fm_fma(-den, r, 1.0), r);
+	r = vdl2_fm_fma(r, vdl2_fm_fma(-den, r, 1.0), r);
+	double t = num * r;
+	t = vdl2_fm_fma(vdl2_fm_fma(-den, t, num), r, t);       /* one correction: t within an ulp of num/den */
+	const double s = t * t;
+	double p = -0x1.745d1745d1746p-4;                       /* -1/11 */
+	p = vdl2_fm_fma(p, s, 0x1.c71c71c71c71cp-4);            /*  1/9  */
+	p = vdl2_fm_fma(p, s, -0x1.2492492492492p-3);           /* -1/7  */
+	p = vdl2_fm_fma(p, s, 0x1.999999999999ap-3);            /*  1/5  */
+	p = vdl2_fm_fma(p, s, -0x1.5555555555555p-2);           /* -1/3  */
+	double a = A + vdl2_fm_fma(t * s, p, t);
+	if(ay > ax) a = (VDL2_PIO2_HI - a) + VDL2_PIO2_LO;
+	if(re < 0.0f) a = (VDL2_PI_HI - a) + VDL2_PI_LO;
+	/* distance of the double from the nearest float rounding boundary: the 29 bits the narrowing drops */
+	uint64_t bits;
+#if defined(__CUDA_ARCH__)
+	bits = (uint64_t)__double_as_longlong(a);
+#else
+	memcpy(&bits, &a, 8);
+#endif
+	const uint32_t drop = (uint32_t)bits & 0x1FFFFFFFu;
+	const uint32_t dist = drop > 0x10000000u ? drop - 0x10000000u : 0x10000000u - drop;
+	/* 2^-44 relative = 2^8..2^9 units of the last double bit.  a == 0 (im == 0, re > 0) is exact. */
+	*slow = (dist < 512u && a != 0.0) ? 1 : 0;
+	float f = (float)a;
+#if defined(__CUDA_ARCH__)
+	return __uint_as_float(__float_as_uint(f) | (__float_as_uint(im) & 0x80000000u));
+#else
+	return copysignf(f, im);
+#endif
+}
+
+#endif

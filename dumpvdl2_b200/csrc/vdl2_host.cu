@@ -16,6 +16,7 @@
 #include <sys/time.h>
 #include <algorithm>
 #include <deque>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/vdl2gpu.h"
@@ -45,8 +46,13 @@ struct chunk_slot {
 	uint8_t *h_raw = nullptr, *d_raw = nullptr;
 	uint8_t *h_out = nullptr, *d_out = nullptr;
 	cudaEvent_t done = nullptr;
-	cudaEvent_t tk[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   /* front: 0,1,2  back: 3,4,5 */
+	cudaEvent_t tk[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   /* front: 0,1,2  back: 3,6,4,5 */
 	bool busy = false, timed = false;
+	/* per-chunk arguments (pinned host copy, device copy made by the first node of the front graph) and the three
+	 * CUDA graphs of this slot per decimated-sample buffer: front {args copy, K0, K1}, K2a, back {K2, history, K3, finish} */
+	vdl2_chunk_args *h_args = nullptr, *d_args = nullptr;
+	cudaGraphExec_t g_front[2] = { nullptr, nullptr }, g_k2a[2] = { nullptr, nullptr }, g_back[2] = { nullptr, nullptr };
+	uint32_t graph_pairs[2] = { 0, 0 };
 	uint64_t first_pair = 0, dec_base = 0;
 	uint32_t n_pairs = 0, n_dec = 0;
 	struct timeval arrival = { 0, 0 };
@@ -66,6 +72,10 @@ struct vdl2gpu_ctx {
 	uint64_t chunk_seq = 0;
 	cudaEvent_t ev_input_ready = nullptr, ev_input_consumed = nullptr;
 	uint32_t n_ch = 0, n_chp = 0, max_pairs = 0, max_dec = 0, n_slots = 0, out_cap = 0, event_cap = 0;
+	uint32_t n_streams = 1, ch_per_stream = 0;          /* independent-streams mode: n_streams > 1, channels [s*C, (s+1)*C) on stream s */
+	int k1_variant = 2, k2_variant = 2, k2a_mode = 1;   /* A/B knobs (VDL2GPU_K1_VARIANT, VDL2GPU_K2_VARIANT, VDL2GPU_K2A), read at create */
+	bool use_graphs = true;
+	uint64_t overflows_reported = 0;
 	host_tables tab;
 	vdl2_tables *d_tab = nullptr;
 	float4 *d_samples = nullptr;
@@ -84,8 +94,9 @@ struct vdl2gpu_ctx {
 	uint64_t total_pairs = 0, total_dec = 0;
 	uint32_t events_read = 0;
 	bool timing = false;
-	double k_ms[4] = { 0, 0, 0, 0 };
-	uint64_t k_launches[4] = { 0, 0, 0, 0 };
+	double k_ms[5] = { 0, 0, 0, 0, 0 };                 /* K0, K1, K2a, K2 (+history copy), K3 (+finish) */
+	uint64_t k_launches[5] = { 0, 0, 0, 0, 0 };
+	uint32_t graph_nominal = 0;                         /* chunk shape (n_pairs) the graphs are kept for */
 	vdl2gpu_stats stats;
 	std::vector<pending_frame> pending;
 	std::vector<std::vector<uint8_t>> blobs;
@@ -95,6 +106,9 @@ struct vdl2gpu_ctx {
 static uint32_t dphi_for(uint32_t centerfreq, uint32_t freq, uint32_t rate) {      /* src/demod.c:385 */
 	return (uint32_t)(int)(((float)centerfreq - (float)freq) / (float)rate * 256.0f * 65536.0f);
 }
+
+static void initial_state(const vdl2gpu_config &cfg, const uint32_t *freqs, uint32_t n_ch, uint32_t n_chp,
+		std::vector<uint32_t> &k1, std::vector<uint32_t> &k2);
 
 extern "C" int vdl2gpu_abi_version(void) { return VDL2GPU_ABI_VERSION; }
 
@@ -130,6 +144,13 @@ static int free_ctx(vdl2gpu_ctx *c) {
 		if(s.h_out) cudaFreeHost(s.h_out);
 		if(s.done) cudaEventDestroy(s.done);
 		for(auto &e : s.tk) if(e) cudaEventDestroy(e);
+		for(int i = 0; i < 2; i++) {
+			if(s.g_front[i]) cudaGraphExecDestroy(s.g_front[i]);
+			if(s.g_k2a[i]) cudaGraphExecDestroy(s.g_k2a[i]);
+			if(s.g_back[i]) cudaGraphExecDestroy(s.g_back[i]);
+		}
+		if(s.h_args) cudaFreeHost(s.h_args);
+		if(s.d_args) cudaFree(s.d_args);
 	}
 	cudaFree(c->d_tab); cudaFree(c->d_samples); cudaFree(c->d_dec2[0]); cudaFree(c->d_dec2[1]); cudaFree(c->d_phase); cudaFree(c->d_mag); cudaFree(c->d_hist_tmp); cudaFree(c->d_k1); cudaFree(c->d_k2);
 	cudaFree(c->d_counters); cudaFree(c->d_ready); cudaFree(c->d_ring); cudaFree(c->d_pool); cudaFree(c->d_free);
@@ -162,7 +183,26 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 		snprintf(g_last_error, sizeof(g_last_error), "device %d is sm_%d%d; this library carries sm_100a code only", c->device, prop.major, prop.minor);
 		return VDL2GPU_ENODEV;
 	}
+	KL(vdl2_kernels_init_device(c->device));             /* per device: function attributes do not carry over */
 	c->cfg = *cfg;
+	c->n_streams = cfg->n_streams ? cfg->n_streams : 1u;
+	c->cfg.n_streams = c->n_streams;
+	if(c->n_streams > 1) {
+		if(cfg->n_channels % c->n_streams != 0 || (cfg->n_channels / c->n_streams) % 32u != 0) {
+			snprintf(g_last_error, sizeof(g_last_error), "independent-streams mode needs n_channels = n_streams x C with C a multiple of 32 (got %u x %u streams)",
+					cfg->n_channels, c->n_streams);
+			return VDL2GPU_EINVAL;
+		}
+		c->ch_per_stream = cfg->n_channels / c->n_streams;
+	}
+	{
+		const char *e;
+		if((e = getenv("VDL2GPU_K1_VARIANT"))) c->k1_variant = atoi(e);
+		if((e = getenv("VDL2GPU_K2_VARIANT"))) c->k2_variant = atoi(e);
+		if((e = getenv("VDL2GPU_K2A"))) c->k2a_mode = atoi(e);
+		if((e = getenv("VDL2GPU_NO_GRAPH")) && atoi(e)) c->use_graphs = false;
+	}
+	if(cfg->flags & (VDL2GPU_FLAG_NO_GRAPH | VDL2GPU_FLAG_TRACE)) c->use_graphs = false;
 	c->freqs.assign(cfg->freqs, cfg->freqs + cfg->n_channels);
 	c->cfg.freqs = c->freqs.data();
 	c->n_ch = cfg->n_channels;
@@ -198,7 +238,7 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	CU(cudaEventCreateWithFlags(&c->ev_drain, cudaEventDisableTiming));
 	CU(cudaMalloc(&c->d_tab, sizeof(vdl2_tables)));
 	CU(cudaMemcpy(c->d_tab, &c->tab.t, sizeof(vdl2_tables), cudaMemcpyHostToDevice));
-	CU(cudaMalloc(&c->d_samples, (size_t)c->max_pairs * sizeof(float4)));
+	CU(cudaMalloc(&c->d_samples, (size_t)c->n_streams * c->max_pairs * sizeof(float4)));
 	for(int i = 0; i < 2; i++) {
 		CU(cudaMalloc(&c->d_dec2[i], (size_t)c->max_dec * c->n_chp * sizeof(float2)));
 		CU(cudaMemset(c->d_dec2[i], 0, (size_t)c->max_dec * c->n_chp * sizeof(float2)));
@@ -220,23 +260,8 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	CU(cudaMemset(c->d_ring, 0, (size_t)VDL2_SYNC_BUFLEN * c->n_chp * 4));
 	CU(cudaMemset(c->d_pool, 0, (size_t)c->n_slots * sizeof(vdl2_burst_slot)));
 
-	/* per-channel state: vdl2_channel_init + demod_reset (src/demod.c:205-220,379-392), process_samples
-	 * locals (src/demod.c:289-298) */
-	std::vector<uint32_t> k1((size_t)K1_NFIELDS * c->n_chp, 0), k2((size_t)K2_NFIELDS * c->n_chp, 0);
-	auto fbits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
-	for(uint32_t ch = 0; ch < c->n_ch; ch++) {
-		/* a channel on the centre frequency skips the mixer in the reference (src/demod.c:312); with a zero
-		 * phase step the table gives cos = 1, sin = 0 and the products are exact, so no branch is needed */
-		k1[(size_t)K1_DPHI * c->n_chp + ch] = (cfg->centerfreq != c->freqs[ch]) ? dphi_for(cfg->centerfreq, c->freqs[ch], cfg->sample_rate) : 0u;
-		k2[(size_t)K2_MAG_NF * c->n_chp + ch] = fbits(2.0f);
-		k2[(size_t)K2_PHERR1 * c->n_chp + ch] = fbits(1000.f);
-		k2[(size_t)K2_PHERR2 * c->n_chp + ch] = fbits(1000.f);
-		k2[(size_t)K2_STATE * c->n_chp + ch] = VDL2_DEC_HEADER << VDL2_DEC_SHIFT;
-		k2[(size_t)K2_NEED_BITS * c->n_chp + ch] = VDL2_HEADER_LEN;
-		k2[(size_t)K2_SLOT * c->n_chp + ch] = (uint32_t)-1;
-		k2[(size_t)K2_FREQ * c->n_chp + ch] = c->freqs[ch];
-		k2[(size_t)K2_PURE_RUN * c->n_chp + ch] = 0x40000000u;      /* VDL2_PURE_SATURATED: ring of zeros == history of zeros */
-	}
+	std::vector<uint32_t> k1, k2;
+	initial_state(c->cfg, c->freqs.data(), c->n_ch, c->n_chp, k1, k2);
 	CU(cudaMemcpy(c->d_k1, k1.data(), k1.size() * 4, cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(c->d_k2, k2.data(), k2.size() * 4, cudaMemcpyHostToDevice));
 	std::vector<int32_t> fl(c->n_slots);
@@ -249,8 +274,10 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 
 	c->chunks.resize(n_inflight);
 	for(auto &s : c->chunks) {
-		CU(cudaHostAlloc((void **)&s.h_raw, max_bytes, cudaHostAllocDefault));
-		CU(cudaMalloc(&s.d_raw, max_bytes));
+		CU(cudaHostAlloc((void **)&s.h_raw, (size_t)max_bytes * c->n_streams, cudaHostAllocDefault));
+		CU(cudaMalloc(&s.d_raw, (size_t)max_bytes * c->n_streams));
+		CU(cudaHostAlloc((void **)&s.h_args, sizeof(vdl2_chunk_args), cudaHostAllocDefault));
+		CU(cudaMalloc(&s.d_args, sizeof(vdl2_chunk_args)));
 		CU(cudaHostAlloc((void **)&s.h_out, sizeof(vdl2_out_header) + c->out_cap, cudaHostAllocMapped));
 		CU(cudaHostGetDevicePointer((void **)&s.d_out, s.h_out, 0));
 		memset(s.h_out, 0, sizeof(vdl2_out_header));
@@ -265,6 +292,10 @@ extern "C" int vdl2gpu_create(const vdl2gpu_config *cfg, vdl2gpu_ctx **out) {
 			|| cfg->sample_rate != (uint32_t)VDL2_SYMBOL_RATE * VDL2_SPS * cfg->oversample) {
 		snprintf(g_last_error, sizeof(g_last_error), "bad vdl2gpu_config (sample_rate must be 105000*oversample)");
 		return VDL2GPU_EINVAL;
+	}
+	if((uint64_t)(cfg->max_chunk_bytes ? cfg->max_chunk_bytes : (1u << 20)) * (cfg->n_streams ? cfg->n_streams : 1u) >= (1ull << 32)) {
+		snprintf(g_last_error, sizeof(g_last_error), "n_streams x max_chunk_bytes must stay below 4 GiB");
+		return VDL2GPU_ETOOBIG;
 	}
 	vdl2gpu_ctx *c = new vdl2gpu_ctx();
 	int rc = create_impl(cfg, c);
@@ -283,42 +314,34 @@ static uint32_t synd_weight_of(uint32_t syn) {       /* src/decode.c:98-100 */
 	return w[syn & 31u];
 }
 
-static void harvest(vdl2gpu_ctx *c, chunk_slot &s) {
-	if(s.timed) {
-		static const int from[4] = { 0, 1, 3, 4 };              /* K0, K1 on the front stream; K2(+K2a), K3 on the back stream */
-		for(int k = 0; k < 4; k++) {
-			float ms = 0.f;
-			if(cudaEventElapsedTime(&ms, s.tk[from[k]], s.tk[from[k] + 1]) == cudaSuccess) { c->k_ms[k] += ms; c->k_launches[k]++; }
-		}
-		s.timed = false;
-	}
-	const vdl2_out_header *h = reinterpret_cast<const vdl2_out_header *>(s.h_out);
-	const uint8_t *base = s.h_out + sizeof(vdl2_out_header);
-	const vdl2_out_header hcopy = *h; h = &hcopy;
-	/* one copy out of the mapped region, so the region can be handed back to the device at once */
-	c->blobs.emplace_back(base, base + std::min(h->bytes_used, c->out_cap));
-	const uint32_t blob_id = (uint32_t)c->blobs.size() - 1;
-	base = c->blobs.back().data();
-	c->stats.out_bytes += h->bytes_used;            /* out_bytes: record bytes written by K3 (D2H traffic) */
+/* burst records (region = vdl2_out_header + records) -> frames.  Offsets in the pending frames are relative to the
+ * first record.  `dec_end` / `arrival` place the burst in time (see burst_timestamp below). */
+static void parse_region(const uint8_t *region, uint32_t out_cap, double rate, struct timeval arrival, uint64_t dec_end,
+		uint32_t blob_id, std::vector<pending_frame> &pending, vdl2gpu_stats &stats) {
+	vdl2_out_header h;
+	memcpy(&h, region, sizeof(h));
+	const uint8_t *base = region + sizeof(vdl2_out_header);
+	const uint32_t used = std::min(h.bytes_used, out_cap);
+	stats.out_bytes += h.bytes_used;            /* out_bytes: record bytes written by K3 (D2H traffic) */
 	std::vector<const vdl2_burst_record *> recs;
+	recs.reserve(h.n_records);
 	uint32_t off = 0;
-	for(uint32_t k = 0; k < h->n_records && off + sizeof(vdl2_burst_record) <= h->bytes_used; k++) {
+	for(uint32_t k = 0; k < h.n_records && off + sizeof(vdl2_burst_record) <= used; k++) {
 		const vdl2_burst_record *r = reinterpret_cast<const vdl2_burst_record *>(base + off);
-		if(r->rec_bytes < sizeof(vdl2_burst_record) || off + r->rec_bytes > h->bytes_used) break;
+		if(r->rec_bytes < sizeof(vdl2_burst_record) || off + r->rec_bytes > used) break;
 		recs.push_back(r);
 		off += r->rec_bytes;
 	}
 	std::sort(recs.begin(), recs.end(), [](const vdl2_burst_record *a, const vdl2_burst_record *b) {
 		return a->channel != b->channel ? a->channel < b->channel : a->burst_seq < b->burst_seq;
 	});
-	c->stats.pool_overflows = h->pool_overflows;
-	c->stats.out_overflows = h->out_overflows;
-	const double rate = (double)c->cfg.sample_rate / (double)c->cfg.oversample;     /* decimated samples per second */
+	stats.pool_overflows = h.pool_overflows;
+	stats.out_overflows = h.out_overflows;
 	for(const vdl2_burst_record *r : recs) {
-		c->stats.bursts++;
-		if(r->status != VDL2_BURST_OK) c->stats.burst_errors++;
+		stats.bursts++;
+		if(r->status != VDL2_BURST_OK) stats.burst_errors++;
 		for(uint32_t q = 0; q < r->num_blocks && q < VDL2_MAX_BLOCKS; q++)
-			if(r->rs_ret[q] != -128) { c->stats.blocks_processed++; if(r->rs_ret[q] >= 0) c->stats.blocks_fec_ok++; }
+			if(r->rs_ret[q] != -128) { stats.blocks_processed++; if(r->rs_ret[q] >= 0) stats.blocks_fec_ok++; }
 		const uint32_t *tab = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(r) + sizeof(vdl2_burst_record));
 		const uint8_t *bytes = reinterpret_cast<const uint8_t *>(tab + r->n_frames);
 		uint32_t foff = 0;
@@ -342,26 +365,53 @@ static void harvest(vdl2gpu_ctx *c, chunk_slot &s) {
 			pf.f.sync_dec_index = sync_idx;
 			/* the reference stamps gettimeofday() at sync (src/demod.c:246); here: arrival time of the chunk
 			 * being processed when the burst completed, moved back by the distance to the sync sample */
-			double back = ((double)(s.dec_base + s.n_dec) - (double)sync_idx) / rate;
-			double ts = (double)s.arrival.tv_sec + 1e-6 * (double)s.arrival.tv_usec - back;
+			double back = dec_end > sync_idx ? ((double)dec_end - (double)sync_idx) / rate : 0.0;
+			double ts = (double)arrival.tv_sec + 1e-6 * (double)arrival.tv_usec - back;
 			pf.f.burst_timestamp.tv_sec = (time_t)floor(ts);
 			pf.f.burst_timestamp.tv_usec = (suseconds_t)((ts - floor(ts)) * 1e6);
 			pf.f.fcs_residue = (uint16_t)crc;
 			pf.f.fcs_ok = (len >= 11 && crc == 0xF0B8u) ? 1 : 0;
-			c->stats.msg_good++;
-			if(len >= 11) { if(crc == 0xF0B8u) c->stats.fcs_good++; else c->stats.fcs_bad++; }
-			c->pending.push_back(pf);
+			stats.msg_good++;
+			if(len >= 11) { if(crc == 0xF0B8u) stats.fcs_good++; else stats.fcs_bad++; }
+			pending.push_back(pf);
 		}
 	}
+}
+
+static void harvest(vdl2gpu_ctx *c, chunk_slot &s) {
+	if(s.timed) {
+		static const int from[5] = { 0, 1, 3, 6, 4 }, to[5] = { 1, 2, 6, 4, 5 };   /* K0, K1 on the front stream; K2a, K2, K3 on the back stream */
+		for(int k = 0; k < 5; k++) {
+			float ms = 0.f;
+			if(cudaEventElapsedTime(&ms, s.tk[from[k]], s.tk[to[k]]) == cudaSuccess) { c->k_ms[k] += ms; c->k_launches[k]++; }
+		}
+		s.timed = false;
+	}
+	/* one copy out of the mapped region (header + the bytes K3 used), so the region can be handed back to the device at once */
+	const vdl2_out_header *h = reinterpret_cast<const vdl2_out_header *>(s.h_out);
+	const uint32_t used = std::min(h->bytes_used, c->out_cap);
+	c->blobs.emplace_back(s.h_out, s.h_out + sizeof(vdl2_out_header) + used);
+	const uint32_t blob_id = (uint32_t)c->blobs.size() - 1;
+	const double rate = (double)c->cfg.sample_rate / (double)c->cfg.oversample;     /* decimated samples per second */
+	parse_region(c->blobs.back().data(), c->out_cap, rate, s.arrival, s.dec_base + s.n_dec, blob_id, c->pending, c->stats);
 	c->stats.chunks_completed++;
 	s.busy = false;
 }
 
 static int deliver(vdl2gpu_ctx *c, vdl2gpu_frame_cb cb, void *user) {
 	int n = (int)c->pending.size();
+	/* bursts dropped on the device (burst pool or output region exhausted) are an error the caller must see, once per
+	 * increase; the frames that did arrive are still delivered first */
+	const uint64_t ov = c->stats.pool_overflows + c->stats.out_overflows;
+	if(ov > c->overflows_reported) {
+		snprintf(g_last_error, sizeof(g_last_error), "%llu burst(s) dropped on the device: burst pool overflows %llu, output region overflows %llu",
+				(unsigned long long)(ov - c->overflows_reported), (unsigned long long)c->stats.pool_overflows, (unsigned long long)c->stats.out_overflows);
+		c->overflows_reported = ov;
+		n = VDL2GPU_EOVERFLOW;
+	}
 	if(cb) {
 		for(auto &pf : c->pending) {
-			pf.f.data = c->blobs[pf.blob].data() + pf.offset;
+			pf.f.data = c->blobs[pf.blob].data() + sizeof(vdl2_out_header) + pf.offset;
 			cb(&pf.f, user);
 		}
 	}
@@ -386,8 +436,97 @@ static int acquire_slot(vdl2gpu_ctx *c, chunk_slot **out) {
 	return VDL2GPU_OK;
 }
 
+/* parameter blocks of one chunk.  With `ca` the per-chunk values come from the device copy of the chunk arguments
+ * (graph replay); the sizes given here then only size the grids. */
+static void fill_params(vdl2gpu_ctx *c, chunk_slot &s, int db, uint32_t n_pairs, uint32_t cnt0, uint32_t n_dec, uint64_t dec_base,
+		const vdl2_chunk_args *ca, vdl2_k1_params &p1, vdl2_k2_params &p2, vdl2_k3_params &p3) {
+	float2 *d_dec = c->d_dec2[db];
+	p1.samples = c->d_samples; p1.n_pairs = n_pairs; p1.oversample = c->cfg.oversample; p1.cnt0 = cnt0;
+	p1.n_ch = c->n_ch; p1.n_chp = c->n_chp; p1.dec = d_dec; p1.state = c->d_k1;
+	p1.lut = reinterpret_cast<const float4 *>(c->d_tab->lut);
+	p1.a0 = c->tab.t.A[0]; p1.a1 = c->tab.t.A[1]; p1.a2 = c->tab.t.A[2]; p1.b1 = c->tab.t.B[1]; p1.b2 = c->tab.t.B[2];
+	p1.one = 1.0f; p1.neg_one = -1.0f; p1.two = 2.0f;
+	p1.ch_per_stream = c->ch_per_stream; p1.stream_stride = c->max_pairs; p1.ca = ca;
+	p2.dec = d_dec; p2.phase = c->d_phase; p2.mag = c->d_mag; p2.hist_tmp = c->d_hist_tmp; p2.n_dec = n_dec; p2.n_ch = c->n_ch; p2.n_chp = c->n_chp; p2.dec_base = dec_base;
+	p2.state = c->d_k2; p2.ring = c->d_ring; p2.tables = c->d_tab; p2.max_ppm = c->cfg.max_ppm; p2.s27 = c->tab.s27;
+	p2.pool = c->d_pool; p2.free_list = c->d_free; p2.ready = c->d_ready; p2.ctl = c->d_ctl;
+	p2.events = c->d_events; p2.event_cap = c->event_cap; p2.trace = (c->cfg.flags & VDL2GPU_FLAG_TRACE) ? 1u : 0u;
+	p2.variant = (uint32_t)c->k2_variant; p2.k2a_mode = (uint32_t)c->k2a_mode; p2.ca = ca;
+	p3.pool = c->d_pool; p3.free_list = c->d_free; p3.ready = c->d_ready; p3.ctl = c->d_ctl; p3.tables = c->d_tab;
+	p3.out = s.d_out; p3.out_cap = c->out_cap; p3.n_chp = c->n_chp; p3.counters = c->d_counters;
+}
+
+#define K3_GRID (148u * 16u)      /* 16 resident blocks per SM (11.4 KB shared memory each): ~1.5 bursts per block per chunk at the bench traffic */
+
+/* One CUDA graph per stage, slot and decimated-sample buffer, captured once for the chunk shape (n_pairs) and replayed:
+ * a chunk then costs three graph launches and a handful of event calls instead of eight kernel launches.  Everything
+ * that differs between two chunks of the same shape (input pointer, decimation phase, sample counts, absolute sample
+ * index) travels in the chunk-argument block the front graph copies to the device first. */
+static int capture_one(cudaStream_t st, cudaGraphExec_t *out, int (*body)(void *), void *arg) {
+	cudaGraph_t g = nullptr;
+	CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+	int rc = body(arg);
+	cudaError_t e = cudaStreamEndCapture(st, &g);
+	if(rc != 0 || e != cudaSuccess) { if(g) cudaGraphDestroy(g); cudaGetLastError(); return rc ? rc : fail_cuda(e, "cudaStreamEndCapture", __LINE__); }
+	e = cudaGraphInstantiate(out, g, 0);
+	cudaGraphDestroy(g);
+	if(e != cudaSuccess) return fail_cuda(e, "cudaGraphInstantiate", __LINE__);
+	return VDL2GPU_OK;
+}
+
+struct capture_env { vdl2gpu_ctx *c; chunk_slot *s; int db; uint32_t n_pairs; uint32_t k0_fmt; };
+
+static int body_front(void *a) {
+	capture_env *e = static_cast<capture_env *>(a);
+	vdl2gpu_ctx *c = e->c;
+	vdl2_k1_params p1; vdl2_k2_params p2; vdl2_k3_params p3;
+	const uint32_t os = c->cfg.oversample;
+	fill_params(c, *e->s, e->db, e->n_pairs, 0, (os - 1 + e->n_pairs) / os, 0, e->s->d_args, p1, p2, p3);
+	CU(cudaMemcpyAsync(e->s->d_args, e->s->h_args, sizeof(vdl2_chunk_args), cudaMemcpyHostToDevice, c->stream));
+	const uint32_t bpp = c->cfg.sample_fmt == VDL2GPU_FMT_S16_LE ? 4u : 2u;
+	KL(vdl2_launch_k0(nullptr, e->n_pairs, e->k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->n_streams,
+			e->n_pairs * bpp, c->max_pairs, e->s->d_args, c->stream));
+	KL(vdl2_launch_k1(&p1, (c->cfg.flags & VDL2GPU_FLAG_K1_SCALAR) ? 1 : 0, c->k1_variant, c->stream));
+	return 0;
+}
+static int body_k2a(void *a) {
+	capture_env *e = static_cast<capture_env *>(a);
+	vdl2gpu_ctx *c = e->c;
+	vdl2_k1_params p1; vdl2_k2_params p2; vdl2_k3_params p3;
+	const uint32_t os = c->cfg.oversample;
+	fill_params(c, *e->s, e->db, e->n_pairs, 0, (os - 1 + e->n_pairs) / os, 0, e->s->d_args, p1, p2, p3);
+	KL(vdl2_launch_k2a(&p2, c->s_back));
+	return 0;
+}
+static int body_back(void *a) {
+	capture_env *e = static_cast<capture_env *>(a);
+	vdl2gpu_ctx *c = e->c;
+	vdl2_k1_params p1; vdl2_k2_params p2; vdl2_k3_params p3;
+	const uint32_t os = c->cfg.oversample;
+	fill_params(c, *e->s, e->db, e->n_pairs, 0, (os - 1 + e->n_pairs) / os, 0, e->s->d_args, p1, p2, p3);
+	KL(vdl2_launch_k2(&p2, c->s_back));
+	KL(vdl2_launch_copy_hist(&p2, c->s_back));
+	KL(vdl2_launch_k3(&p3, K3_GRID, c->s_back));
+	return 0;
+}
+
+static int ensure_graphs(vdl2gpu_ctx *c, chunk_slot &s, int db, uint32_t n_pairs, uint32_t k0_fmt) {
+	if(s.g_front[db] && s.graph_pairs[db] == n_pairs) return VDL2GPU_OK;
+	if(s.g_front[db]) { cudaGraphExecDestroy(s.g_front[db]); s.g_front[db] = nullptr; }
+	if(s.g_k2a[db]) { cudaGraphExecDestroy(s.g_k2a[db]); s.g_k2a[db] = nullptr; }
+	if(s.g_back[db]) { cudaGraphExecDestroy(s.g_back[db]); s.g_back[db] = nullptr; }
+	capture_env e = { c, &s, db, n_pairs, k0_fmt };
+	int rc = capture_one(c->stream, &s.g_front[db], body_front, &e);
+	if(rc == 0) rc = capture_one(c->s_back, &s.g_k2a[db], body_k2a, &e);
+	if(rc == 0) rc = capture_one(c->s_back, &s.g_back[db], body_back, &e);
+	if(rc == 0) s.graph_pairs[db] = n_pairs;
+	return rc;
+}
+
 static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t n_pairs, uint32_t k0_fmt = 0xFFFFFFFFu) {
 	const uint32_t os = c->cfg.oversample;
+	const bool planar = k0_fmt != 0xFFFFFFFFu;
+	if(!planar) k0_fmt = c->cfg.sample_fmt;
 	s.first_pair = c->total_pairs;
 	s.n_pairs = n_pairs;
 	s.dec_base = c->total_dec;
@@ -395,43 +534,53 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	gettimeofday(&s.arrival, NULL);
 	s.timed = c->timing;
 	const int db = (int)(c->chunk_seq & 1u);                 /* decimated-sample buffer of this chunk */
-	float2 *d_dec = c->d_dec2[db];
+	const uint32_t bpp = c->cfg.sample_fmt == VDL2GPU_FMT_S16_LE ? 4u : 2u;
+	/* graph replay needs the history copy to be the single-kernel form for every chunk of this shape (n_dec >= 160) */
+	bool graph = c->use_graphs && !s.timed && !planar && c->s_back != c->stream && n_pairs / os >= VDL2_SYNC_BUFLEN;
+	if(graph && c->graph_nominal == 0) c->graph_nominal = n_pairs;
+	graph = graph && n_pairs == c->graph_nominal;            /* odd-sized chunks (the tail of a file) take the direct path */
+	if(graph && ensure_graphs(c, s, db, n_pairs, k0_fmt) != VDL2GPU_OK) { c->use_graphs = false; graph = false; }
+	vdl2_k1_params p1; vdl2_k2_params p2; vdl2_k3_params p3;
+	fill_params(c, s, db, n_pairs, c->decim_cnt, s.n_dec, s.dec_base, nullptr, p1, p2, p3);
 	/* ---- front stage: K0, K1 ---- */
-	if(s.timed) CU(cudaEventRecord(s.tk[0], c->stream));
-	KL(vdl2_launch_k0(d_raw, n_pairs, k0_fmt == 0xFFFFFFFFu ? c->cfg.sample_fmt : k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->stream));
-	CU(cudaEventRecord(c->ev_input_consumed, c->stream));
-	if(s.timed) CU(cudaEventRecord(s.tk[1], c->stream));
 	if(c->chunk_seq >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_back_done[db], 0));   /* K2 of chunk c-2 has read this buffer */
 	/* K1 (one warp per SM sub-partition, latency-bound) pairs well with the equally latency-bound walker K2 and K3 of
 	 * the previous chunk, but not with K2a, a full-occupancy issue-bound pass: let K2a of chunk c-1 finish first */
 	if(c->chunk_seq >= 1 && c->s_back != c->stream) CU(cudaStreamWaitEvent(c->stream, c->ev_k2a_done, 0));
-	vdl2_k1_params p1;
-	p1.samples = c->d_samples; p1.n_pairs = n_pairs; p1.oversample = os; p1.cnt0 = c->decim_cnt;
-	p1.n_ch = c->n_ch; p1.n_chp = c->n_chp; p1.dec = d_dec; p1.state = c->d_k1;
-	p1.lut = reinterpret_cast<const float4 *>(c->d_tab->lut);
-	p1.a0 = c->tab.t.A[0]; p1.a1 = c->tab.t.A[1]; p1.a2 = c->tab.t.A[2]; p1.b1 = c->tab.t.B[1]; p1.b2 = c->tab.t.B[2];
-	p1.one = 1.0f; p1.neg_one = -1.0f; p1.two = 2.0f;
-	KL(vdl2_launch_k1(&p1, (c->cfg.flags & VDL2GPU_FLAG_K1_SCALAR) ? 1 : 0, c->stream));
-	if(s.timed) CU(cudaEventRecord(s.tk[2], c->stream));
-	CU(cudaEventRecord(c->ev_k1_done[db], c->stream));
-	/* ---- back stage: K2a, K2, K3 ---- */
-	CU(cudaStreamWaitEvent(c->s_back, c->ev_k1_done[db], 0));
-	if(s.timed) CU(cudaEventRecord(s.tk[3], c->s_back));
-	vdl2_k2_params p2;
-	p2.dec = d_dec; p2.phase = c->d_phase; p2.mag = c->d_mag; p2.hist_tmp = c->d_hist_tmp; p2.n_dec = s.n_dec; p2.n_ch = c->n_ch; p2.n_chp = c->n_chp; p2.dec_base = s.dec_base;
-	p2.state = c->d_k2; p2.ring = c->d_ring; p2.tables = c->d_tab; p2.max_ppm = c->cfg.max_ppm; p2.s27 = c->tab.s27;
-	p2.pool = c->d_pool; p2.free_list = c->d_free; p2.ready = c->d_ready; p2.ctl = c->d_ctl;
-	p2.events = c->d_events; p2.event_cap = c->event_cap; p2.trace = (c->cfg.flags & VDL2GPU_FLAG_TRACE) ? 1u : 0u;
-	KL(vdl2_launch_k2a(&p2, c->s_back));
-	CU(cudaEventRecord(c->ev_k2a_done, c->s_back));
-	KL(vdl2_launch_k2(&p2, c->s_back));
-	CU(cudaEventRecord(c->ev_back_done[db], c->s_back));
-	if(s.timed) CU(cudaEventRecord(s.tk[4], c->s_back));
-	vdl2_k3_params p3;
-	p3.pool = c->d_pool; p3.free_list = c->d_free; p3.ready = c->d_ready; p3.ctl = c->d_ctl; p3.tables = c->d_tab;
-	p3.out = s.d_out; p3.out_cap = c->out_cap; p3.n_chp = c->n_chp; p3.counters = c->d_counters;
-	KL(vdl2_launch_k3(&p3, 148u * 16u, c->s_back));      /* 16 resident blocks per SM (11.4 KB shared memory each): ~1.5 bursts per block per chunk at the bench traffic */
-	if(s.timed) CU(cudaEventRecord(s.tk[5], c->s_back));
+	if(graph) {
+		s.h_args->raw = d_raw; s.h_args->dec_base = s.dec_base; s.h_args->n_pairs = n_pairs; s.h_args->cnt0 = c->decim_cnt;
+		s.h_args->n_dec = s.n_dec; s.h_args->pad = 0;
+		CU(cudaGraphLaunch(s.g_front[db], c->stream));
+		CU(cudaEventRecord(c->ev_input_consumed, c->stream));
+		CU(cudaEventRecord(c->ev_k1_done[db], c->stream));
+		CU(cudaStreamWaitEvent(c->s_back, c->ev_k1_done[db], 0));
+		CU(cudaGraphLaunch(s.g_k2a[db], c->s_back));
+		CU(cudaEventRecord(c->ev_k2a_done, c->s_back));
+		CU(cudaGraphLaunch(s.g_back[db], c->s_back));
+		CU(cudaEventRecord(c->ev_back_done[db], c->s_back));
+		c->stats.graph_launches += 3;
+	} else {
+		if(s.timed) CU(cudaEventRecord(s.tk[0], c->stream));
+		KL(vdl2_launch_k0(d_raw, n_pairs, k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->n_streams,
+				n_pairs * bpp, c->max_pairs, nullptr, c->stream));
+		CU(cudaEventRecord(c->ev_input_consumed, c->stream));
+		if(s.timed) CU(cudaEventRecord(s.tk[1], c->stream));
+		KL(vdl2_launch_k1(&p1, (c->cfg.flags & VDL2GPU_FLAG_K1_SCALAR) ? 1 : 0, c->k1_variant, c->stream));
+		if(s.timed) CU(cudaEventRecord(s.tk[2], c->stream));
+		CU(cudaEventRecord(c->ev_k1_done[db], c->stream));
+		/* ---- back stage: K2a, K2, K3 ---- */
+		CU(cudaStreamWaitEvent(c->s_back, c->ev_k1_done[db], 0));
+		if(s.timed) CU(cudaEventRecord(s.tk[3], c->s_back));
+		KL(vdl2_launch_k2a(&p2, c->s_back));
+		CU(cudaEventRecord(c->ev_k2a_done, c->s_back));
+		if(s.timed) CU(cudaEventRecord(s.tk[6], c->s_back));
+		KL(vdl2_launch_k2(&p2, c->s_back));
+		KL(vdl2_launch_copy_hist(&p2, c->s_back));
+		CU(cudaEventRecord(c->ev_back_done[db], c->s_back));
+		if(s.timed) CU(cudaEventRecord(s.tk[4], c->s_back));
+		KL(vdl2_launch_k3(&p3, K3_GRID, c->s_back));
+		if(s.timed) CU(cudaEventRecord(s.tk[5], c->s_back));
+	}
 	CU(cudaEventRecord(s.done, c->s_back));
 	c->chunk_seq++;
 	s.busy = true;
@@ -452,20 +601,25 @@ extern "C" int vdl2gpu_submit(vdl2gpu_ctx *c, const void *iq, uint32_t len) {
 	if(!c || (!iq && len)) return VDL2GPU_EINVAL;
 	if(len == 0) return VDL2GPU_OK;                                   /* src/demod.c:341,358 */
 	if(len > c->cfg.max_chunk_bytes) return VDL2GPU_ETOOBIG;
-	const uint32_t n_pairs = len / (c->cfg.sample_fmt == VDL2GPU_FMT_S16_LE ? 4u : 2u);
+	const uint32_t bpp = c->cfg.sample_fmt == VDL2GPU_FMT_S16_LE ? 4u : 2u;
+	const uint32_t n_pairs = len / bpp;
 	if(n_pairs == 0) return VDL2GPU_OK;
 	CU(cudaSetDevice(c->device));
 	chunk_slot *s;
 	int rc = acquire_slot(c, &s);
 	if(rc) return rc;
-	memcpy(s->h_raw, iq, len);
-	CU(cudaMemcpyAsync(s->d_raw, s->h_raw, len, cudaMemcpyHostToDevice, c->stream));
+	/* n_streams buffers of `len` bytes back to back; a ragged tail (len not a multiple of the sample size) is dropped
+	 * per stream, so the streams are repacked at n_pairs * bpp */
+	const size_t used = (size_t)n_pairs * bpp;
+	for(uint32_t st = 0; st < c->n_streams; st++)
+		memcpy(s->h_raw + st * used, static_cast<const uint8_t *>(iq) + (size_t)st * len, used);
+	CU(cudaMemcpyAsync(s->d_raw, s->h_raw, used * c->n_streams, cudaMemcpyHostToDevice, c->stream));
 	return run_chain(c, *s, s->d_raw, n_pairs);
 }
 
 extern "C" int vdl2gpu_submit_planar_s16(vdl2gpu_ctx *c, const int16_t *xi, const int16_t *xq, uint32_t n_pairs) {
 	if(!c || ((!xi || !xq) && n_pairs)) return VDL2GPU_EINVAL;
-	if(c->cfg.sample_fmt != VDL2GPU_FMT_S16_LE) return VDL2GPU_EINVAL;
+	if(c->cfg.sample_fmt != VDL2GPU_FMT_S16_LE || c->n_streams != 1) return VDL2GPU_EINVAL;
 	if(n_pairs == 0) return VDL2GPU_OK;
 	if((uint64_t)n_pairs * 4u > c->cfg.max_chunk_bytes) return VDL2GPU_ETOOBIG;
 	CU(cudaSetDevice(c->device));
@@ -512,7 +666,7 @@ extern "C" int vdl2gpu_serialize_raw_frame(const vdl2gpu_frame *f, const char *s
 	size_t nd = f->len ? pb_varint(dh, (2u << 3) | 2u) : 0;
 	if(f->len) nd += pb_varint(dh + nd, f->len);
 	const size_t total = 2 + nh + nmd + nd + f->len;
-	if(total > 65536 || total > cap) return VDL2GPU_ETOOBIG;         /* OUT_BINARY_FRAME_LEN_MAX, src/output-file.h:26 */
+	if(total > 65535 || total > cap) return VDL2GPU_ETOOBIG;         /* OUT_BINARY_FRAME_LEN_MAX, src/output-file.h:26 */
 	uint8_t *o = out;
 	*o++ = (uint8_t)(total >> 8); *o++ = (uint8_t)total;
 	memcpy(o, hdr, nh); o += nh; memcpy(o, md, nmd); o += nmd;
@@ -524,8 +678,10 @@ extern "C" int vdl2gpu_submit_device(vdl2gpu_ctx *c, const void *dev_iq, uint32_
 	if(!c || (!dev_iq && len)) return VDL2GPU_EINVAL;
 	if(len == 0) return VDL2GPU_OK;
 	if(len > c->cfg.max_chunk_bytes) return VDL2GPU_ETOOBIG;
-	const uint32_t n_pairs = len / (c->cfg.sample_fmt == VDL2GPU_FMT_S16_LE ? 4u : 2u);
+	const uint32_t bpp = c->cfg.sample_fmt == VDL2GPU_FMT_S16_LE ? 4u : 2u;
+	const uint32_t n_pairs = len / bpp;
 	if(n_pairs == 0) return VDL2GPU_OK;
+	if(c->n_streams > 1 && len % bpp != 0) return VDL2GPU_EINVAL;     /* streams are `len` bytes apart in dev_iq */
 	CU(cudaSetDevice(c->device));
 	chunk_slot *s;
 	int rc = acquire_slot(c, &s);
@@ -665,30 +821,43 @@ extern "C" int vdl2gpu_enable_timing(vdl2gpu_ctx *c, int on) {
 	return VDL2GPU_OK;
 }
 
-extern "C" int vdl2gpu_get_kernel_ms(vdl2gpu_ctx *c, double ms[4], uint64_t launches[4]) {
+extern "C" int vdl2gpu_get_kernel_ms(vdl2gpu_ctx *c, double ms[5], uint64_t launches[5]) {
 	if(!c || !ms) return VDL2GPU_EINVAL;
-	for(int k = 0; k < 4; k++) { ms[k] = c->k_ms[k]; if(launches) launches[k] = c->k_launches[k]; }
+	for(int k = 0; k < 5; k++) { ms[k] = c->k_ms[k]; if(launches) launches[k] = c->k_launches[k]; }
 	return VDL2GPU_OK;
 }
 
 /* ------------------------------------------------------------------------------------------------
- * raw launch stubs (device pointers in, device pointers out)
+ * raw launch stubs (device pointers in, device pointers out; no allocation, no synchronisation)
  * ---------------------------------------------------------------------------------------------- */
-static vdl2_tables *g_stub_tables = nullptr;       /* GF tables for the stand-alone RS stub, per process */
+/* GF tables for the stand-alone RS stub, one copy per device, made on first use on that device */
+static vdl2_tables *g_stub_tables[64] = { nullptr };
+static std::mutex g_stub_lock;
+
+static int stub_tables(vdl2_tables **out) {
+	int dev = 0;
+	CU(cudaGetDevice(&dev));
+	if(dev < 0 || dev >= 64) return VDL2GPU_EINVAL;
+	std::lock_guard<std::mutex> lk(g_stub_lock);
+	if(!g_stub_tables[dev]) {
+		host_tables *h = new host_tables();
+		memset(h, 0, sizeof(*h));
+		make_gf(h->t);
+		vdl2_tables *d = nullptr;
+		cudaError_t e = cudaMalloc(&d, sizeof(vdl2_tables));
+		if(e == cudaSuccess) e = cudaMemcpy(d, &h->t, sizeof(vdl2_tables), cudaMemcpyHostToDevice);
+		delete h;
+		if(e != cudaSuccess) { cudaFree(d); return fail_cuda(e, "RS stub tables", __LINE__); }
+		g_stub_tables[dev] = d;
+	}
+	*out = g_stub_tables[dev];
+	return VDL2GPU_OK;
+}
 
 extern "C" int vdl2gpu_launch_convert(const void *raw, uint32_t n_pairs, uint32_t sample_fmt, const float *levels256,
-		float *samples_out, void *stream) {
-	/* stand-alone form writes float2 {re, im}: convert into a temporary float4 layout is not needed by callers,
-	 * so this stub runs the K0 kernel into a scratch buffer and compacts */
-	if(!raw || !samples_out || sample_fmt > 1 || (sample_fmt == 0 && !levels256)) return VDL2GPU_EINVAL;
-	float4 *tmp = nullptr;
-	CU(cudaMalloc(&tmp, (size_t)std::max(n_pairs, 1u) * sizeof(float4)));
-	int rc = vdl2_launch_k0(raw, n_pairs, sample_fmt, levels256, reinterpret_cast<float *>(tmp), (cudaStream_t)stream);
-	if(rc == 0 && n_pairs)
-		rc = (int)cudaMemcpy2DAsync(samples_out, sizeof(float2), tmp, sizeof(float4), sizeof(float2), n_pairs, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-	cudaStreamSynchronize((cudaStream_t)stream);
-	cudaFree(tmp);
-	if(rc) return fail_cuda((cudaError_t)rc, "vdl2gpu_launch_convert", __LINE__);
+		float *samples4_out, void *stream) {
+	if(!raw || !samples4_out || sample_fmt > 1 || (sample_fmt == 0 && !levels256)) return VDL2GPU_EINVAL;
+	KL(vdl2_launch_k0(raw, n_pairs, sample_fmt, levels256, samples4_out, 1, 0, 0, nullptr, (cudaStream_t)stream));
 	return VDL2GPU_OK;
 }
 
@@ -701,14 +870,224 @@ extern "C" int vdl2gpu_launch_fcs_crc16(const uint8_t *frames, const uint32_t *o
 
 extern "C" int vdl2gpu_launch_rs_verify(uint8_t *blocks, const int32_t *fec_octets, uint32_t n_blocks, int32_t *ret_out, void *stream) {
 	if(n_blocks && (!blocks || !fec_octets || !ret_out)) return VDL2GPU_EINVAL;
-	if(!g_stub_tables) {
-		host_tables *h = new host_tables();
-		memset(h, 0, sizeof(*h));
-		make_gf(h->t);
-		CU(cudaMalloc(&g_stub_tables, sizeof(vdl2_tables)));
-		CU(cudaMemcpy(g_stub_tables, &h->t, sizeof(vdl2_tables), cudaMemcpyHostToDevice));
-		delete h;
-	}
-	KL(vdl2_launch_rs(blocks, fec_octets, n_blocks, ret_out, g_stub_tables, (cudaStream_t)stream));
+	vdl2_tables *t = nullptr;
+	int rc = stub_tables(&t);            /* first call on a device allocates; later calls only launch */
+	if(rc) return rc;
+	KL(vdl2_launch_rs(blocks, fec_octets, n_blocks, ret_out, t, (cudaStream_t)stream));
 	return VDL2GPU_OK;
+}
+
+/* ---- stage stubs: K1, K2 (+K2a), K3 one at a time, on device memory the caller owns ---- */
+struct vdl2gpu_stage {
+	vdl2gpu_config cfg;
+	std::vector<uint32_t> freqs;
+	host_tables tab;
+	uint32_t n_ch = 0, n_chp = 0, max_dec = 0, n_slots = 0, event_cap = 0;
+	uint32_t decim_cnt = 0;
+	uint64_t total_dec = 0;
+	uint32_t events_read = 0;
+	int k1_variant = 2, k2_variant = 2, k2a_mode = 1;
+	vdl2_tables *d_tab = nullptr;
+	uint32_t *d_k1 = nullptr, *d_k2 = nullptr, *d_counters = nullptr, *d_ready = nullptr;
+	float *d_ring = nullptr, *d_phase = nullptr, *d_mag = nullptr, *d_hist_tmp = nullptr;
+	vdl2_burst_slot *d_pool = nullptr;
+	int32_t *d_free = nullptr;
+	vdl2_queue_ctl *d_ctl = nullptr;
+	void *d_events = nullptr;
+};
+
+static size_t al256(size_t x) { return (x + 255u) & ~(size_t)255u; }
+
+struct stage_layout {
+	size_t tab, k1, k2, counters, ring, phase, mag, hist, pool, free_list, ready, ctl, events, total;
+};
+
+static stage_layout stage_layout_of(uint32_t n_ch, uint32_t max_dec, uint32_t event_cap) {
+	const size_t n_chp = (n_ch + 31u) & ~31u, n_slots = std::max(256u, 3u * n_ch);
+	stage_layout L;
+	size_t o = 0;
+	L.tab = o; o += al256(sizeof(vdl2_tables));
+	L.k1 = o; o += al256((size_t)K1_NFIELDS * n_chp * 4);
+	L.k2 = o; o += al256((size_t)K2_NFIELDS * n_chp * 4);
+	L.counters = o; o += al256((size_t)VDL2_NUM_COUNTERS * n_chp * 4);
+	L.ring = o; o += al256((size_t)VDL2_SYNC_BUFLEN * n_chp * 4);
+	L.phase = o; o += al256((size_t)(max_dec + VDL2_SYNC_BUFLEN) * n_chp * 4);
+	L.mag = o; o += al256((size_t)max_dec * n_chp * 4);
+	L.hist = o; o += al256((size_t)VDL2_SYNC_BUFLEN * n_chp * 4);
+	L.pool = o; o += al256(n_slots * sizeof(vdl2_burst_slot));
+	L.free_list = o; o += al256(n_slots * 4);
+	L.ready = o; o += al256(n_slots * 4);
+	L.ctl = o; o += al256(sizeof(vdl2_queue_ctl));
+	L.events = o; o += al256((size_t)event_cap * sizeof(vdl2gpu_event));
+	L.total = o;
+	return L;
+}
+
+static uint32_t stage_event_cap(uint32_t flags) { return (flags & VDL2GPU_FLAG_TRACE) ? (1u << 18) : 1u; }
+
+extern "C" size_t vdl2gpu_stage_device_bytes(uint32_t n_channels, uint32_t max_dec, uint32_t flags) {
+	return stage_layout_of(n_channels, max_dec, stage_event_cap(flags)).total;
+}
+
+extern "C" uint32_t vdl2gpu_stage_row_stride(uint32_t n_channels) { return (n_channels + 31u) & ~31u; }
+
+/* initial per-channel state: vdl2_channel_init + demod_reset (src/demod.c:205-220,379-392), process_samples locals
+ * (src/demod.c:289-298); shared by the batch context and the stage stubs */
+static void initial_state(const vdl2gpu_config &cfg, const uint32_t *freqs, uint32_t n_ch, uint32_t n_chp,
+		std::vector<uint32_t> &k1, std::vector<uint32_t> &k2) {
+	k1.assign((size_t)K1_NFIELDS * n_chp, 0u); k2.assign((size_t)K2_NFIELDS * n_chp, 0u);
+	auto fbits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+	for(uint32_t ch = 0; ch < n_ch; ch++) {
+		/* a channel on the centre frequency skips the mixer in the reference (src/demod.c:312); with a zero
+		 * phase step the table gives cos = 1, sin = 0 and the products are exact, so no branch is needed */
+		k1[(size_t)K1_DPHI * n_chp + ch] = (cfg.centerfreq != freqs[ch]) ? dphi_for(cfg.centerfreq, freqs[ch], cfg.sample_rate) : 0u;
+		k2[(size_t)K2_MAG_NF * n_chp + ch] = fbits(2.0f);
+		k2[(size_t)K2_PHERR1 * n_chp + ch] = fbits(1000.f);
+		k2[(size_t)K2_PHERR2 * n_chp + ch] = fbits(1000.f);
+		k2[(size_t)K2_STATE * n_chp + ch] = VDL2_DEC_HEADER << VDL2_DEC_SHIFT;
+		k2[(size_t)K2_NEED_BITS * n_chp + ch] = VDL2_HEADER_LEN;
+		k2[(size_t)K2_SLOT * n_chp + ch] = (uint32_t)-1;
+		k2[(size_t)K2_FREQ * n_chp + ch] = freqs[ch];
+		k2[(size_t)K2_PURE_RUN * n_chp + ch] = 0x40000000u;      /* VDL2_PURE_SATURATED: ring of zeros == history of zeros */
+	}
+}
+
+extern "C" int vdl2gpu_stage_create(const vdl2gpu_config *cfg, uint32_t max_dec, void *device_mem, size_t device_bytes, vdl2gpu_stage **out) {
+	if(!cfg || !out || !device_mem || !cfg->freqs || cfg->n_channels == 0 || cfg->oversample == 0 || max_dec == 0
+			|| cfg->sample_rate != (uint32_t)VDL2_SYMBOL_RATE * VDL2_SPS * cfg->oversample) return VDL2GPU_EINVAL;
+	const uint32_t ecap = stage_event_cap(cfg->flags);
+	const stage_layout L = stage_layout_of(cfg->n_channels, max_dec, ecap);
+	if(device_bytes < L.total || ((uintptr_t)device_mem & 255u)) return VDL2GPU_EINVAL;
+	int dev = 0;
+	CU(cudaGetDevice(&dev));
+	KL(vdl2_kernels_init_device(dev));
+	vdl2gpu_stage *st = new vdl2gpu_stage();
+	st->cfg = *cfg;
+	st->freqs.assign(cfg->freqs, cfg->freqs + cfg->n_channels);
+	st->cfg.freqs = st->freqs.data();
+	st->n_ch = cfg->n_channels; st->n_chp = (st->n_ch + 31u) & ~31u; st->max_dec = max_dec;
+	st->n_slots = std::max(256u, 3u * st->n_ch); st->event_cap = ecap;
+	const char *e;
+	if((e = getenv("VDL2GPU_K1_VARIANT"))) st->k1_variant = atoi(e);
+	if((e = getenv("VDL2GPU_K2_VARIANT"))) st->k2_variant = atoi(e);
+	if((e = getenv("VDL2GPU_K2A"))) st->k2a_mode = atoi(e);
+	make_tables(st->tab, cfg->sample_rate);
+	uint8_t *b = static_cast<uint8_t *>(device_mem);
+	st->d_tab = reinterpret_cast<vdl2_tables *>(b + L.tab); st->d_k1 = reinterpret_cast<uint32_t *>(b + L.k1);
+	st->d_k2 = reinterpret_cast<uint32_t *>(b + L.k2); st->d_counters = reinterpret_cast<uint32_t *>(b + L.counters);
+	st->d_ring = reinterpret_cast<float *>(b + L.ring); st->d_phase = reinterpret_cast<float *>(b + L.phase);
+	st->d_mag = reinterpret_cast<float *>(b + L.mag); st->d_hist_tmp = reinterpret_cast<float *>(b + L.hist);
+	st->d_pool = reinterpret_cast<vdl2_burst_slot *>(b + L.pool); st->d_free = reinterpret_cast<int32_t *>(b + L.free_list);
+	st->d_ready = reinterpret_cast<uint32_t *>(b + L.ready); st->d_ctl = reinterpret_cast<vdl2_queue_ctl *>(b + L.ctl);
+	st->d_events = b + L.events;
+	std::vector<uint32_t> k1, k2;
+	initial_state(st->cfg, st->freqs.data(), st->n_ch, st->n_chp, k1, k2);
+	std::vector<int32_t> fl(st->n_slots);
+	for(uint32_t i = 0; i < st->n_slots; i++) fl[i] = (int32_t)i;
+	vdl2_queue_ctl ctl;
+	memset(&ctl, 0, sizeof(ctl));
+	ctl.free_top = (int32_t)st->n_slots;
+	cudaError_t ce = cudaMemset(device_mem, 0, L.total);
+	if(ce == cudaSuccess) ce = cudaMemcpy(st->d_tab, &st->tab.t, sizeof(vdl2_tables), cudaMemcpyHostToDevice);
+	if(ce == cudaSuccess) ce = cudaMemcpy(st->d_k1, k1.data(), k1.size() * 4, cudaMemcpyHostToDevice);
+	if(ce == cudaSuccess) ce = cudaMemcpy(st->d_k2, k2.data(), k2.size() * 4, cudaMemcpyHostToDevice);
+	if(ce == cudaSuccess) ce = cudaMemcpy(st->d_free, fl.data(), fl.size() * 4, cudaMemcpyHostToDevice);
+	if(ce == cudaSuccess) ce = cudaMemcpy(st->d_ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice);
+	if(ce != cudaSuccess) { delete st; return fail_cuda(ce, "vdl2gpu_stage_create", __LINE__); }
+	*out = st;
+	return VDL2GPU_OK;
+}
+
+extern "C" int vdl2gpu_stage_destroy(vdl2gpu_stage *st) { delete st; return VDL2GPU_OK; }
+
+extern "C" int vdl2gpu_stage_levels(vdl2gpu_stage *st, const float **levels256_dev) {
+	if(!st || !levels256_dev) return VDL2GPU_EINVAL;
+	*levels256_dev = st->d_tab->levels;
+	return VDL2GPU_OK;
+}
+
+/* K1 == the per-sample loop of process_samples (src/demod.c:288-337) for every channel of the stage */
+extern "C" int vdl2gpu_launch_mix_iir_decimate(vdl2gpu_stage *st, const float *samples4, uint32_t n_pairs, float *dec_out,
+		uint32_t *n_dec_out, void *stream) {
+	if(!st || (n_pairs && (!samples4 || !dec_out))) return VDL2GPU_EINVAL;
+	const uint32_t os = st->cfg.oversample;
+	const uint32_t n_dec = (st->decim_cnt + n_pairs) / os;
+	if(n_dec > st->max_dec) return VDL2GPU_ETOOBIG;
+	vdl2_k1_params p1;
+	memset(&p1, 0, sizeof(p1));
+	p1.samples = reinterpret_cast<const float4 *>(samples4); p1.n_pairs = n_pairs; p1.oversample = os; p1.cnt0 = st->decim_cnt;
+	p1.n_ch = st->n_ch; p1.n_chp = st->n_chp; p1.dec = reinterpret_cast<float2 *>(dec_out); p1.state = st->d_k1;
+	p1.lut = reinterpret_cast<const float4 *>(st->d_tab->lut);
+	p1.a0 = st->tab.t.A[0]; p1.a1 = st->tab.t.A[1]; p1.a2 = st->tab.t.A[2]; p1.b1 = st->tab.t.B[1]; p1.b2 = st->tab.t.B[2];
+	p1.one = 1.0f; p1.neg_one = -1.0f; p1.two = 2.0f;
+	KL(vdl2_launch_k1(&p1, (st->cfg.flags & VDL2GPU_FLAG_K1_SCALAR) ? 1 : 0, st->k1_variant, (cudaStream_t)stream));
+	st->decim_cnt = (st->decim_cnt + n_pairs) % os;
+	if(n_dec_out) *n_dec_out = n_dec;
+	return VDL2GPU_OK;
+}
+
+/* K2a + K2 == demod() (src/demod.c:222-286) + the header part of decode_vdl2_burst (src/decode.c:198-258) over n_dec
+ * decimated samples of every channel; completed bursts queue up for vdl2gpu_launch_burst_fec */
+extern "C" int vdl2gpu_launch_sync_slice(vdl2gpu_stage *st, const float *dec, uint32_t n_dec, void *stream) {
+	if(!st || (n_dec && !dec)) return VDL2GPU_EINVAL;
+	if(n_dec > st->max_dec) return VDL2GPU_ETOOBIG;
+	if(n_dec == 0) return VDL2GPU_OK;
+	vdl2_k2_params p2;
+	memset(&p2, 0, sizeof(p2));
+	p2.dec = reinterpret_cast<const float2 *>(dec); p2.phase = st->d_phase; p2.mag = st->d_mag; p2.hist_tmp = st->d_hist_tmp;
+	p2.n_dec = n_dec; p2.n_ch = st->n_ch; p2.n_chp = st->n_chp; p2.dec_base = st->total_dec;
+	p2.state = st->d_k2; p2.ring = st->d_ring; p2.tables = st->d_tab; p2.max_ppm = st->cfg.max_ppm; p2.s27 = st->tab.s27;
+	p2.pool = st->d_pool; p2.free_list = st->d_free; p2.ready = st->d_ready; p2.ctl = st->d_ctl;
+	p2.events = st->d_events; p2.event_cap = st->event_cap; p2.trace = (st->cfg.flags & VDL2GPU_FLAG_TRACE) ? 1u : 0u;
+	p2.variant = (uint32_t)st->k2_variant; p2.k2a_mode = (uint32_t)st->k2a_mode;
+	KL(vdl2_launch_k2a(&p2, (cudaStream_t)stream));
+	KL(vdl2_launch_k2(&p2, (cudaStream_t)stream));
+	KL(vdl2_launch_copy_hist(&p2, (cudaStream_t)stream));
+	st->total_dec += n_dec;
+	return VDL2GPU_OK;
+}
+
+/* K3 (+K4) == the data part of decode_vdl2_burst (src/decode.c:259-380) for every queued burst.  `region` receives a
+ * vdl2_out_header followed by the burst records (device memory or mapped pinned host memory, 16-byte aligned);
+ * vdl2gpu_parse_records turns a host copy of it into frames. */
+extern "C" int vdl2gpu_launch_burst_fec(vdl2gpu_stage *st, uint8_t *region, uint32_t region_bytes, void *stream) {
+	if(!st || !region || region_bytes < sizeof(vdl2_out_header) + 256u || ((uintptr_t)region & 15u)) return VDL2GPU_EINVAL;
+	vdl2_k3_params p3;
+	memset(&p3, 0, sizeof(p3));
+	p3.pool = st->d_pool; p3.free_list = st->d_free; p3.ready = st->d_ready; p3.ctl = st->d_ctl; p3.tables = st->d_tab;
+	p3.out = region; p3.out_cap = region_bytes - (uint32_t)sizeof(vdl2_out_header); p3.n_chp = st->n_chp; p3.counters = st->d_counters;
+	KL(vdl2_launch_k3(&p3, K3_GRID, (cudaStream_t)stream));
+	return VDL2GPU_OK;
+}
+
+extern "C" int vdl2gpu_stage_read_events(vdl2gpu_stage *st, vdl2gpu_event *out, uint32_t cap) {
+	if(!st || !out) return VDL2GPU_EINVAL;
+	if(!(st->cfg.flags & VDL2GPU_FLAG_TRACE)) return 0;
+	CU(cudaDeviceSynchronize());
+	vdl2_queue_ctl ctl;
+	CU(cudaMemcpy(&ctl, st->d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost));
+	uint32_t total = std::min(ctl.n_events, st->event_cap);
+	uint32_t n = total > st->events_read ? total - st->events_read : 0;
+	if(n > cap) n = cap;
+	if(n) CU(cudaMemcpy(out, (const vdl2gpu_event *)st->d_events + st->events_read, (size_t)n * sizeof(vdl2gpu_event), cudaMemcpyDeviceToHost));
+	st->events_read += n;
+	return (int)n;
+}
+
+extern "C" int vdl2gpu_parse_records(const uint8_t *region_host, uint32_t region_bytes, uint32_t decimated_rate,
+		vdl2gpu_frame_cb cb, void *user) {
+	if(!region_host || region_bytes < sizeof(vdl2_out_header)) return VDL2GPU_EINVAL;
+	std::vector<pending_frame> pending;
+	vdl2gpu_stats stats;
+	memset(&stats, 0, sizeof(stats));
+	struct timeval now;
+	gettimeofday(&now, NULL);
+	parse_region(region_host, region_bytes - (uint32_t)sizeof(vdl2_out_header), (double)decimated_rate, now, 0, 0, pending, stats);
+	const uint8_t *base = region_host + sizeof(vdl2_out_header);
+	for(auto &pf : pending) {
+		pf.f.data = base + pf.offset;
+		if(cb) cb(&pf.f, user);
+	}
+	if(stats.pool_overflows || stats.out_overflows) return VDL2GPU_EOVERFLOW;
+	return (int)pending.size();
 }

@@ -16,7 +16,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <mutex>
 #include "vdl2_core.cuh"
+#include "vdl2_fastmath.cuh"
 #include "vdl2_kernels.h"
 
 /* ------------------------------------------------------------------------------------------------
@@ -24,8 +26,12 @@
  * consumes (re,im) and (im,re) as two f32x2 operands, so the swap is paid once per sample here
  * instead of once per channel-sample there.
  * ---------------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(256) k0_convert(const uint8_t *__restrict__ raw, uint32_t n_pairs, uint32_t fmt,
-		const float *__restrict__ levels, float4 *__restrict__ out) {
+__global__ void __launch_bounds__(256) k0_convert(const uint8_t *__restrict__ raw0, uint32_t n_pairs_p, uint32_t fmt,
+		const float *__restrict__ levels, float4 *__restrict__ out0, uint32_t raw_stride, uint32_t out_stride,
+		const vdl2_chunk_args *__restrict__ ca) {
+	const uint32_t n_pairs = ca ? ca->n_pairs : n_pairs_p;
+	const uint8_t *raw = (ca ? static_cast<const uint8_t *>(ca->raw) : raw0) + (size_t)blockIdx.y * raw_stride;   /* stream blockIdx.y */
+	float4 *out = out0 + (size_t)blockIdx.y * out_stride;
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= n_pairs) return;
 	float re, im;
@@ -76,6 +82,12 @@ __device__ __forceinline__ void k1_store_state(const vdl2_k1_params &p, uint32_t
 	st[K1_PHI * s + ch] = phi & 0xFFFFFFu;
 }
 
+/* independent-streams mode: the block's 32 channels all belong to stream (first channel / ch_per_stream); a block
+ * never straddles two streams because ch_per_stream is a multiple of the block size (checked by vdl2gpu_create) */
+__device__ __forceinline__ const float4 *k1_stream_of(const vdl2_k1_params &p, uint32_t first_ch) {
+	return p.ch_per_stream ? p.samples + (size_t)(first_ch / p.ch_per_stream) * p.stream_stride : p.samples;
+}
+
 template<int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_scalar(vdl2_k1_params p) {
 	__shared__ float4 s_lut[257];
@@ -83,16 +95,18 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_scalar(vdl2_k1_para
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ch = blockIdx.x * BLOCK + tid;
 	const bool active = ch < p.n_ch;
+	const uint32_t n_pairs = p.ca ? p.ca->n_pairs : p.n_pairs, cnt0 = p.ca ? p.ca->cnt0 : p.cnt0;
+	const float4 *samples = k1_stream_of(p, blockIdx.x * BLOCK);
 	for(uint32_t i = tid; i < 257; i += BLOCK) s_lut[i] = p.lut[i];
 	float xr1 = 0, xr2 = 0, xi1 = 0, xi2 = 0, yr1 = 0, yr2 = 0, yi1 = 0, yi2 = 0;
 	uint32_t phi = 0, dphi = 0;
 	if(active) k1_load_state(p, ch, xr1, xr2, xi1, xi2, yr1, yr2, yi1, yi2, phi, dphi);
-	uint32_t cnt = p.cnt0, m = 0;
+	uint32_t cnt = cnt0, m = 0;
 	const float a0 = p.a0, a1 = p.a1, a2 = p.a2, b1 = p.b1, b2 = p.b2;
-	for(uint32_t base = 0; base < p.n_pairs; base += K1_TILE) {
-		const uint32_t n = min((uint32_t)K1_TILE, p.n_pairs - base);
+	for(uint32_t base = 0; base < n_pairs; base += K1_TILE) {
+		const uint32_t n = min((uint32_t)K1_TILE, n_pairs - base);
 		__syncthreads();
-		for(uint32_t i = tid; i < n; i += BLOCK) { float4 v = p.samples[base + i]; s_tile[i] = make_float2(v.x, v.y); }
+		for(uint32_t i = tid; i < n; i += BLOCK) { float4 v = samples[base + i]; s_tile[i] = make_float2(v.x, v.y); }
 		__syncthreads();
 		if(!active) continue;
 		for(uint32_t k = 0; k < n; k++) {
@@ -210,6 +224,8 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ch = blockIdx.x * BLOCK + tid;
 	const bool active = ch < p.n_ch;
+	const uint32_t n_pairs = p.ca ? p.ca->n_pairs : p.n_pairs, cnt0 = p.ca ? p.ca->cnt0 : p.cnt0;
+	const float4 *samples = k1_stream_of(p, blockIdx.x * BLOCK);
 	for(uint32_t i = tid; i < 257; i += BLOCK) s_lut[i] = p.lut[i];
 	if(tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
 	float xr1 = 0, xr2 = 0, xi1 = 0, xi2 = 0, yr1 = 0, yr2 = 0, yi1 = 0, yi2 = 0;
@@ -227,28 +243,28 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	u64 P1 = f2_mul(c.A0, x1), P2 = f2_mul(c.A0, x2);
 	__syncthreads();
 
-	uint32_t cnt = p.cnt0, m = 0, pos = 0;
+	uint32_t cnt = cnt0, m = 0, pos = 0;
 	/* head: samples up to the first decimation-group boundary, straight from global memory */
-	const uint32_t head = min(p.n_pairs, (OS - p.cnt0 % OS) % OS);
+	const uint32_t head = min(n_pairs, (OS - cnt0 % OS) % OS);
 	if(active) {
 		for(; pos < head; pos++) {
-			u64 y0 = k1_packed_step(p.samples[pos], s_lut, phi, dphi, x1, x2, y1, y2, c);
+			u64 y0 = k1_packed_step(samples[pos], s_lut, phi, dphi, x1, x2, y1, y2, c);
 			if(++cnt == OS) { cnt = 0; p.dec[(size_t)m * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0)); m++; }
 		}
 	}
 	/* same bookkeeping for every lane, active or not */
 	pos = head;
-	m = (p.cnt0 + head) / OS;
-	cnt = (p.cnt0 + head) % OS;
+	m = (cnt0 + head) / OS;
+	cnt = (cnt0 + head) % OS;
 	P1 = f2_mul(c.A0, x1); P2 = f2_mul(c.A0, x2);            /* after the head samples */
 	/* body: whole groups, staged through shared memory tile by tile */
-	const uint32_t n_groups = (p.n_pairs - pos) / OS;
+	const uint32_t n_groups = (n_pairs - pos) / OS;
 	const uint32_t n_tiles = (n_groups + TG - 1) / TG;
 	/* prologue: the first two tiles are requested at once; tile t lands in buffer t & 1, its mbarrier phase is (t >> 1) & 1 */
 	if(tid == 0) {
 		for(uint32_t t = 0; t < 2 && t < n_tiles; t++) {
 			const uint32_t ngt = min((uint32_t)TG, n_groups - t * TG);
-			tma_load_tile(s_tiles[t], p.samples + pos + (size_t)t * TG * OS, ngt * OS * (uint32_t)sizeof(float4), &s_bar[t]);
+			tma_load_tile(s_tiles[t], samples + pos + (size_t)t * TG * OS, ngt * OS * (uint32_t)sizeof(float4), &s_bar[t]);
 		}
 	}
 	for(uint32_t g0 = 0, tile = 0; g0 < n_groups; g0 += TG, tile++) {
@@ -312,13 +328,13 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 		__syncthreads();                                           /* every lane is done with this buffer */
 		if(tid == 0 && tile + 2 < n_tiles) {
 			const uint32_t ngn = min((uint32_t)TG, n_groups - (tile + 2) * TG);
-			tma_load_tile(s_tiles[tile & 1u], p.samples + pos + (size_t)TG * OS, ngn * OS * (uint32_t)sizeof(float4), &s_bar[tile & 1u]);
+			tma_load_tile(s_tiles[tile & 1u], samples + pos + (size_t)TG * OS, ngn * OS * (uint32_t)sizeof(float4), &s_bar[tile & 1u]);
 		}
 	}
 	/* tail: fewer than OS samples left */
 	if(active) {
-		for(; pos < p.n_pairs; pos++) {
-			u64 y0 = k1_packed_step(p.samples[pos], s_lut, phi, dphi, x1, x2, y1, y2, c);
+		for(; pos < n_pairs; pos++) {
+			u64 y0 = k1_packed_step(samples[pos], s_lut, phi, dphi, x1, x2, y1, y2, c);
 			if(++cnt == OS) { cnt = 0; p.dec[(size_t)m * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0)); m++; }
 		}
 		k1_store_state(p, ch, f2_lo(x1), f2_lo(x2), f2_hi(x1), f2_hi(x2), f2_lo(y1), f2_lo(y2), f2_hi(y1), f2_hi(y2), phi);
@@ -334,20 +350,47 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 
 /* K2a: phase and magnitude of every decimated sample of the chunk (src/demod.c:232,238,256), one thread per
  * (time, channel) element: the double-precision atan2/sqrt run at full occupancy here instead of inside the
- * sequential per-channel walk of K2. */
+ * sequential per-channel walk of K2.
+ * FAST: the phase comes from vdl2_phase_fast (vdl2_fastmath.cuh: 9 break points, one division, degree-5 polynomial,
+ * ~22 FP64 operations) whose float result is the correctly rounded fl32(atan2); only when it reports that the double
+ * lies within 2^-44 of a float rounding boundary, or for zero / non-finite / extreme inputs (about one sample in
+ * 3e5), the libdevice routine decides, as it does for every sample when FAST is off. */
+template<bool FAST>
 __global__ void __launch_bounds__(256) k2a_phase_mag(const float2 *__restrict__ dec, float *__restrict__ phase,
-		float *__restrict__ mag, uint32_t n_elems) {
+		float *__restrict__ mag, uint32_t n_elems_p, uint32_t n_chp, const vdl2_chunk_args *__restrict__ ca) {
+	__shared__ double s_atan[VDL2_ATAN_TABLE_DOUBLES];
+	if(FAST) {
+		const double tab[VDL2_ATAN_TABLE_DOUBLES] = VDL2_ATAN_TABLE_INIT;
+		if(threadIdx.x < VDL2_ATAN_TABLE_DOUBLES) s_atan[threadIdx.x] = tab[threadIdx.x];
+		__syncthreads();
+	}
+	const uint32_t n_elems = ca ? ca->n_dec * n_chp : n_elems_p;
 	uint32_t i = blockIdx.x * 256u + threadIdx.x;
 	if(i >= n_elems) return;
 	const float2 d = dec[i];
-	phase[i] = vdl2_phase_of(d.x, d.y);
+	float ph;
+	if(FAST) {
+		int slow;
+		ph = vdl2_phase_fast(d.x, d.y, s_atan, &slow);
+		if(slow) ph = vdl2_phase_of(d.x, d.y);
+	} else {
+		ph = vdl2_phase_of(d.x, d.y);
+	}
+	phase[i] = ph;
 	mag[i] = vdl2_mag_of(d.x, d.y);
 }
 
-/* carry the last 160 phase rows over to the front of the plane for the next chunk */
+/* carry the last 160 phase rows over to the front of the plane for the next chunk: rows [n_dec, n_dec+160) -> [0, 160) */
 __global__ void __launch_bounds__(256) k_copy_rows(const float *__restrict__ src, float *__restrict__ dst, uint32_t n) {
 	uint32_t i = blockIdx.x * 256u + threadIdx.x;
 	if(i < n) dst[i] = src[i];
+}
+/* the same with the row offset taken from the chunk arguments (n_dec >= 160: source and destination do not overlap) */
+__global__ void __launch_bounds__(256) k_copy_hist(float *__restrict__ phase, uint32_t n, uint32_t n_chp, uint32_t n_dec_p,
+		const vdl2_chunk_args *__restrict__ ca) {
+	const uint32_t n_dec = ca ? ca->n_dec : n_dec_p;
+	uint32_t i = blockIdx.x * 256u + threadIdx.x;
+	if(i < n) phase[i] = phase[(size_t)n_dec * n_chp + i];
 }
 
 /* 4-byte asynchronous global->shared copies (LDGSTS): completion is tracked per thread by commit/wait groups, not
@@ -406,6 +449,8 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	const float2 *dec = p.dec + ch;
 	const float *phs = p.phase + (size_t)VDL2_SYNC_BUFLEN * s + ch;      /* row 0 of phs = first sample of this chunk */
 	const float *mgs = p.mag + ch;
+	const uint32_t n_dec = p.ca ? p.ca->n_dec : p.n_dec;
+	const uint64_t dec_base = p.ca ? p.ca->dec_base : p.dec_base;
 	uint32_t m = 0;
 	if(BLOCKED) {
 		if(MODE == 3) {
@@ -414,7 +459,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 			float *stg = s_stage + tid;
 			int first_cur = 0;                                   /* attempt offset the buffer about to be consumed was staged for */
 			uint32_t b = 0;
-			if(m + VDL2_WALK_BLOCK <= p.n_dec) {
+			if(m + VDL2_WALK_BLOCK <= n_dec) {
 				const int f0 = vdl2_walk_first(v);
 #pragma unroll
 				for(int t = 0; t < VDL2_WALK_BLOCK; t++) k2_cp_async4(stg + t * BLOCK, phs + (size_t)t * s);
@@ -424,7 +469,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 				first_cur = f0;
 			}
 #pragma unroll 1
-			for(; m + VDL2_WALK_BLOCK <= p.n_dec; m += VDL2_WALK_BLOCK, b ^= 1u) {
+			for(; m + VDL2_WALK_BLOCK <= n_dec; m += VDL2_WALK_BLOCK, b ^= 1u) {
 				const size_t o = (size_t)m * s;
 				k2_cp_async_wait_all();
 				vdl2_walk_pref pf;
@@ -434,7 +479,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 #pragma unroll
 				for(int j = 0; j < 4; j++) pf.mg[j] = cur[(12 + j) * BLOCK];
 				pf.first = first_cur; pf.valid = 1;
-				if(m + 2 * VDL2_WALK_BLOCK <= p.n_dec) {             /* next block's inputs into the other buffer */
+				if(m + 2 * VDL2_WALK_BLOCK <= n_dec) {             /* next block's inputs into the other buffer */
 					const int fn = vdl2_walk_first(v);                /* prediction: the attempt offset repeats every block */
 					float *nxt = stg + (b ^ 1u) * 16 * BLOCK;
 					const float *ph_n = phs + o + (size_t)VDL2_WALK_BLOCK * s;
@@ -446,7 +491,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 					first_cur = fn;
 				}
 				k2_cp_async_commit();
-				vdl2_walk_block_ring(v, ring, BLOCK, env, ch, p.dec_base + m, dec + o, phs + o, mgs + o, s, pf, false);
+				vdl2_walk_block_ring(v, ring, BLOCK, env, ch, dec_base + m, dec + o, phs + o, mgs + o, s, pf, false);
 			}
 			k2_cp_async_wait_all();
 		} else if(MODE == 2) {
@@ -457,24 +502,24 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 #pragma unroll
 			for(int j = 0; j < 4; j++) pf.mg[j] = 0.f;
 #pragma unroll 1
-			for(; m + VDL2_WALK_BLOCK <= p.n_dec; m += VDL2_WALK_BLOCK) {
+			for(; m + VDL2_WALK_BLOCK <= n_dec; m += VDL2_WALK_BLOCK) {
 				const size_t o = (size_t)m * s;
-				vdl2_walk_block_ring(v, ring, BLOCK, env, ch, p.dec_base + m, dec + o, phs + o, mgs + o, s, pf,
-						m + 2 * VDL2_WALK_BLOCK <= p.n_dec);
+				vdl2_walk_block_ring(v, ring, BLOCK, env, ch, dec_base + m, dec + o, phs + o, mgs + o, s, pf,
+						m + 2 * VDL2_WALK_BLOCK <= n_dec);
 			}
 		} else {
 #pragma unroll 1
-			for(; m + VDL2_WALK_BLOCK <= p.n_dec; m += VDL2_WALK_BLOCK) {
+			for(; m + VDL2_WALK_BLOCK <= n_dec; m += VDL2_WALK_BLOCK) {
 				const size_t o = (size_t)m * s;
-				vdl2_walk_block<MODE == 1>(v, ring, BLOCK, env, ch, p.dec_base + m, dec + o, phs + o, mgs + o, s);
+				vdl2_walk_block<MODE == 1>(v, ring, BLOCK, env, ch, dec_base + m, dec + o, phs + o, mgs + o, s);
 			}
 		}
 	}
 #pragma unroll 1
-	for(; m < p.n_dec; m++) {
+	for(; m < n_dec; m++) {
 		const size_t o = (size_t)m * s;
 		const float2 d = __ldg(&dec[o]);
-		vdl2_demod_step_pm(v, ring, BLOCK, env, ch, p.dec_base + m, d.x, d.y, __ldg(&phs[o]), __ldg(&mgs[o]), false, 0.f, 0.f);
+		vdl2_demod_step_pm(v, ring, BLOCK, env, ch, dec_base + m, d.x, d.y, __ldg(&phs[o]), __ldg(&mgs[o]), false, 0.f, 0.f);
 	}
 
 #pragma unroll 4
@@ -642,46 +687,63 @@ __global__ void k_rs_verify(uint8_t *blocks, const int32_t *fec_octets, uint32_t
 /* ------------------------------------------------------------------------------------------------
  * launch stubs
  * ---------------------------------------------------------------------------------------------- */
-/* One shared-memory carve-out for every kernel of the chain, so that an SM never has to drain to re-partition
- * its L1/shared memory when kernels of two chunks are resident together (the default two-stream pipeline, see vdl2_host.cu). */
-template<typename K> static void vdl2_set_carveout(K kernel) {
-	static const char *ev = getenv("VDL2GPU_CARVEOUT");
-	const int pct = ev ? atoi(ev) : 100;          /* default: maximum shared memory, the same for every kernel */
-	if(pct >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-}
-
 #define K1_BLOCK 32
 #define K2_BLOCK 32
 
-extern "C" int vdl2_launch_k0(const void *raw, uint32_t n_pairs, uint32_t fmt, const float *levels, float *out4, cudaStream_t st) {
-	if(n_pairs == 0) return 0;
-	k0_convert<<<(n_pairs + 255) / 256, 256, 0, st>>>(static_cast<const uint8_t *>(raw), n_pairs, fmt, levels, reinterpret_cast<float4 *>(out4));
+/* One shared-memory carve-out for every kernel of the chain, so that an SM never has to drain to re-partition
+ * its L1/shared memory when kernels of two chunks are resident together (the default two-stream pipeline, see
+ * vdl2_host.cu).  Function attributes are per device: vdl2gpu_create calls this after cudaSetDevice, once per device. */
+template<typename K> static void vdl2_set_carveout(K kernel, int pct) {
+	if(pct >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
+static std::once_flag g_dev_once[64];
+
+extern "C" int vdl2_kernels_init_device(int device) {
+	if(device < 0 || device >= 64) return 0;
+	std::call_once(g_dev_once[device], [] {
+		const char *ev = getenv("VDL2GPU_CARVEOUT");
+		const int pct = ev ? atoi(ev) : 100;      /* default: maximum shared memory, the same for every kernel */
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, true>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, false>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK, 0, false>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK, 10, true>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK, 10, false>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK, 0, false>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<13, K1_BLOCK, 10, true>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<13, K1_BLOCK, 10, false>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_scalar<K1_BLOCK>, pct);
+		vdl2_set_carveout(k0_convert, pct);
+		vdl2_set_carveout(k2a_phase_mag<true>, pct);
+		vdl2_set_carveout(k2a_phase_mag<false>, pct);
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 3>, pct);
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 2>, pct);
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 1>, pct);
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 0>, pct);
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, false, 0>, pct);
+		vdl2_set_carveout(k_copy_rows, pct);
+		vdl2_set_carveout(k_copy_hist, pct);
+		vdl2_set_carveout(k3_burst_fec, pct);
+		vdl2_set_carveout(k_chunk_finish, pct);
+	});
 	return (int)cudaGetLastError();
 }
 
-extern "C" int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, cudaStream_t st) {
+extern "C" int vdl2_launch_k0(const void *raw, uint32_t n_pairs, uint32_t fmt, const float *levels, float *out4, uint32_t n_streams,
+		uint32_t raw_stride, uint32_t out_stride, const vdl2_chunk_args *ca, cudaStream_t st) {
+	if(n_pairs == 0 || n_streams == 0) return 0;
+	k0_convert<<<dim3((n_pairs + 255) / 256, n_streams), 256, 0, st>>>(static_cast<const uint8_t *>(raw), n_pairs, fmt, levels,
+			reinterpret_cast<float4 *>(out4), raw_stride, out_stride, ca);
+	return (int)cudaGetLastError();
+}
+
+/* variant: 0 un-pipelined packed kernel, 4 no symmetric-tap specialisation, anything else the default */
+extern "C" int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, int variant, cudaStream_t st) {
 	if(p->n_pairs == 0 || p->n_ch == 0) return 0;
 	const uint32_t blocks = (p->n_ch + K1_BLOCK - 1) / K1_BLOCK;
-	static int variant = -1;
-	if(variant < 0) {
-		const char *e = getenv("VDL2GPU_K1_VARIANT"); variant = e ? atoi(e) : 2;
-		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, true>);
-		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, false>);
-		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK, 0, false>);
-		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK, 10, true>);
-		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK, 10, false>);
-		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK, 0, false>);
-		vdl2_set_carveout(k1_mix_iir_decimate_packed<13, K1_BLOCK, 10, true>);
-		vdl2_set_carveout(k1_mix_iir_decimate_packed<13, K1_BLOCK, 10, false>);
-		vdl2_set_carveout(k1_mix_iir_decimate_scalar<K1_BLOCK>);
-		vdl2_set_carveout(k0_convert);
-	}
 	const bool sym = (p->a1 == 2.0f * p->a0) && (p->a2 == p->a0) && variant != 4;
 	if(!force_scalar && p->oversample == 20) {
 		if(variant == 0) k1_mix_iir_decimate_packed<20, K1_BLOCK, 0, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
-		else if(sym && variant == 5) k1_mix_iir_decimate_packed<20, K1_BLOCK, 6, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
-		else if(sym && variant == 6) k1_mix_iir_decimate_packed<20, K1_BLOCK, 14, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
-		else if(sym && variant == 7) k1_mix_iir_decimate_packed<20, K1_BLOCK, 20, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
 		else if(sym) k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
 		else k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
 	} else if(!force_scalar && p->oversample == 10) {
@@ -699,38 +761,31 @@ extern "C" int vdl2_launch_k2a(const vdl2_k2_params *p, cudaStream_t st) {
 	if(p->n_dec == 0 || p->n_ch == 0) return 0;
 	const uint32_t n_elems = p->n_dec * p->n_chp;
 	const uint32_t hist = VDL2_SYNC_BUFLEN * p->n_chp;
-	static bool once = false;
-	if(!once) { once = true; vdl2_set_carveout(k2a_phase_mag); }
-	k2a_phase_mag<<<(n_elems + 255u) / 256u, 256, 0, st>>>(p->dec, p->phase + hist, p->mag, n_elems);
+	if(p->k2a_mode) k2a_phase_mag<true><<<(n_elems + 255u) / 256u, 256, 0, st>>>(p->dec, p->phase + hist, p->mag, n_elems, p->n_chp, p->ca);
+	else k2a_phase_mag<false><<<(n_elems + 255u) / 256u, 256, 0, st>>>(p->dec, p->phase + hist, p->mag, n_elems, p->n_chp, p->ca);
 	return (int)cudaGetLastError();
 }
 
+/* variant: 0 per-sample walk; 1 blocked, phase plane, TwoSum unwrap; 3 blocked, phase ring, block inputs one block
+ * ahead in registers; 4 the same with cp.async staging; anything else (2) the default: blocked, phase plane, table unwrap */
 extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
 	if(p->n_dec == 0 || p->n_ch == 0) return 0;
 	const uint32_t blocks = (p->n_ch + K2_BLOCK - 1) / K2_BLOCK;
+	const uint32_t variant = p->variant;
+	if(variant == 0) k2_sync_slice<K2_BLOCK, false, 0><<<blocks, K2_BLOCK, 0, st>>>(*p);
+	else if(variant == 1) k2_sync_slice<K2_BLOCK, true, 0><<<blocks, K2_BLOCK, 0, st>>>(*p);
+	else if(variant == 3) k2_sync_slice<K2_BLOCK, true, 2><<<blocks, K2_BLOCK, 0, st>>>(*p);
+	else if(variant == 4) k2_sync_slice<K2_BLOCK, true, 3><<<blocks, K2_BLOCK, 0, st>>>(*p);
+	else k2_sync_slice<K2_BLOCK, true, 1><<<blocks, K2_BLOCK, 0, st>>>(*p);
+	return (int)cudaGetLastError();
+}
+
+/* history for the next chunk: phase rows [n_dec, n_dec+160) -> [0, 160) */
+extern "C" int vdl2_launch_copy_hist(const vdl2_k2_params *p, cudaStream_t st) {
+	if(p->n_dec == 0 || p->n_ch == 0) return 0;
 	const uint32_t hist = VDL2_SYNC_BUFLEN * p->n_chp;
-	static int variant = -1;
-	if(variant < 0) {
-		const char *ev = getenv("VDL2GPU_K2_VARIANT"); variant = ev ? atoi(ev) : 2;
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 3>);
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 2>);
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 1>);
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 0>);
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, false, 0>);
-		vdl2_set_carveout(k_copy_rows);
-		vdl2_set_carveout(k3_burst_fec);
-		vdl2_set_carveout(k_chunk_finish);
-	}
-	if(variant == 0) k2_sync_slice<K2_BLOCK, false, 0><<<blocks, K2_BLOCK, 0, st>>>(*p);              /* per-sample walk */
-	else if(variant == 1) k2_sync_slice<K2_BLOCK, true, 0><<<blocks, K2_BLOCK, 0, st>>>(*p);         /* blocked, phase plane, TwoSum unwrap */
-	else if(variant == 3) k2_sync_slice<K2_BLOCK, true, 2><<<blocks, K2_BLOCK, 0, st>>>(*p);         /* blocked, phase ring, inputs one block ahead (registers) */
-	else if(variant == 4) k2_sync_slice<K2_BLOCK, true, 3><<<blocks, K2_BLOCK, 0, st>>>(*p);         /* blocked, phase ring, inputs one block ahead (cp.async staging) */
-	else k2_sync_slice<K2_BLOCK, true, 1><<<blocks, K2_BLOCK, 0, st>>>(*p);                          /* default (2, or any unknown value): blocked, phase plane, table unwrap */
-	int e = (int)cudaGetLastError();
-	if(e) return e;
-	/* history for the next chunk: rows [n_dec, n_dec+160) -> [0, 160) */
 	if(p->n_dec >= VDL2_SYNC_BUFLEN) {
-		k_copy_rows<<<(hist + 255u) / 256u, 256, 0, st>>>(p->phase + (size_t)p->n_dec * p->n_chp, p->phase, hist);
+		k_copy_hist<<<(hist + 255u) / 256u, 256, 0, st>>>(p->phase, hist, p->n_chp, p->n_dec, p->ca);
 	} else {
 		k_copy_rows<<<(hist + 255u) / 256u, 256, 0, st>>>(p->phase + (size_t)p->n_dec * p->n_chp, p->hist_tmp, hist);
 		k_copy_rows<<<(hist + 255u) / 256u, 256, 0, st>>>(p->hist_tmp, p->phase, hist);

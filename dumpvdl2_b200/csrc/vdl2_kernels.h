@@ -5,8 +5,20 @@
 #include <cuda_runtime.h>
 #include "vdl2_types.h"
 
+/* Per-chunk values that change from one chunk to the next.  The host writes one of these into pinned memory and the
+ * first node of the chunk's CUDA graph copies it to the device, so the captured kernel nodes never need new
+ * parameters: kernels given a non-NULL `ca` take these fields from it instead of from their parameter block. */
 typedef struct {
-	const float4 *samples;       /* K0 output: {re, im, im, re} per complex sample */
+	const void *raw;             /* K0 input (device pointer) */
+	uint64_t dec_base;           /* absolute index of the chunk's first decimated sample */
+	uint32_t n_pairs;            /* complex samples per stream in this chunk */
+	uint32_t cnt0;               /* decimation counter on entry */
+	uint32_t n_dec;              /* decimated samples this chunk produces */
+	uint32_t pad;
+} vdl2_chunk_args;
+
+typedef struct {
+	const float4 *samples;       /* K0 output: {re, im, im, re} per complex sample; stream s at samples + s * stream_stride */
 	uint32_t n_pairs;
 	uint32_t oversample;
 	uint32_t cnt0;               /* decimation counter on entry (src/demod.c:289,322), same for all channels */
@@ -16,6 +28,9 @@ typedef struct {
 	const float4 *lut;           /* 257 x {cos, sin, dcos*2^-16, dsin*2^-16} */
 	float a0, a1, a2, b1, b2;
 	float one, neg_one, two;     /* run-time 1.0f / -1.0f / 2.0f (see k1_mix_iir_decimate_packed) */
+	uint32_t ch_per_stream;      /* independent-streams mode: channels [s*C, (s+1)*C) read stream s; 0 = one stream for all */
+	uint32_t stream_stride;      /* float4 elements between consecutive streams in `samples` */
+	const vdl2_chunk_args *ca;   /* NULL, or device pointer overriding n_pairs / cnt0 */
 } vdl2_k1_params;
 
 typedef struct {
@@ -38,6 +53,9 @@ typedef struct {
 	void *events;
 	uint32_t event_cap;
 	uint32_t trace;
+	uint32_t variant;            /* walk variant, see vdl2_launch_k2 */
+	uint32_t k2a_mode;           /* 0: libdevice atan2 for every sample; 1: vdl2_phase_fast with the Ziv fall-back */
+	const vdl2_chunk_args *ca;   /* NULL, or device pointer overriding n_dec / dec_base */
 } vdl2_k2_params;
 
 typedef struct {
@@ -55,8 +73,13 @@ typedef struct {
 #ifdef __cplusplus
 extern "C" {
 #endif
-int vdl2_launch_k0(const void *raw, uint32_t n_pairs, uint32_t fmt, const float *levels, float *out4, cudaStream_t st);
-int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, cudaStream_t st);
+/* once per device (thread-safe): the shared-memory carve-out every kernel of the chain asks for */
+int vdl2_kernels_init_device(int device);
+/* n_streams streams of n_pairs samples each: raw stream s at raw + s * raw_stride bytes, output at out4 + s * out_stride float4 */
+int vdl2_launch_k0(const void *raw, uint32_t n_pairs, uint32_t fmt, const float *levels, float *out4, uint32_t n_streams,
+		uint32_t raw_stride, uint32_t out_stride, const vdl2_chunk_args *ca, cudaStream_t st);
+int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, int variant, cudaStream_t st);
+int vdl2_launch_copy_hist(const vdl2_k2_params *p, cudaStream_t st);
 int vdl2_launch_k2a(const vdl2_k2_params *p, cudaStream_t st);
 int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st);
 int vdl2_launch_k3(const vdl2_k3_params *p, uint32_t grid, cudaStream_t st);

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VDL2GPU_ABI_VERSION 1
+#define VDL2GPU_ABI_VERSION 2
 
 /* error codes */
 enum {
@@ -50,7 +50,8 @@ enum {
 	VDL2GPU_FLAG_TRACE = 1u << 0,        /* record sync/header/burst events (debug, parity tests) */
 	VDL2GPU_FLAG_KEEP_DEC = 1u << 1,     /* keep the decimated samples of the last chunk readable (parity tests) */
 	VDL2GPU_FLAG_K1_SCALAR = 1u << 2,    /* use the plain per-sample K1 kernel instead of the pipelined one */
-	VDL2GPU_FLAG_NO_OVERLAP = 1u << 3    /* one stream: do not run K0/K1 of chunk c+1 beside K2/K3 of chunk c (profiling) */
+	VDL2GPU_FLAG_NO_OVERLAP = 1u << 3,   /* one stream: do not run K0/K1 of chunk c+1 beside K2/K3 of chunk c (profiling) */
+	VDL2GPU_FLAG_NO_GRAPH = 1u << 4      /* launch every kernel individually instead of replaying the per-chunk CUDA graphs */
 };
 
 typedef struct {
@@ -65,7 +66,9 @@ typedef struct {
 	int32_t device;              /* CUDA device ordinal; -1 = current device */
 	uint32_t flags;              /* VDL2GPU_FLAG_* */
 	uint32_t n_inflight;         /* chunks in flight before submit blocks (back-pressure); 0 = 4 */
-	uint32_t reserved[5];
+	uint32_t n_streams;          /* independent IQ streams (0 = 1).  With S > 1 the n_channels = S x C channels are split
+	                              * stream-major: channels [s*C, (s+1)*C) demodulate stream s; C must be a multiple of 32 */
+	uint32_t reserved[4];
 } vdl2gpu_config;
 
 /* One AVLC frame with the metadata the reference attaches in decode_frame (src/decode.c:173-194,
@@ -106,7 +109,8 @@ typedef struct {
 	uint64_t out_overflows;              /* bursts lost because the output region was exhausted (must be 0) */
 	uint64_t kernel_launches;            /* kernels launched by this context so far */
 	uint64_t out_bytes;                  /* burst-record bytes K3 wrote to host memory (device->host traffic) */
-	uint64_t reserved[3];
+	uint64_t graph_launches;             /* CUDA graph replays (3 per chunk of the nominal shape; 0 with VDL2GPU_FLAG_NO_GRAPH) */
+	uint64_t reserved[2];
 } vdl2gpu_stats;
 
 /* trace event (VDL2GPU_FLAG_TRACE): same layout as the oracle's vo_event */
@@ -130,7 +134,8 @@ const char *vdl2gpu_last_error(void);
 /* ---- data path ---- */
 /* == process_buf_uchar / process_buf_short (src/demod.c:339-365): `iq` is interleaved I,Q, `len` is in BYTES,
  * the caller may reuse `iq` as soon as the call returns.  Asynchronous: copies into a pinned staging ring,
- * enqueues H2D + kernels.  Blocks only when n_inflight chunks are pending (the reference's back-pressure). */
+ * enqueues H2D + kernels.  Blocks only when n_inflight chunks are pending (the reference's back-pressure).
+ * With n_streams = S > 1, `iq` holds S buffers of `len` bytes back to back (stream 0 first) and `len` is the size of ONE. */
 int vdl2gpu_submit(vdl2gpu_ctx *ctx, const void *iq, uint32_t len);
 /* Ingest adaptor for front-ends that deliver I and Q as separate int16 arrays (SDRplay: src/sdrplay.c:72-134,
  * src/sdrplay3.c): n_pairs values each; replaces the host-side interleave + process_buf_short.  The context must
@@ -171,21 +176,62 @@ int vdl2gpu_read_dec(vdl2gpu_ctx *ctx, float *out, size_t cap_floats, uint32_t *
 /* drain trace events (VDL2GPU_FLAG_TRACE).  Synchronises.  Returns the number copied. */
 int vdl2gpu_read_events(vdl2gpu_ctx *ctx, vdl2gpu_event *out, uint32_t cap);
 /* device time (ms) spent in each kernel for the chunks completed so far, measured with CUDA events on
- * the library's stream when timing was enabled with vdl2gpu_enable_timing(ctx, 1). Order: K0,K1,K2,K3. */
+ * the library's streams when timing was enabled with vdl2gpu_enable_timing(ctx, 1) (timed chunks are launched
+ * kernel by kernel, not as graphs).  Order: K0, K1, K2a, K2 (+history copy), K3 (+finish). */
 int vdl2gpu_enable_timing(vdl2gpu_ctx *ctx, int on);
-int vdl2gpu_get_kernel_ms(vdl2gpu_ctx *ctx, double ms[4], uint64_t launches[4]);
+int vdl2gpu_get_kernel_ms(vdl2gpu_ctx *ctx, double ms[5], uint64_t launches[5]);
 
 /* ---- raw launch stubs (extern "C", plain pointers; used by the micro-parity tests and by hosts that
- *      manage device memory themselves).  All pointers are DEVICE pointers; stream is a cudaStream_t. ---- */
-/* K0: raw cu8/cs16 -> float2 samples (src/demod.c:339-365) */
+ *      manage device memory themselves).  All pointers are DEVICE pointers unless stated otherwise; `stream` is a
+ *      cudaStream_t.  The launch stubs only enqueue kernels: no allocation, no synchronisation.
+ *      (vdl2gpu_launch_rs_verify builds its GF tables on the first call on a device.) ---- */
+/* K0: raw cu8/cs16 -> float samples in the layout K1 consumes, {re, im, im, re} per complex sample
+ * (src/demod.c:339-365: process_buf_uchar / process_buf_short).  levels256 = the 256-entry table of
+ * process_buf_uchar_init (src/demod.c:349-354), only read for VDL2GPU_FMT_U8. */
 int vdl2gpu_launch_convert(const void *raw, uint32_t n_pairs, uint32_t sample_fmt, const float *levels256,
-		float *samples_out /* [n_pairs][2] */, void *stream);
+		float *samples4_out /* [n_pairs][4] */, void *stream);
 /* K4: FCS residue of n frames stored back to back (src/crc.c:21-64 as used at src/avlc.c:177) */
 int vdl2gpu_launch_fcs_crc16(const uint8_t *frames, const uint32_t *offsets, const uint32_t *lens,
 		uint32_t n_frames, uint16_t *residues_out, void *stream);
 /* RS(255,249) errors-and-erasures decode of n blocks in place (src/rs.c:32-49); fec_octets[i] in {0,2,4,6} */
 int vdl2gpu_launch_rs_verify(uint8_t *blocks /* [n][255] */, const int32_t *fec_octets, uint32_t n_blocks,
 		int32_t *ret_out, void *stream);
+
+/* ---- stage stubs: the three per-channel stages one at a time, on device memory the caller owns.
+ * A vdl2gpu_stage is the device-resident state of n_channels vdl2_channel_t's (src/dumpvdl2.h:321-352) plus the
+ * read-only tables, laid out inside ONE block of device memory that the caller allocates (256-byte aligned,
+ * vdl2gpu_stage_device_bytes() bytes).  vdl2gpu_stage_create fills it (synchronous copies, no allocation); the three
+ * launch stubs below then only enqueue kernels on `stream`.  Decimated samples travel between K1 and K2 in a caller
+ * buffer dec[n_dec][row_stride][2] floats, row_stride = vdl2gpu_stage_row_stride(n_channels) (channels padded to 32).
+ * Config fields used: sample_rate, oversample, centerfreq, n_channels, freqs, max_ppm, flags (TRACE, K1_SCALAR). ---- */
+typedef struct vdl2gpu_stage vdl2gpu_stage;
+size_t vdl2gpu_stage_device_bytes(uint32_t n_channels, uint32_t max_dec, uint32_t flags);
+uint32_t vdl2gpu_stage_row_stride(uint32_t n_channels);
+int vdl2gpu_stage_create(const vdl2gpu_config *cfg, uint32_t max_dec /* decimated samples per launch, at most */,
+		void *device_mem, size_t device_bytes, vdl2gpu_stage **out);
+int vdl2gpu_stage_destroy(vdl2gpu_stage *stage);
+/* device address of the stage's cu8 level table, for vdl2gpu_launch_convert */
+int vdl2gpu_stage_levels(vdl2gpu_stage *stage, const float **levels256_dev);
+/* K1: NCO mix + 2-pole Chebyshev IIR + decimation == the sample loop of process_samples (src/demod.c:288-337, with
+ * sincosf_lut :58-72, multiply :200-203, chebyshev_lpf_2pole :74-79) for every channel.  Filter, NCO and decimation
+ * state persist in the stage across calls.  *n_dec_out (host) receives the number of rows written to dec_out. */
+int vdl2gpu_launch_mix_iir_decimate(vdl2gpu_stage *stage, const float *samples4 /* [n_pairs][4] */, uint32_t n_pairs,
+		float *dec_out /* [n_dec][row_stride][2] */, uint32_t *n_dec_out, void *stream);
+/* K2a + K2: demod() (src/demod.c:222-286: phase ring, got_sync :105-198, D8PSK slicing) and the header part of
+ * decode_vdl2_burst (src/decode.c:198-258) over n_dec decimated samples of every channel; completed bursts are
+ * queued inside the stage for vdl2gpu_launch_burst_fec. */
+int vdl2gpu_launch_sync_slice(vdl2gpu_stage *stage, const float *dec /* [n_dec][row_stride][2] */, uint32_t n_dec, void *stream);
+/* K3 (+K4): the data part of decode_vdl2_burst (src/decode.c:259-380: descramble, de-interleave, RS, HDLC unstuff)
+ * and the FCS residue of every frame, for all queued bursts.  `region` (device memory, or mapped pinned host memory;
+ * 16-byte aligned) receives a 32-byte header followed by the burst records; copy it to the host and hand it to
+ * vdl2gpu_parse_records. */
+int vdl2gpu_launch_burst_fec(vdl2gpu_stage *stage, uint8_t *region, uint32_t region_bytes, void *stream);
+/* HOST helper: records of one region -> frames in (channel, burst, idx) order through cb (`data` valid during the
+ * callback).  decimated_rate = sample_rate / oversample.  Returns the number of frames or a negative error. */
+int vdl2gpu_parse_records(const uint8_t *region_host, uint32_t region_bytes, uint32_t decimated_rate,
+		vdl2gpu_frame_cb cb, void *user);
+/* trace events of the stage (VDL2GPU_FLAG_TRACE).  Synchronises the device. */
+int vdl2gpu_stage_read_events(vdl2gpu_stage *stage, vdl2gpu_event *out, uint32_t cap);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported(header):
 
 def test_abi_version_and_struct_sizes():
     L = vd.load_library()
-    assert L.vdl2gpu_abi_version() == 1
+    assert L.vdl2gpu_abi_version() == 2
     from dumpvdl2_b200 import api
     assert C.sizeof(api._Config) == 72 and C.sizeof(api._Stats) == 160 and C.sizeof(api._Event) == 80
 

@@ -1,0 +1,92 @@
+// tools/check_fastmath.cpp — CPU check of vdl2_phase_fast (dumpvdl2_b200/csrc/vdl2_fastmath.cuh) against
+// glibc's (float)atan2((double)im, (double)re), the expression of src/demod.c:232,256.
+//   g++ -O2 -std=c++17 -ffp-contract=off -pthread -I dumpvdl2_b200/csrc tools/check_fastmath.cpp -o /tmp/check_fastmath
+//   /tmp/check_fastmath [millions of samples per thread] [threads]
+// Prints every sample whose non-slow result differs from glibc's (arbitrate those with mpmath: glibc's atan2 is
+// not correctly rounded either) and the rate of slow-path requests.  The reciprocal seed is perturbed by up to
+// 2^-18 to cover the device's MUFU.RCP64H.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <thread>
+#include <vector>
+#include <atomic>
+
+static thread_local double g_seed_err = 0.0;
+#define vdl2_fm_rcp_seed vdl2_fm_rcp_seed_unused
+#include "vdl2_fastmath.cuh"
+#undef vdl2_fm_rcp_seed
+static inline double vdl2_fm_rcp_seed(double d) { return (double)(1.0f / (float)d) * (1.0 + g_seed_err); }
+// second copy of the routine bound to the perturbed seed
+
+static const double TAB[VDL2_ATAN_TABLE_DOUBLES] = VDL2_ATAN_TABLE_INIT;
+static std::atomic<uint64_t> n_total{0}, n_slow{0}, n_bad{0}, n_slow_mode[8];
+
+static void worker(int id, uint64_t n) {
+	std::mt19937_64 rng(0x56444C32ull + id);
+	std::uniform_real_distribution<double> U(0.0, 1.0);
+	std::normal_distribution<float> G(0.f, 1.f);
+	uint64_t slow_c = 0, bad = 0;
+	for(uint64_t i = 0; i < n; i++) {
+		float re, im;
+		const int mode = (int)(i % 8);
+		if(mode == 0) {                                // log-uniform magnitudes
+			re = (float)std::exp(std::log(1e-8) + U(rng) * std::log(1e11)); im = (float)std::exp(std::log(1e-8) + U(rng) * std::log(1e11));
+		} else if(mode == 1) {                         // uniform angle, signal-like radius
+			double a = U(rng) * 6.283185307179586, r = 0.001 + U(rng) * 0.5; re = (float)(r * std::cos(a)); im = (float)(r * std::sin(a));
+		} else if(mode == 2) {                         // noise-like
+			re = 0.01f * G(rng); im = 0.01f * G(rng);
+		} else if(mode == 3) {                         // near the axes and the diagonals
+			double a = (int)(U(rng) * 8) * 0.7853981633974483 + (U(rng) - 0.5) * 1e-3 * std::pow(10.0, -6 * U(rng)); double r = 0.3;
+			re = (float)(r * std::cos(a)); im = (float)(r * std::sin(a));
+		} else if(mode == 4) {                         // near the selection boundaries mn/mx = (k + 0.5)/8
+			double q = ((int)(U(rng) * 8) + 0.5) / 8.0 * (1.0 + (U(rng) - 0.5) * 1e-6); double r = 0.2 * U(rng) + 1e-3;
+			re = (float)r; im = (float)(r * q); if(U(rng) < 0.5) std::swap(re, im);
+		} else if(mode == 5) {                         // small integers / exactly representable ratios
+			re = (float)((int)(U(rng) * 33) - 16); im = (float)((int)(U(rng) * 33) - 16);
+		} else if(mode == 6) {                         // 8-bit sample levels through a scale
+			re = ((int)(U(rng) * 256) - 127.5f) / 127.5f * 0.01f; im = ((int)(U(rng) * 256) - 127.5f) / 127.5f * 0.01f;
+		} else {                                       // wide dynamic range between the components
+			re = (float)std::exp(std::log(1e-20) + U(rng) * std::log(1e40)); im = re * (float)std::exp(-U(rng) * 16.0);
+			if(U(rng) < 0.5) std::swap(re, im);
+		}
+		if(U(rng) < 0.5) re = -re;
+		if(U(rng) < 0.5) im = -im;
+		g_seed_err = (U(rng) - 0.5) * 7.6e-6;          // +-2^-18
+		int slow = 0;
+		const float got = vdl2_phase_fast(re, im, TAB, &slow);
+		const float want = (float)atan2((double)im, (double)re);
+		if(slow) { slow_c++; n_slow_mode[mode]++; continue; }
+		uint32_t a, b; memcpy(&a, &got, 4); memcpy(&b, &want, 4);
+		if(a != b) {
+			bad++;
+			if(bad < 20) printf("MISMATCH re=%a im=%a got=%a want=%a (glibc double %a)\n", re, im, got, want, atan2((double)im, (double)re));
+		}
+	}
+	n_total += n; n_slow += slow_c; n_bad += bad;
+}
+
+int main(int argc, char **argv) {
+	uint64_t per = (argc > 1 ? atoll(argv[1]) : 20) * 1000000ull;
+	int nt = argc > 2 ? atoi(argv[2]) : 8;
+	std::vector<std::thread> th;
+	for(int t = 0; t < nt; t++) th.emplace_back(worker, t, per);
+	for(auto &t : th) t.join();
+	// special values
+	const float sp[] = { 0.f, -0.f, 1.f, -1.f, INFINITY, -INFINITY, NAN, 1e-38f, 1e-45f, 3e38f };
+	int sp_bad = 0;
+	for(float re : sp) for(float im : sp) {
+		int slow = 0; g_seed_err = 0;
+		float got = vdl2_phase_fast(re, im, TAB, &slow);
+		float want = (float)atan2((double)im, (double)re);
+		uint32_t a, b; memcpy(&a, &got, 4); memcpy(&b, &want, 4);
+		if(!slow && a != b) { sp_bad++; printf("SPECIAL MISMATCH re=%a im=%a got=%a want=%a\n", re, im, got, want); }
+	}
+	printf("samples %llu  slow %llu (%.3g)  mismatches %llu  special mismatches %d\n", (unsigned long long)n_total.load(),
+			(unsigned long long)n_slow.load(), (double)n_slow.load() / (double)n_total.load(), (unsigned long long)n_bad.load(), sp_bad);
+	for(int m = 0; m < 8; m++) printf("  mode %d slow rate %.3g\n", m, (double)n_slow_mode[m].load() / ((double)n_total.load() / 8));
+	return (n_bad.load() || sp_bad) ? 1 : 0;
+}
