@@ -5,21 +5,33 @@ Metric (BASELINE.json): VDL2 channels demodulated in real time @ 2.1 Msps, repor
 M channel-samples/s (one channel-sample = one complex input sample processed for one channel);
 channels_at_realtime = value / 2.1.
 
-Workload (BASELINE.json config 5 at one GPU, the largest configuration that fits a single B200):
-16384 channels per GPU = 64 slots x 256 replicas fanned out from ONE synthetic 2.1 Msps cu8 stream
-(Poisson bursts 2/s/slot, Es/N0 20 dB).  One "step" = one pass of the whole path
-(K0 convert, K1 mix+IIR+decimate, K2 sync/slice/header, K3 FEC/unstuff/FCS, frames back on the host) over
-`chunks_per_step` chunks of 262144 IQ pairs (0.125 s of signal each) for every channel.
-With N GPUs the channel count scales with N (weak scaling): global channel k lives on GPU k mod N, rank 0
-owns the stream and every chunk is broadcast with NCCL before each rank demodulates its own shard.
+Workload (BASELINE.json config 5, the largest configuration that fits a single B200): 16384 channels per GPU on
+64 frequency slots x 256 replicas, fanned out from ONE synthetic 2.1 Msps cu8 stream (Poisson bursts 2/s/slot,
+Es/N0 20 dB).  One "step" = one pass of the whole path (K0 convert, K1 mix+IIR+decimate, K2a phase,
+K2 sync/slice/header, K3 FEC/unstuff/FCS, frames back on the host) over `chunks_per_step` chunks of 262144 IQ pairs
+(0.125 s of signal each) for every channel; the default 256 chunks per step make the default K = 6 timed steps a
+region of >= 10 s (SURVEY §8d "steady state, >= 10 s").
 
-  value : chunks resident in HBM before the timed region (N>1: resident on rank 0, NCCL broadcast timed).
-  e2e   : same metric through the public host-buffer API (Vdl2Channels.process_buf_uchar): host->device copy
+  --channel-order interleaved (default): channel k sits on slot k mod 64, so the 32 channels of every warp are 32
+      different signals (what a deployment looks like); `replica`: the 256 replicas of a slot are adjacent, every warp
+      walks 32 copies of one signal and never diverges.  The other order is measured too and printed beside `value`.
+  --scaling weak (default): 16384 channels PER GPU; strong: BASELINE config 5 as written, 16384 channels in total,
+      channel k on GPU k mod N.  Rank 0 owns the stream; every step's chunks reach the other GPUs through the
+      library's multi-GPU ingest helper (vdl2gpu_mg_*: NCCL broadcast or copy-engine peer copies), one step ahead.
+
+  value : chunks resident in HBM before the timed region (N>1: resident on rank 0, the fan-out is timed).
+  e2e   : the same metric through the public host-buffer API (Vdl2Channels.process_buf_uchar): host->device copy
           of every chunk and device->host frame records inside the timed region.
-  --impl reference : the unmodified reference (oracle/_ref/vdl2_ref_fast, one pthread per channel, all host
+  The two legs run A-B-A-B; the first pair gives value / e2e, the second is printed as `repeat`.
+  parity: after the timed legs every rank demodulates the first second of the stream once more on ITS shard, hashes
+          each channel's (burst, idx, frame octets, FEC corrections, header syndrome weight) list and counters and
+          compares them with the oracle (run as a separate checker process on the 64 slot channels); a mismatch
+          anywhere makes the benchmark fail.
+  --impl reference : the unmodified reference (oracle/_ref/vdl2_ref_fast, one pinned pthread per channel, all host
           threads) on a bounded sample of the same stream; falls back to the oracle port if _ref is absent.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -38,126 +50,213 @@ OVERSAMPLE = 20
 CENTER = 136975000
 CHUNK_PAIRS = 262144
 CHUNK_BYTES = 2 * CHUNK_PAIRS
+N_SLOTS = 64
 B_CS = 8.0 + 8.0 / OVERSAMPLE        # algorithmic bytes per channel-sample for K1: 8 B read + 8/os B written
+PARITY_CHUNKS = 8                    # the first second of the stream is re-run for the in-bench parity check
+METRIC = "VDL2 channel-samples demodulated per second (2.1 Msps channels; real-time channels = value/2.1)"
 
 
 def make_stream(seconds):
     from dumpvdl2_b200 import synth
-    iq, offs, bursts = synth.traffic_stream(FS, seconds, 64, 2.0, 20.0, -20.0, 0x56444C33, "u8")
+    iq, offs, bursts = synth.traffic_stream(FS, seconds, N_SLOTS, 2.0, 20.0, -20.0, 0x56444C33, "u8")
     n_chunks = iq.size // CHUNK_BYTES
     return iq[:n_chunks * CHUNK_BYTES].reshape(n_chunks, CHUNK_BYTES), offs, bursts
 
 
-def channel_freqs(offs, n_total):
-    reps = -(-n_total // len(offs))
-    return np.array([CENTER + int(o) for o in offs for _ in range(reps)][:n_total], dtype=np.uint32)
+def slot_of_channel(n_total, order):
+    """global channel index -> frequency slot"""
+    k = np.arange(n_total)
+    if order == "interleaved":
+        return k % N_SLOTS
+    reps = -(-n_total // N_SLOTS)
+    return np.minimum(k // reps, N_SLOTS - 1)
 
 
+def channel_freqs(offs, n_total, order="replica"):
+    slot = slot_of_channel(n_total, order)
+    return (CENTER + np.asarray(offs, dtype=np.int64)[slot]).astype(np.uint32)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks (NVML in-process: no nvidia-smi child competing for the driver during the timed region)
+# ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    def __init__(self, gpu_index, period=0.25):
+        self.gpu, self.period, self.rows, self.stop_flag, self.thread, self.h = gpu_index, period, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(gpu_index))
+        except Exception:
+            self.nv = None
 
-    def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+    @staticmethod
+    def _physical_index(i):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[i])
+            except Exception:
+                return i
+        return i
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((time.time(), sm, mx, reasons, pw))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+        if self.nv is None or self.h is None:
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self, t0, t1):
-        if self.proc is None:
+        if self.thread is None:
             return None
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows]
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows
         if not rows:
             return None
-        sm = sorted(float(r[1]) for r in rows if r[1].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 5 + k and r[5 + k].lower().startswith("active") for r in rows)]
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=float(rows[0][2]) if rows[0][2].replace(".", "").isdigit() else None,
-                    reasons=reasons, samples=len(rows))
+        sm = sorted(r[1] for r in rows)
+        bits = 0
+        for r in rows:
+            bits |= int(r[3])
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        return dict(sm_mhz=float(sm[len(sm) // 2]), sm_min_mhz=float(sm[0]), sm_max_mhz=float(rows[0][2]),
+                    reasons=[n for b, n in names.items() if bits & b], samples=len(rows), power_w_max=max(r[4] for r in rows),
+                    source="NVML in-process, 4 Hz, during the first timed leg")
 
 
-def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path on this host's cores."""
-    if rank != 0:
-        return
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline
+# ------------------------------------------------------------------------------------------------------------------
+def _ref_passes(chunks, offs, passes, loops):
+    """oracle/_ref/vdl2_ref_fast (the unmodified reference) on a bounded sample: returns (n_ch, cores, [M ch-samples/s per pass])"""
     from oracle import pyoracle as po
     cores = os.cpu_count() or 1
     n_ch = max(1, min(cores - 1 if cores > 1 else 1, 256))
-    chunks, offs, _ = make_stream(1.0)
-    freqs = channel_freqs(offs, n_ch)
-    exe = po.ref_binary("fast")
-    sample_pairs = chunks.size // 2
+    freqs = channel_freqs(offs, n_ch, "interleaved")
     with tempfile.NamedTemporaryFile(suffix=".cu8", delete=False) as tf:
         tf.write(chunks.tobytes())
         path = tf.name
-    per = []
-    kind = "reference" if exe else "port"
+    vals = []
     try:
-        for step in range(args.warmup + args.steps):
-            if exe:
-                _, st = po.run_ref(path, po.FMT_U8, OVERSAMPLE, CENTER, freqs, flavour="fast", chunk=CHUNK_BYTES, quiet=True)
-                dt = st["wall_s"]
-            else:
-                n_ch = 4
-                o = po.Oracle(FS, OVERSAMPLE, po.FMT_U8, CENTER, freqs[:n_ch])
-                t0 = time.time(); o.process_chunked(chunks.reshape(-1), CHUNK_BYTES); dt = time.time() - t0
-            if step >= args.warmup:
-                per.append(dt)
+        for _ in range(passes):
+            _, st = po.run_ref(path, po.FMT_U8, OVERSAMPLE, CENTER, freqs, flavour="fast", chunk=CHUNK_BYTES, quiet=True, loop=loops, pin=True)
+            vals.append(st["ch_msamples_per_s"])
     finally:
         os.unlink(path)
-    t = float(np.mean(per))
-    value = n_ch * sample_pairs / t / 1e6
-    sample = f"{n_ch} channels x {sample_pairs / FS:.2f} s of the bench stream per step ({'one pthread per channel + producer' if exe else 'single-thread oracle port'})"
-    line = dict(impl="reference", metric="VDL2 channel-samples demodulated per second (2.1 Msps channels; real-time channels = value/2.1)",
-                value=value, unit="Msamples/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3,
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=f"reference CPU path on a bounded sample: {sample}", fs=FS, oversample=OVERSAMPLE,
-                            channels=n_ch, sample_fmt="cu8", l2="n/a (CPU)"),
-                channels_at_realtime=value / 2.1,
-                cpu_baseline=dict(value=value, unit="Msamples/s", cores=(n_ch + 1 if exe else 1), kind=kind, sample=sample,
-                                  host_cpus=cores),
-                e2e=dict(value=value, unit="Msamples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    return n_ch, cores, vals
 
 
-def cpu_baseline_leg():
-    """Bounded (~10-30 s) timing of the reference CPU path on this host, reported beside the GPU numbers."""
+def cpu_baseline_leg(passes=3):
+    """Bounded (~10-30 s) timing of the reference CPU path on this host, reported beside the GPU numbers: median of
+    `passes` runs, one pinned thread per channel."""
     from oracle import pyoracle as po
-    cores = os.cpu_count() or 1
-    exe = po.ref_binary("fast")
     chunks, offs, _ = make_stream(1.0)
-    if exe:
-        n_ch = max(1, min(cores - 1 if cores > 1 else 1, 256))
-        freqs = channel_freqs(offs, n_ch)
-        with tempfile.NamedTemporaryFile(suffix=".cu8", delete=False) as tf:
-            tf.write(chunks.tobytes()); path = tf.name
-        try:
-            loops = 4
-            _, st = po.run_ref(path, po.FMT_U8, OVERSAMPLE, CENTER, freqs, flavour="fast", chunk=CHUNK_BYTES, quiet=True, loop=loops)
-        finally:
-            os.unlink(path)
-        v = st["ch_msamples_per_s"]
-        return dict(value=v, unit="Msamples/s", cores=n_ch + 1, kind="reference", host_cpus=cores,
-                    sample=f"{n_ch} channels (one pthread each + 1 producer) x {loops} x {chunks.size / 2 / FS:.2f} s of the bench stream, "
-                           f"unmodified reference built -O2 -ffast-math", channels_at_realtime=v / 2.1)
+    cores = os.cpu_count() or 1
+    if po.ref_binary("fast"):
+        loops = 2
+        n_ch, cores, vals = _ref_passes(chunks, offs, passes, loops)
+        v = float(np.median(vals))
+        return dict(value=v, unit="Msamples/s", cores=n_ch + 1, kind="reference", host_cpus=cores, passes=[round(x, 1) for x in vals],
+                    sample=f"{n_ch} channels (one pinned pthread each + 1 producer) x {loops} x {chunks.size / 2 / FS:.2f} s of the bench stream, "
+                           f"median of {passes} passes, unmodified reference built -O2 -ffast-math", channels_at_realtime=v / 2.1)
     n_ch = 4
-    o = po.Oracle(FS, OVERSAMPLE, po.FMT_U8, CENTER, channel_freqs(offs, n_ch))
+    o = po.Oracle(FS, OVERSAMPLE, po.FMT_U8, CENTER, channel_freqs(offs, n_ch, "interleaved"))
     t0 = time.time(); o.process_chunked(chunks.reshape(-1), CHUNK_BYTES); dt = time.time() - t0
     v = n_ch * chunks.size / 2 / dt / 1e6
     return dict(value=v, unit="Msamples/s", cores=1, kind="port", host_cpus=cores,
                 sample=f"{n_ch} channels x {chunks.size / 2 / FS:.2f} s, single-thread oracle port", channels_at_realtime=v / 2.1)
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path on this host's cores; a step = one pass of
+    all channel threads over the bounded sample."""
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    chunks, offs, _ = make_stream(1.0)
+    cores = os.cpu_count() or 1
+    per = []
+    if po.ref_binary("fast"):
+        kind = "reference"
+        loops = 4
+        n_ch, cores, vals = _ref_passes(chunks, offs, args.warmup + args.steps, loops)
+        per = vals[args.warmup:]
+        threads = n_ch + 1
+        how = "one pinned pthread per channel + producer"
+    else:
+        kind, n_ch, threads, how, loops = "port", 4, 1, "single-thread oracle port", 1
+        for step in range(args.warmup + args.steps):
+            o = po.Oracle(FS, OVERSAMPLE, po.FMT_U8, CENTER, channel_freqs(offs, n_ch, "interleaved"))
+            t0 = time.time(); o.process_chunked(chunks.reshape(-1), CHUNK_BYTES); dt = time.time() - t0
+            if step >= args.warmup:
+                per.append(n_ch * chunks.size / 2 / dt / 1e6)
+    value = float(np.median(per))
+    sample_pairs = loops * chunks.size // 2
+    sample = f"{n_ch} channels x {sample_pairs / FS:.2f} s of the bench stream per step ({how}); value = median over the timed steps"
+    line = dict(impl="reference", metric=METRIC, value=value, unit="Msamples/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=n_ch * sample_pairs / value / 1e3, higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32",
+                data="synthetic",
+                config=dict(workload=f"reference CPU path on a bounded sample: {sample}", fs=FS, oversample=OVERSAMPLE,
+                            channels=n_ch, sample_fmt="cu8", l2="n/a (CPU)"),
+                channels_at_realtime=value / 2.1, per_step=[round(x, 1) for x in per],
+                cpu_baseline=dict(value=value, unit="Msamples/s", cores=threads, kind=kind, sample=sample, host_cpus=cores),
+                e2e=dict(value=value, unit="Msamples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# parity checker (the oracle runs in its own process: nothing under oracle/ is loaded into the measured process)
+# ------------------------------------------------------------------------------------------------------------------
+def digest_frames(frames, counters_row):
+    h = hashlib.sha256()
+    for f in sorted(frames, key=lambda f: (f.burst_seq, f.idx)):
+        h.update(f"{f.burst_seq},{f.idx},{f.num_fec_corrections},{f.synd_weight},{f.data.hex()};".encode())
+    h.update(",".join(str(int(x)) for x in counters_row).encode())
+    return h.hexdigest()
+
+
+def oracle_digest_main(path_in, path_out):
+    """hidden mode (--oracle-digest): oracle over the 64 slot channels of the parity sample -> per-slot digests"""
+    from oracle import pyoracle as po
+    with open(path_in, "rb") as f:
+        meta = json.loads(f.readline().decode())
+        iq = np.frombuffer(f.read(), np.uint8)
+    o = po.Oracle(FS, OVERSAMPLE, po.FMT_U8, CENTER, np.asarray(meta["freqs"], dtype=np.uint32))
+    o.process_chunked(iq, CHUNK_BYTES)
+    by = {}
+    for f in o.frames():
+        by.setdefault(f.channel, []).append(f)
+    cnt = o.counters()
+    out = dict(digests=[digest_frames(by.get(s, []), cnt[s]) for s in range(len(meta["freqs"]))],
+               frames=sum(len(v) for v in by.values()))
+    with open(path_out, "w") as f:
+        json.dump(out, f)
+
+
+def oracle_slot_digests(chunks, offs):
+    with tempfile.TemporaryDirectory() as td:
+        pin, pout = os.path.join(td, "in.bin"), os.path.join(td, "out.json")
+        with open(pin, "wb") as f:
+            f.write((json.dumps(dict(freqs=[int(CENTER + int(o)) for o in offs])) + "\n").encode())
+            f.write(chunks[:PARITY_CHUNKS].tobytes())
+        subprocess.run([sys.executable, os.path.abspath(__file__), "--oracle-digest", pin, pout], check=True)
+        with open(pout) as f:
+            return json.load(f)
 
 
 def main():
@@ -166,18 +265,27 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--channels", type=int, default=16384, help="channels per GPU")
-    ap.add_argument("--chunks-per-step", type=int, default=8)
+    ap.add_argument("--channels", type=int, default=16384, help="channels per GPU (weak scaling) / in total (strong scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--channel-order", default="interleaved", choices=["interleaved", "replica"])
+    ap.add_argument("--chunks-per-step", type=int, default=256)
     ap.add_argument("--stream-seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-repeat", action="store_true", help="skip the second value/e2e pair and the other channel order")
     ap.add_argument("--k1-scalar", action="store_true")
+    ap.add_argument("--fanout", default="auto", choices=["auto", "nccl", "ce"], help="multi-GPU ingest: NCCL broadcast or copy-engine peer copies")
+    ap.add_argument("--oracle-digest", nargs=2, metavar=("IN", "OUT"), help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.oracle_digest:
+        oracle_digest_main(*args.oracle_digest)
+        return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
 
     # keep stdout clean for the single JSON line: libraries (NCCL prints its version banner there) write to stderr instead
@@ -188,6 +296,7 @@ def main():
     import torch
     import torch.distributed as dist
     import dumpvdl2_b200 as vd
+    from dumpvdl2_b200 import shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the demodulator path has no CPU fallback")
@@ -197,214 +306,328 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     W, K, CPS = max(args.warmup, 3), args.steps, args.chunks_per_step
-    n_total = args.channels * world
+    n_total = args.channels * world if args.scaling == "weak" else args.channels
     chunks, offs, bursts = make_stream(args.stream_seconds)       # same seed on every rank
     n_chunks = chunks.shape[0]
-    all_freqs = channel_freqs(offs, n_total)
-    my_freqs = all_freqs[rank::world]                             # channel k -> GPU k mod N
     flags = vd.FLAG_K1_SCALAR if args.k1_scalar else 0
-    g = vd.Vdl2Channels(FS, OVERSAMPLE, vd.FMT_U8, CENTER, my_freqs, max_chunk_bytes=CHUNK_BYTES, device=local_rank, flags=flags)
     stream = torch.cuda.current_stream()
 
-    # chunks resident in HBM on the ingest rank (rank 0).  With N > 1 every step's CPS chunks are broadcast in ONE
-    # NCCL call (bucket sized for launch latency: 4 MiB instead of 8 x 0.5 MiB) into a double-buffered receive
-    # area, then each rank demodulates its channel shard straight out of that buffer.
-    if rank == 0:
-        d_chunks = torch.from_numpy(chunks).cuda()
+    def make_ctx(order, extra_flags=0):
+        all_freqs = channel_freqs(offs, n_total, order)
+        mine = shard.my_channels(all_freqs, rank, world)          # channel k -> GPU k mod N
+        return vd.Vdl2Channels(FS, OVERSAMPLE, vd.FMT_U8, CENTER, mine, max_chunk_bytes=CHUNK_BYTES, device=local_rank,
+                               flags=flags | extra_flags), mine
+
+    g, my_freqs = make_ctx(args.channel_order)
+    n_mine = len(my_freqs)
+
+    # chunks resident in HBM on the ingest rank (rank 0) and in pinned host memory
+    d_chunks = torch.from_numpy(chunks).cuda()          # every rank keeps a copy for the local kernel timing; rank 0's is the fan-out source
     h_chunks = torch.from_numpy(chunks).pin_memory()
-    d_recv = [torch.empty(CPS * CHUNK_BYTES, dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    state = dict(chunk=0, bcast=0)
+    # N > 1: the library's multi-GPU ingest helper owns the double-buffered receive area and the fan-out
+    mg = shard.MultiGpuIngest(g, rank, world, CPS * CHUNK_BYTES, mode=args.fanout) if world > 1 else None
+    state = dict(chunk=0)
 
     def next_indices():
         idx = [(state["chunk"] + k) % n_chunks for k in range(CPS)]
         state["chunk"] += CPS
         return idx
 
-    def gather_rows(src, idx, dst):
-        """rows idx of src -> dst (flat), contiguous runs copied in one go"""
-        k = 0
+    host_t = dict(submit_s=0.0, submits=0)
+
+    def gather_rows(src, idx):
+        """[(ptr, nbytes)] of the contiguous runs of rows idx in src (device- or pinned-host-resident tensor)"""
+        runs, k = [], 0
         while k < len(idx):
             j = k
             while j + 1 < len(idx) and idx[j + 1] == idx[j] + 1:
                 j += 1
-            dst[k * CHUNK_BYTES:(j + 1) * CHUNK_BYTES].copy_(src[idx[k]:idx[j] + 1].reshape(-1), non_blocking=True)
+            runs.append((src[idx[k]].data_ptr(), (j + 1 - k) * CHUNK_BYTES))
             k = j + 1
+        return runs
 
-    # N > 1: the broadcast of step s+1 is issued BEFORE the chunks of step s are submitted (the receive area is double
-    # buffered), so no rank ever waits for the ingest rank at a step boundary: the collective overlaps the kernels.
-    def stage_bcast(src_rows):
-        """rank 0 gathers the next step's chunks (device- or pinned-host-resident) into the free half of the receive
-        area and everybody joins the broadcast; returns the buffer"""
-        idx = next_indices()
-        buf = d_recv[state["bcast"] % 2]
-        state["bcast"] += 1
-        g.wait_input_consumed(stream.cuda_stream)              # every K0 that read this half has run (2 steps ago)
-        if rank == 0:
-            gather_rows(src_rows, idx, buf)
-        dist.broadcast(buf, src=0)
-        return buf
-
-    def step_multi(src_rows):
-        if state.get("staged") is None or state.get("staged_src") is not src_rows:
-            state["staged"] = stage_bcast(src_rows)            # first step of a pass
+    def step_multi(src_rows, src_is_host):
+        """stage step s+1 (rank 0 gathers the chunks into the free half of the receive area, all ranks take part in the
+        fan-out) BEFORE the chunks of step s are submitted: the transfer overlaps the kernels"""
+        if state.get("staged_src") is not src_rows or state.get("staged") is None:
+            state["staged"] = mg.stage(gather_rows(src_rows, next_indices()) if rank == 0 else None, src_is_host)
             state["staged_src"] = src_rows
         buf = state["staged"]
-        nxt = stage_bcast(src_rows)                             # next step's chunks travel while this step computes
-        for k in range(CPS):
-            g.submit_device(buf.data_ptr() + k * CHUNK_BYTES, CHUNK_BYTES, stream.cuda_stream)
-        state["staged"] = nxt
+        state["staged"] = mg.stage(gather_rows(src_rows, next_indices()) if rank == 0 else None, src_is_host)
+        t0 = time.perf_counter()
+        mg.submit_staged(buf, CPS, CHUNK_BYTES)
+        host_t["submit_s"] += time.perf_counter() - t0; host_t["submits"] += CPS
         return g.poll_count()
 
     def step_device():
-        """one step, chunks already in HBM (N>1: one NCCL broadcast per step from rank 0, one step ahead)"""
+        """one step, chunks already in HBM (N>1: fanned out from rank 0, one step ahead)"""
         if world > 1:
-            return step_multi(d_chunks if rank == 0 else None)
+            return step_multi(d_chunks if rank == 0 else None, False)
+        t0 = time.perf_counter()
         for i in next_indices():
             g.submit_device(d_chunks[i].data_ptr(), CHUNK_BYTES, stream.cuda_stream)
+        host_t["submit_s"] += time.perf_counter() - t0; host_t["submits"] += CPS
         return g.poll_count()
 
     def step_host():
         """one step through the public host-buffer entry point (process_buf_uchar); with N > 1 the ingest rank copies
-        the step's chunks host->device and broadcasts them, the other ranks receive"""
+        the step's chunks host->device and fans them out, the other ranks receive"""
         if world > 1:
-            return step_multi(h_chunks)
+            return step_multi(h_chunks, True)
+        hn = h_chunks.numpy()
+        t0 = time.perf_counter()
         for i in next_indices():
-            g.process_buf_uchar(h_chunks[i].numpy())
+            g.process_buf_uchar(hn[i])
+        host_t["submit_s"] += time.perf_counter() - t0; host_t["submits"] += CPS
         return g.poll_count()
 
     def timed(step_fn, steps, sample_clocks=False):
-        # one sampler for the job (rank 0's GPU): eight concurrent nvidia-smi pollers contend for the driver lock.
-        # It is started BEFORE the barrier so that no rank enters the timed region late.
         sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
-        if sampler:
-            sampler.start()
-        if sample_clocks:
-            time.sleep(0.3)
         barrier()
         s0 = g.stats()
+        host_t["submit_s"], host_t["submits"] = 0.0, 0
+        if sampler:
+            sampler.start()
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 2)]
         t0 = time.time()
-        e0.record(stream)
+        ev[0].record(stream)
         frames = 0
-        for _ in range(steps):
+        for k in range(steps):
             frames += step_fn()          # submits + non-blocking harvest: the pipeline stays full across steps
-        frames += g.flush_count()       # everything submitted is processed and its frames are on the host
+            g.stream_wait(stream.cuda_stream)
+            ev[k + 1].record(stream)     # completes when every kernel of steps 0..k has run
+        frames += g.flush_count()        # everything submitted is processed and its frames are on the host
         g.stream_wait(stream.cuda_stream)
-        e1.record(stream)
+        ev[steps + 1].record(stream)
         barrier()
         t1 = time.time()
-        ms = e0.elapsed_time(e1)
+        ms = ev[0].elapsed_time(ev[steps + 1])
+        per = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
         if world > 1:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         clocks = sampler.stop(t0, t1) if sampler else None
         s1 = g.stats()
-        return ms, frames, {k: s1[k] - s0[k] for k in s1}, clocks, (t1 - t0) * 1e3
+        return dict(ms=ms, per_step=per, frames=frames, d={k: s1[k] - s0[k] for k in s1}, clocks=clocks, wall_ms=(t1 - t0) * 1e3,
+                    host_us_per_submit=host_t["submit_s"] / max(host_t["submits"], 1) * 1e6)
 
-    for _ in range(W):
-        step_device()
-    g.flush_count()
-    ms_dev, frames_dev, d_dev, clocks, wall_dev = timed(step_device, K, sample_clocks=True)
-    for _ in range(2):
-        step_host()
-    g.flush_count()
-    ms_e2e, frames_e2e, d_e2e, _, wall_e2e = timed(step_host, K)
+    def reset_staging():
+        state["staged"] = None; state["staged_src"] = None
 
-    # Per-kernel durations for the roofline.  The production pipeline runs K0/K1 of chunk c+1 beside K2/K3 of chunk c
-    # on two streams, which stretches every kernel's wall time; the kernel's OWN launch duration is therefore measured
-    # here, live, with CUDA events on the library's stream, same workload, same process, with that overlap switched off
+    def leg(kind, steps, warm, sample_clocks=False):
+        fn = step_device if kind == "device" else step_host
+        reset_staging()
+        for _ in range(warm):
+            fn()
+        g.flush_count()
+        r = timed(fn, steps, sample_clocks)
+        g.flush_count()
+        reset_staging()
+        return r
+
+    cs_per_step = float(n_total) * CPS * CHUNK_PAIRS
+
+    def rate(r, steps):
+        return cs_per_step * steps / (r["ms"] * 1e-3) / 1e6
+
+    # ---- A-B-A-B ----
+    A1 = leg("device", K, W, sample_clocks=True)
+    B1 = leg("host", K, 1)
+    A2 = B2 = None
+    if not args.no_repeat:
+        A2 = leg("device", K, 1)
+        B2 = leg("host", K, 1)
+
+    # ---- the other channel order, same code path, a shorter region ----
+    other = None
+    if not args.no_repeat:
+        other_order = "replica" if args.channel_order == "interleaved" else "interleaved"
+        g_main, mg_main = g, mg
+        g, _ = make_ctx(other_order)
+        if world > 1:
+            mg = shard.MultiGpuIngest(g, rank, world, CPS * CHUNK_BYTES, mode=args.fanout)
+        ko = max(2, K // 2)
+        r = leg("device", ko, 1)
+        other = dict(order=other_order, value=rate(r, ko), ms_per_step=r["ms"] / ko)
+        if world > 1:
+            mg.close()
+        g.close()
+        g, mg = g_main, mg_main
+
+    # ---- per-kernel durations for the roofline: the production pipeline runs K0/K1 of chunk c+1 beside K2/K3 of chunk c
+    # on two streams, which stretches every kernel's wall time; the kernel's OWN launch duration is therefore measured here,
+    # live, with CUDA events on the library's streams, same workload, same process, with that overlap switched off
     # (VDL2GPU_FLAG_NO_OVERLAP) - the condition the committed ncu launch list is taken under as well.
-    g_main = g
-    g = vd.Vdl2Channels(FS, OVERSAMPLE, vd.FMT_U8, CENTER, my_freqs, max_chunk_bytes=CHUNK_BYTES, device=local_rank,
-                        flags=flags | vd.FLAG_NO_OVERLAP)
-    for _ in range(2):
-        step_device()
-    g.flush_count()
-    g.enable_timing(True)
-    k0 = g.kernel_ms()
-    ms_serial, _, _, _, _ = timed(step_device, max(2, K // 2))
-    k1 = g.kernel_ms()
-    g.close()
-    g = g_main
+    kms, ms_serial, n_serial = None, None, 0
+    if True:                             # at any N: every rank times its own kernels on locally resident chunks (no fan-out involved)
+        g_main = g
+        g, _ = make_ctx(args.channel_order, vd.FLAG_NO_OVERLAP)
+        for _ in range(8):
+            g.submit_device(d_chunks[_ % n_chunks].data_ptr(), CHUNK_BYTES, stream.cuda_stream)
+        g.flush_count()
+        g.enable_timing(True)
+        k0 = g.kernel_ms()
+        n_serial = 48
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(n_serial):
+            g.submit_device(d_chunks[i % n_chunks].data_ptr(), CHUNK_BYTES, stream.cuda_stream)
+            g.poll_count()
+        g.flush_count()
+        g.stream_wait(stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_serial = e0.elapsed_time(e1) / n_serial
+        k1 = g.kernel_ms()
+        g.close()
+        g = g_main
+        kms = {k: ((k1[k][0] - k0[k][0]) / max(k1[k][1] - k0[k][1], 1)) for k in k1}
 
-    pairs_per_step = CPS * CHUNK_PAIRS
-    cs_per_step = float(n_total) * pairs_per_step
-    value = cs_per_step * K / (ms_dev * 1e-3) / 1e6
-    e2e_value = cs_per_step * K / (ms_e2e * 1e-3) / 1e6
-    kms = {k: (k1[k][0] - k0[k][0], k1[k][1] - k0[k][1]) for k in k1}
-    k1_ms_per_launch = kms["K1"][0] / max(kms["K1"][1], 1)
-    achieved = len(my_freqs) * CHUNK_PAIRS * B_CS / (k1_ms_per_launch * 1e-3) / 1e9 if k1_ms_per_launch > 0 else None
-    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peak = float(json.load(f)["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json, burst copy)"
-    except Exception:
-        pass
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "k1_ncu_traffic.json")) as f:
-            tj = json.load(f)
-            if tj.get("channels") == len(my_freqs) and tj.get("chunk_pairs") == CHUNK_PAIRS:
-                traffic = tj["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    tot_k = sum(v[0] for v in kms.values()) or 1.0
+    # ---- parity: every rank re-runs the first second on its shard and compares with the oracle's slot channels ----
+    parity = None
+    if not args.no_parity:
+        ref = None
+        if rank == 0:
+            ref = oracle_slot_digests(chunks, offs)
+        if world > 1:
+            box = [ref]
+            dist.broadcast_object_list(box, src=0)
+            ref = box[0]
+        gp, mine = make_ctx(args.channel_order)
+        for i in range(PARITY_CHUNKS):
+            gp.process_buf_uchar(chunks[i])
+        by = {}
+        for f in gp.flush():
+            by.setdefault(f.channel, []).append(f)
+        cnt = gp.channel_counters()
+        gp.close()
+        slot = slot_of_channel(n_total, args.channel_order)[rank::world]
+        mism, frames_checked = 0, 0
+        for j in range(len(mine)):
+            fr = by.get(j, [])
+            frames_checked += len(fr)
+            if digest_frames(fr, cnt[j]) != ref["digests"][int(slot[j])]:
+                mism += 1
+        tot = torch.tensor([mism, len(mine), frames_checked, 1], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot)
+        parity = dict(ranks_checked=int(tot[3]), channels_checked=int(tot[1]), frames_checked=int(tot[2]), mismatches=int(tot[0]),
+                      oracle_frames_per_slot_set=ref["frames"], seconds=PARITY_CHUNKS * CHUNK_PAIRS / FS,
+                      what="per-channel (burst, idx, frame octets, FEC corrections, syndrome weight) lists + 9 counters vs the oracle port")
+
+    value = rate(A1, K)
+    e2e_value = rate(B1, K)
 
     if rank == 0:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peak = float(json.load(f)["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json, burst copy)"
+        except Exception:
+            pass
+        prof = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "kernel_counters.json")) as f:
+                prof = json.load(f)
+        except Exception:
+            pass
+        roofline = None
+        if kms:
+            k1_ms = kms["K1"]
+            achieved = n_mine * CHUNK_PAIRS * B_CS / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
+            tot_k = sum(kms.values()) or 1.0
+            n_dec = CHUNK_PAIRS // OVERSAMPLE
+            sm_clock = 1.965e9
+            smsp = 148 * 4
+            traffic = None
+            tj = prof.get("K1", {})
+            if tj.get("channels") == n_mine and tj.get("chunk_pairs") == CHUNK_PAIRS:
+                traffic = tj.get("dram_bytes_per_launch")
+            stages = {}
+            for name in ("K1", "K2a", "K2", "K3"):
+                pj = prof.get(name, {})
+                ent = dict(ms_per_launch=kms[name], share_of_step=kms[name] / tot_k)
+                wi = pj.get("warp_instructions_per_launch")
+                if wi and pj.get("channels") == n_mine and kms[name] > 0:
+                    # issue-slot model: warp-instructions issued / (SM sub-partitions x clock x duration)
+                    ent["issue_slots"] = dict(warp_instructions=wi, frac=wi / (smsp * sm_clock * kms[name] * 1e-3),
+                                              per_decimated_sample_per_warp=wi / (n_dec * -(-n_mine // 32)))
+                if pj.get("dram_bytes_per_launch") and pj.get("channels") == n_mine:
+                    ent["dram_gbs"] = pj["dram_bytes_per_launch"] / (kms[name] * 1e-3) / 1e9
+                    ent["dram_frac_of_peak"] = ent["dram_gbs"] / peak
+                stages[name] = ent
+            fp32 = n_mine * CHUNK_PAIRS * 24.0 / (k1_ms * 1e-3)
+            roofline = dict(bound="hbm", kernel="k1_mix_iir_decimate", achieved=achieved, peak=peak, unit="GB/s",
+                            frac=(achieved / peak) if achieved else None, traffic=traffic, peak_source=peak_src,
+                            bytes_per_channel_sample=B_CS, ms_per_launch=k1_ms,
+                            note="SURVEY §8d effective-bandwidth model (each channel streams the float IQ buffer: 8.4 B per channel-sample). "
+                                 "It is NOT HBM utilisation: the shared stream is staged once per warp in shared memory (TMA), real DRAM traffic "
+                                 "is `traffic`; the bound that binds K1 is `binding` (FP32 issue of one warp per SM sub-partition)",
+                            binding=dict(bound="fp32-issue", achieved=fp32 / 1e12, peak=148 * 128 * sm_clock / 1e12, unit="T lane-ops/s",
+                                         frac=fp32 / (148 * 128 * sm_clock),
+                                         note="24 individually rounded FP32 operations per channel-sample (12 packed FMUL2/FFMA2; contraction is not "
+                                              "allowed by the bit-exactness contract) against 148 SMs x 128 FP32 lanes x 1.965 GHz; a single warp "
+                                              "per sub-partition can reach ~0.72 of it (26.4 of 37 issue cycles per sample are FP32)"),
+                            stages=stages,
+                            measured="CUDA events on the library's streams, kernels serialised (VDL2GPU_FLAG_NO_OVERLAP, kernel-by-kernel "
+                                     "launches), same workload and process; value/e2e run the two-stage overlap with CUDA graph replay",
+                            serial_ms_per_chunk=ms_serial, sum_kernel_ms_per_chunk=tot_k)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cpu = cpu_baseline_leg()
             except Exception as ex:          # the baseline is a report, never a dependency of the GPU path
                 cpu = dict(error=str(ex))
+
+        def stat(per):
+            s = sorted(per)
+            return dict(min=s[0], median=s[len(s) // 2], max=s[-1])
         line = dict(
-            metric="VDL2 channel-samples demodulated per second (2.1 Msps channels; real-time channels = value/2.1)",
-            value=value, unit="Msamples/s", n_gpus=world, steps=K, warmup=W, ms_per_step=ms_dev / K,
-            higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-            config=dict(workload=f"{args.channels} channels/GPU ({n_total} total) = 64 slots x {n_total // 64} replicas from one synthetic "
-                                 f"2.1 Msps cu8 stream (BASELINE config 5 shape; Poisson bursts 2/s/slot, Es/N0 20 dB); "
-                                 f"step = {CPS} chunks x {CHUNK_PAIRS} IQ pairs",
-                        fs=FS, oversample=OVERSAMPLE, channels_per_gpu=args.channels, channels_total=n_total, sample_fmt="cu8",
-                        chunk_pairs=CHUNK_PAIRS, chunks_per_step=CPS, parallelism=f"channel-shard x{world} (k mod N), NCCL broadcast of IQ" if world > 1 else "single GPU",
-                        l2=f"per-chunk working set (decimated buffer {len(my_freqs) * (CHUNK_PAIRS // OVERSAMPLE) * 8 / 1e6:.0f} MB written by K1, read by K2) exceeds the 126 MB L2",
+            metric=METRIC, value=value, unit="Msamples/s", n_gpus=world, steps=K, warmup=W, ms_per_step=A1["ms"] / K,
+            higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic",
+            config=dict(workload=f"{n_mine} channels/GPU ({n_total} total) on 64 slots from one synthetic 2.1 Msps cu8 stream "
+                                 f"(BASELINE config 5; Poisson bursts 2/s/slot, Es/N0 20 dB); step = {CPS} chunks x {CHUNK_PAIRS} IQ pairs "
+                                 f"= {CPS * CHUNK_PAIRS / FS:.1f} s of signal per channel",
+                        fs=FS, oversample=OVERSAMPLE, channels_per_gpu=n_mine, channels_total=n_total, sample_fmt="cu8",
+                        chunk_pairs=CHUNK_PAIRS, chunks_per_step=CPS, channel_order=args.channel_order,
+                        parallelism=(f"channel-shard x{world} (k mod N), {mg.mode_name} fan-out of the IQ chunks" if world > 1 else "single GPU"),
+                        l2=f"inputs larger than L2: the per-chunk working set (decimated buffer {n_mine * (CHUNK_PAIRS // OVERSAMPLE) * 8 / 1e6:.0f} MB "
+                           f"written by K1, read by K2a/K2, + phase/magnitude planes) exceeds the 126 MB L2 and is rewritten every chunk",
                         k1_impl="scalar" if args.k1_scalar else "pipelined f32x2",
-                        pipeline="two streams: K0/K1 of chunk c+1 beside K2a/K2/K3 of chunk c"),
+                        pipeline="two streams: K0/K1 of chunk c+1 beside K2a/K2/K3 of chunk c; three CUDA graph replays per chunk"),
             channels_at_realtime=value / 2.1,
-            frames_per_step=frames_dev / K,
-            e2e=dict(value=e2e_value, unit="Msamples/s", h2d_bytes_per_step=CPS * CHUNK_BYTES if True else 0,
-                     d2h_bytes_per_step=d_e2e["out_bytes"] / K, ms_per_step=ms_e2e / K, channels_at_realtime=e2e_value / 2.1,
-                     frames_per_step=frames_e2e / K, api="Vdl2Channels.process_buf_uchar (vdl2gpu_submit) + flush"),
-            gpu_launches=int(d_dev["kernel_launches"]),
-            roofline=dict(bound="hbm", kernel="k1_mix_iir_decimate", achieved=achieved, peak=peak, unit="GB/s",
-                          frac=(achieved / peak) if achieved else None, traffic=traffic, peak_source=peak_src,
-                          bytes_per_channel_sample=B_CS, ms_per_launch=k1_ms_per_launch,
-                          note="effective-bandwidth model of SURVEY.md §8d (each channel streams the float IQ buffer); the shared stream is "
-                               "served from shared memory so DRAM traffic is far lower and the kernel is FP32-issue bound",
-                          kernel_share_of_step={k: v[0] / tot_k for k, v in kms.items()},
-                          kernel_ms_per_launch={k: v[0] / max(v[1], 1) for k, v in kms.items()},
-                          measured="CUDA events on the library's stream, kernels serialised (VDL2GPU_FLAG_NO_OVERLAP), same "
-                                   "workload and process; value/e2e are measured with the two-stage stream overlap on",
-                          serial_ms_per_step=ms_serial / max(2, K // 2),
-                          fp32_pipe=dict(
-                              achieved=(len(my_freqs) * CHUNK_PAIRS * 24.0 / (k1_ms_per_launch * 1e-3) / 1e12) if k1_ms_per_launch > 0 else None,
-                              peak=148 * 128 * 1.965e9 / 1e12, unit="T lane-ops/s",
-                              frac=(len(my_freqs) * CHUNK_PAIRS * 24.0 / (k1_ms_per_launch * 1e-3) / (148 * 128 * 1.965e9)) if k1_ms_per_launch > 0 else None,
-                              note="the bound that actually binds K1: 24 individually rounded FP32 operations per channel-sample "
-                                   "(12 packed FMUL2/FFMA2; contraction to FMA is not allowed by the bit-exactness contract) "
-                                   "against 148 SMs x 128 FP32 lanes x 1.965 GHz")),
-            clocks=clocks,
-            parity=dict(pool_overflows=int(d_dev["pool_overflows"] + d_e2e["pool_overflows"]), out_overflows=int(d_dev["out_overflows"] + d_e2e["out_overflows"]),
-                        bursts_per_step=d_dev["bursts"] / K, fcs_good_per_step=d_dev["fcs_good"] / K, fcs_bad_per_step=d_dev["fcs_bad"] / K),
-            wall_ms_per_step=wall_dev / K,
+            frames_per_step=A1["frames"] / K,
+            step_ms=stat(A1["per_step"]), host_us_per_submit=A1["host_us_per_submit"],
+            timed_region_s=A1["ms"] / 1e3,
+            e2e=dict(value=e2e_value, unit="Msamples/s", h2d_bytes_per_step=CPS * CHUNK_BYTES,
+                     d2h_bytes_per_step=B1["d"]["out_bytes"] / K, ms_per_step=B1["ms"] / K, channels_at_realtime=e2e_value / 2.1,
+                     frames_per_step=B1["frames"] / K, step_ms=stat(B1["per_step"]), host_us_per_submit=B1["host_us_per_submit"],
+                     api="Vdl2Channels.process_buf_uchar (vdl2gpu_submit) + poll/flush"),
+            gpu_launches=int(A1["d"]["kernel_launches"]), graph_launches=int(A1["d"]["graph_launches"]),
+            clocks=A1["clocks"],
+            counts=dict(pool_overflows=int(A1["d"]["pool_overflows"] + B1["d"]["pool_overflows"]), out_overflows=int(A1["d"]["out_overflows"] + B1["d"]["out_overflows"]),
+                        bursts_per_step=A1["d"]["bursts"] / K, fcs_good_per_step=A1["d"]["fcs_good"] / K, fcs_bad_per_step=A1["d"]["fcs_bad"] / K),
+            wall_ms_per_step=A1["wall_ms"] / K,
         )
+        if A2 is not None:
+            line["repeat"] = dict(value=rate(A2, K), e2e=rate(B2, K), value_rel_diff=rate(A2, K) / value - 1.0,
+                                  e2e_rel_diff=rate(B2, K) / e2e_value - 1.0, order="A-B-A-B, this is the second pair")
+        if other is not None:
+            line["value_" + other["order"].replace("replica", "replica_adjacent")] = other["value"]
+            line["other_channel_order"] = other
+        if roofline is not None:
+            line["roofline"] = roofline
+        if parity is not None:
+            line["parity"] = parity
         if cpu is not None:
             line["cpu_baseline"] = cpu
         sys.stdout.flush()
@@ -412,9 +635,13 @@ def main():
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
     barrier()
+    if mg is not None:
+        mg.close()
     g.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and parity["mismatches"] != 0:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -92,6 +92,8 @@ def load_library():
     L.vdl2gpu_launch_convert.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.vdl2gpu_launch_fcs_crc16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.vdl2gpu_launch_rs_verify.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.vdl2gpu_launch_phase_mag.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.vdl2gpu_chunks_in_flight.argtypes = [C.c_void_p]
     L.vdl2gpu_stage_device_bytes.restype = C.c_size_t
     L.vdl2gpu_stage_device_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
     L.vdl2gpu_stage_row_stride.restype = C.c_uint32

@@ -10,8 +10,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvdl2gpu.so")
-SOURCES = ["vdl2_kernels.cu", "vdl2_host.cu", "vdl2_dropin.cu"]
-HEADERS = ["vdl2_tables_host.h", "vdl2_core.cuh", "vdl2_kernels.h", "vdl2_types.h", "../../include/vdl2gpu.h", "../../include/vdl2_dropin.h"]
+SOURCES = ["vdl2_kernels.cu", "vdl2_host.cu", "vdl2_dropin.cu", "vdl2_mg.cu"]
+HEADERS = ["vdl2_tables_host.h", "vdl2_core.cuh", "vdl2_fastmath.cuh", "vdl2_kernels.h", "vdl2_types.h", "../../include/vdl2gpu.h", "../../include/vdl2_dropin.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-I", CSRC, "-I", os.path.join(HERE, "..", "include")]
 
@@ -36,7 +36,7 @@ def build_native(force=False, verbose=False):
     if not force and not stale():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + ["-lpthread"]
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + ["-lpthread", "-ldl"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

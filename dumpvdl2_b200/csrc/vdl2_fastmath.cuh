@@ -79,7 +79,7 @@ VDL2_FM_HD float vdl2_phase_fast(float re, float im, const double *tab, int *slo
 	if(!(ax <= 1.0e30f && ay <= 1.0e30f && mx >= 1.0e-30f && (mn >= mx * 1.0e-6f || mn == 0.0f))) { *slow = 1; return 0.0f; }
 	/* break point: k = round(8 * mn/mx) from an approximate quotient (any neighbour would do) */
 #if defined(__CUDA_ARCH__)
-	const float q = __fmul_rn(mn, __frcp_rn(mx));
+	const float q = __fdividef(mn, mx);                      /* MUFU.RCP + FMUL: approximate is enough here */
 	const uint32_t k = __float_as_uint(__fmaf_rn(q, 8.0f, 12582912.0f)) & 15u;
 #else
 	const float q = mn / mx;

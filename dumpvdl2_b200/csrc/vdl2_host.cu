@@ -26,6 +26,10 @@
 
 static thread_local char g_last_error[512] = "";
 
+extern "C" void vdl2gpu_set_last_error(const char *msg) {          /* for the other translation units of the library */
+	snprintf(g_last_error, sizeof(g_last_error), "%s", msg ? msg : "");
+}
+
 static int fail_cuda(cudaError_t e, const char *what, int line) {
 	snprintf(g_last_error, sizeof(g_last_error), "%s failed at vdl2_host.cu:%d: %s", what, line, cudaGetErrorString(e));
 	return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? VDL2GPU_ENODEV : VDL2GPU_ECUDA;
@@ -720,6 +724,13 @@ extern "C" int vdl2gpu_poll(vdl2gpu_ctx *c, vdl2gpu_frame_cb cb, void *user) {
 	return deliver(c, cb, user);
 }
 
+extern "C" int vdl2gpu_chunks_in_flight(vdl2gpu_ctx *c) {
+	if(!c) return VDL2GPU_EINVAL;
+	int n = 0;
+	for(auto &s : c->chunks) n += s.busy ? 1 : 0;
+	return n;
+}
+
 extern "C" int vdl2gpu_flush(vdl2gpu_ctx *c, vdl2gpu_frame_cb cb, void *user) {
 	if(!c) return VDL2GPU_EINVAL;
 	CU(cudaSetDevice(c->device));
@@ -874,6 +885,25 @@ extern "C" int vdl2gpu_launch_rs_verify(uint8_t *blocks, const int32_t *fec_octe
 	int rc = stub_tables(&t);            /* first call on a device allocates; later calls only launch */
 	if(rc) return rc;
 	KL(vdl2_launch_rs(blocks, fec_octets, n_blocks, ret_out, t, (cudaStream_t)stream));
+	return VDL2GPU_OK;
+}
+
+/* K2a on its own: phase_out[i] = (float)atan2((double)im, (double)re), mag_out[i] = hypotf(re, im) of n_elems
+ * decimated samples (src/demod.c:232,238,256).  exact_libm = 0: the Ziv-guarded short evaluation the pipeline
+ * uses (vdl2_fastmath.cuh); 1: the libdevice routine for every element.  Both give the same floats. */
+extern "C" int vdl2gpu_launch_phase_mag(const float *dec, uint32_t n_elems, float *phase_out, float *mag_out, int exact_libm, void *stream) {
+	if(n_elems && (!dec || !phase_out || !mag_out)) return VDL2GPU_EINVAL;
+	if(n_elems == 0) return VDL2GPU_OK;
+	int dev = 0;
+	CU(cudaGetDevice(&dev));
+	KL(vdl2_kernels_init_device(dev));
+	vdl2_k2_params p2;
+	memset(&p2, 0, sizeof(p2));
+	/* one row of n_elems "channels": K2a is element-wise, the row structure does not matter */
+	p2.dec = reinterpret_cast<const float2 *>(dec); p2.n_dec = 1; p2.n_ch = n_elems; p2.n_chp = n_elems;
+	p2.phase = phase_out - (size_t)VDL2_SYNC_BUFLEN * n_elems;       /* the launcher skips the 160 history rows */
+	p2.mag = mag_out; p2.k2a_mode = exact_libm ? 0u : 1u;
+	KL(vdl2_launch_k2a(&p2, (cudaStream_t)stream));
 	return VDL2GPU_OK;
 }
 

@@ -153,12 +153,49 @@ int vdl2gpu_stream_wait(vdl2gpu_ctx *ctx, void *stream);
 /* Deliver the frames of every chunk that has finished, in (chunk, channel, burst, idx) order.  Returns the
  * number of frames delivered or a negative error.  cb may be NULL (frames are dropped, counters kept). */
 int vdl2gpu_poll(vdl2gpu_ctx *ctx, vdl2gpu_frame_cb cb, void *user);
+/* Chunks submitted whose frames have not been harvested yet (0 right after a poll = everything delivered). */
+int vdl2gpu_chunks_in_flight(vdl2gpu_ctx *ctx);
 /* Block until everything submitted so far has been processed, then deliver like poll. */
 int vdl2gpu_flush(vdl2gpu_ctx *ctx, vdl2gpu_frame_cb cb, void *user);
 int vdl2gpu_get_stats(vdl2gpu_ctx *ctx, vdl2gpu_stats *out);
 /* per-channel counters, 9 x uint64 per channel in the order: sync_good, hdr_crc_good, bursts, burst_err,
  * blocks_processed, blocks_fec_ok, msg_good, fcs_good, fcs_bad.  Implies a flush of device work. */
 int vdl2gpu_get_channel_counters(vdl2gpu_ctx *ctx, uint64_t *out, uint32_t n_channels);
+
+/* ---- multi-GPU ingest (one process per GPU; global channel k is demodulated on GPU k mod N, the reference's
+ * channel threads share nothing but the read-only sample buffer: src/dumpvdl2.c:117-135, src/demod.c:50,300-301).
+ * Rank 0 owns the IQ source; vdl2gpu_mg_* fans every step's chunks out into a double-buffered receive area on every
+ * rank and feeds the rank's context from it (vdl2gpu_submit_device), either with ncclBroadcast (libnccl is dlopen()ed)
+ * or, with no kernel at all, with copy-engine peer copies into CUDA-IPC-mapped buffers ordered by stream memory
+ * operations.  The caller carries the small opaque blobs between the processes (MPI, sockets, ...).  Typical sequence:
+ *
+ *     uint8_t id[VDL2GPU_MG_ID_BYTES];              // NCCL mode only
+ *     if(rank == 0) vdl2gpu_mg_unique_id(id, sizeof id);   bcast(id);
+ *     vdl2gpu_mg_create(ctx, rank, world, mode, id, step_bytes, &mg);
+ *     // copy-engine mode only:  vdl2gpu_mg_export(mg, blob, n);  allgather(blob -> all);  vdl2gpu_mg_import(mg, all, world * n);
+ *     half = vdl2gpu_mg_stage(mg, pieces, sizes, n_pieces, host?, step_bytes);          // step 0
+ *     for(;;) {
+ *         next = vdl2gpu_mg_stage(mg, ...);          // step s+1 travels while step s is demodulated
+ *         vdl2gpu_mg_submit(mg, half, chunks_per_step, chunk_bytes);
+ *         vdl2gpu_poll(ctx, frame_cb, user);
+ *         half = next;
+ *     }
+ * ---- */
+enum { VDL2GPU_MG_NCCL = 0, VDL2GPU_MG_COPY_ENGINE = 1 };
+#define VDL2GPU_MG_ID_BYTES 128
+typedef struct vdl2gpu_mg vdl2gpu_mg;
+int vdl2gpu_mg_unique_id(uint8_t *id, size_t cap);      /* rank 0: ncclGetUniqueId */
+int vdl2gpu_mg_create(vdl2gpu_ctx *ctx, int rank, int world, int mode, const uint8_t *nccl_id /* NULL in copy-engine mode */,
+		uint32_t stage_bytes /* bytes of one step, at most */, vdl2gpu_mg **out);
+size_t vdl2gpu_mg_blob_bytes(void);
+int vdl2gpu_mg_export(vdl2gpu_mg *mg, uint8_t *blob, size_t cap);
+int vdl2gpu_mg_import(vdl2gpu_mg *mg, const uint8_t *all_blobs, size_t bytes);
+/* rank 0: the pieces (device pointers, or pinned host pointers with src_is_host) that make up the step, `total` bytes;
+ * other ranks: n_src = 0, same total.  Returns the half (0/1) for vdl2gpu_mg_submit or a negative error.  Asynchronous. */
+int vdl2gpu_mg_stage(vdl2gpu_mg *mg, const void *const *src, const uint32_t *src_bytes, uint32_t n_src, int src_is_host, uint32_t total);
+int vdl2gpu_mg_submit(vdl2gpu_mg *mg, int half, uint32_t n_chunks, uint32_t chunk_bytes);
+int vdl2gpu_mg_mode(vdl2gpu_mg *mg);
+int vdl2gpu_mg_destroy(vdl2gpu_mg *mg);
 
 /* One frame in the reference's raw-frame archive format (2-octet big-endian record length + proto3
  * dumpvdl2.raw_avlc_frame, proto/dumpvdl2.proto:25-48, as written by src/fmtr-binary.c + src/output-file.c:181-189):
@@ -196,6 +233,11 @@ int vdl2gpu_launch_fcs_crc16(const uint8_t *frames, const uint32_t *offsets, con
 /* RS(255,249) errors-and-erasures decode of n blocks in place (src/rs.c:32-49); fec_octets[i] in {0,2,4,6} */
 int vdl2gpu_launch_rs_verify(uint8_t *blocks /* [n][255] */, const int32_t *fec_octets, uint32_t n_blocks,
 		int32_t *ret_out, void *stream);
+
+/* K2a: phase_out[i] = (float)atan2((double)im, (double)re) and mag_out[i] = hypotf(re, im) of n_elems decimated
+ * samples dec[n_elems][2] (src/demod.c:232,238,256).  exact_libm = 0: the short double-precision evaluation with a
+ * Ziv rounding test the pipeline uses; 1: the general libdevice atan2 for every element.  Same floats either way. */
+int vdl2gpu_launch_phase_mag(const float *dec, uint32_t n_elems, float *phase_out, float *mag_out, int exact_libm, void *stream);
 
 /* ---- stage stubs: the three per-channel stages one at a time, on device memory the caller owns.
  * A vdl2gpu_stage is the device-resident state of n_channels vdl2_channel_t's (src/dumpvdl2.h:321-352) plus the

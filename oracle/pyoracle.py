@@ -249,7 +249,7 @@ def ref_binary(flavour="strict"):
     return p if os.path.exists(p) else None
 
 
-def run_ref(path, fmt, oversample, centerfreq, freqs, flavour="strict", chunk=None, loop=1, quiet=False, max_ppm=None):
+def run_ref(path, fmt, oversample, centerfreq, freqs, flavour="strict", chunk=None, loop=1, quiet=False, max_ppm=None, pin=False):
     """Run oracle/_ref/vdl2_ref_<flavour> on an IQ file; returns (frames as dicts, stats dict)."""
     exe = ref_binary(flavour)
     if exe is None:
@@ -262,6 +262,8 @@ def run_ref(path, fmt, oversample, centerfreq, freqs, flavour="strict", chunk=No
         cmd += ["--max-ppm", str(max_ppm)]
     if quiet:
         cmd += ["--quiet"]
+    if pin:
+        cmd += ["--pin"]
     cmd.append(path)
     out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
     frames, stats = [], {}

@@ -15,7 +15,8 @@
  * process_buf_uchar/process_buf_short -> process_samples -> demod -> decode_vdl2_burst.
  *
  * Usage: vdl2_ref --fmt u8|s16 --oversample N --centerfreq HZ --freqs f0,f1,... [--chunk BYTES]
- *                 [--max-ppm X] [--loop N] [--quiet] [--debug MASK] FILE
+ *                 [--max-ppm X] [--loop N] [--quiet] [--pin] [--debug MASK] FILE
+ *        --pin: channel thread i is bound to CPU i mod (online CPUs), the producer to the last CPU (timing runs)
  * Output (stdout): one line per pushed frame, sorted by (channel, push order):
  *   FRAME ch=I freq=F idx=K len=L synd=W datalen=D fec=C pwr=%.9g nf=%.9g ppm=%.9g hex=...
  * and a final  STATS ...  line with wall time of the sample loop.
@@ -27,6 +28,8 @@
 #include <stdint.h>
 #include <time.h>
 #include <pthread.h>
+#include <sched.h>
+#include <unistd.h>
 #include <glib.h>
 #include <libacars/libacars.h>
 #include <libacars/list.h>
@@ -146,7 +149,7 @@ static double now_s(void) {
 int main(int argc, char **argv) {
 	char const *fmt = "u8", *freqs_s = NULL, *file = NULL;
 	uint32_t oversample = 10, centerfreq = 0, chunk = FILE_BUFSIZE;
-	int loops = 1, quiet = 0;
+	int loops = 1, quiet = 0, pin = 0;
 	memset(&Config, 0, sizeof(Config));
 	for(int i = 1; i < argc; i++) {
 		if(!strcmp(argv[i], "--fmt") && i+1 < argc) fmt = argv[++i];
@@ -157,6 +160,7 @@ int main(int argc, char **argv) {
 		else if(!strcmp(argv[i], "--max-ppm") && i+1 < argc) Config.max_ppm = strtof(argv[++i], NULL);
 		else if(!strcmp(argv[i], "--loop") && i+1 < argc) loops = atoi(argv[++i]);
 		else if(!strcmp(argv[i], "--quiet")) quiet = 1;
+		else if(!strcmp(argv[i], "--pin")) pin = 1;
 		else if(!strcmp(argv[i], "--debug") && i+1 < argc) {
 #ifdef DEBUG
 			Config.debug_filter = strtoul(argv[++i], NULL, 0);
@@ -214,6 +218,26 @@ int main(int argc, char **argv) {
 		targs[i].idx = i;
 		targs[i].v = chans[i];
 		pthread_create(&chans[i]->demod_thread, NULL, chan_thread, &targs[i]);
+	}
+	if(pin) {
+		/* the CPUs this process may use, in order; channel i -> the (i mod n-1)-th of them, producer -> the last */
+		cpu_set_t all;
+		CPU_ZERO(&all);
+		sched_getaffinity(0, sizeof(all), &all);
+		int cpus[CPU_SETSIZE], ncpu = 0;
+		for(int c = 0; c < CPU_SETSIZE; c++) if(CPU_ISSET(c, &all)) cpus[ncpu++] = c;
+		if(ncpu > 1) {
+			for(int i = 0; i < num_channels; i++) {
+				cpu_set_t one;
+				CPU_ZERO(&one);
+				CPU_SET(cpus[i % (ncpu - 1)], &one);
+				pthread_setaffinity_np(chans[i]->demod_thread, sizeof(one), &one);
+			}
+			cpu_set_t one;
+			CPU_ZERO(&one);
+			CPU_SET(cpus[ncpu - 1], &one);
+			pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+		}
 	}
 
 	/* feed chunks like process_iq_file (reference src/dumpvdl2.c:353-356); the file is NOT

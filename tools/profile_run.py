@@ -12,9 +12,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--chunks", type=int, default=4)
 ap.add_argument("--channels", type=int, default=16384)
 ap.add_argument("--k1-scalar", action="store_true")
+ap.add_argument("--order", default="interleaved", choices=["interleaved", "replica"])
 a = ap.parse_args()
 chunks, offs, _ = bench.make_stream(1.0)
-freqs = bench.channel_freqs(offs, a.channels)
+freqs = bench.channel_freqs(offs, a.channels, a.order)
 g = vd.Vdl2Channels(bench.FS, bench.OVERSAMPLE, vd.FMT_U8, bench.CENTER, freqs, max_chunk_bytes=bench.CHUNK_BYTES,
                     flags=(vd.FLAG_K1_SCALAR if a.k1_scalar else 0) | vd.FLAG_NO_OVERLAP)
 g.enable_timing(True)
