@@ -86,6 +86,7 @@ def load_library():
     L.vdl2gpu_read_events.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.vdl2gpu_enable_timing.argtypes = [C.c_void_p, C.c_int]
     L.vdl2gpu_get_kernel_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.vdl2gpu_get_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.vdl2gpu_strerror.restype = C.c_char_p
     L.vdl2gpu_strerror.argtypes = [C.c_int]
     L.vdl2gpu_last_error.restype = C.c_char_p
@@ -310,6 +311,12 @@ class Vdl2Channels:
 
     def enable_timing(self, on=True):
         _check(self.L, self.L.vdl2gpu_enable_timing(self.h, 1 if on else 0), "vdl2gpu_enable_timing")
+
+    def timeline(self, cap=4096):
+        """rows of [chunk, front start, K0|K1, K1 end, back start, K2a|K2, K2|K3, K3 end] (ms) for the timed chunks"""
+        a = np.zeros((cap, 8), np.float32)
+        n = _check(self.L, self.L.vdl2gpu_get_timeline(self.h, a.ctypes.data, cap), "vdl2gpu_get_timeline")
+        return a[:n]
 
     def kernel_ms(self):
         ms = (C.c_double * 5)()

@@ -602,6 +602,9 @@ VDL2_HD int vdl2_walk_first(const vdl2_chan &v) {
 	return fast ? (VDL2_SYNC_SKIP - 1) - v.sclk : 0;
 }
 
+/* STAGED: dec / phase / mag point into a shared-memory staging buffer (plain loads) instead of global memory (read-only path) */
+#define VDL2_LD(STAGED, p) ((STAGED) ? *(p) : VDL2_LDG(p))
+template<bool STAGED = false>
 VDL2_HD void vdl2_walk_tail(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env, uint32_t chan_idx, uint64_t idx0,
 		const float2 *dec, const float *phase, const float *mag, size_t stride, int resume) {
 	int t = resume;
@@ -609,21 +612,22 @@ VDL2_HD void vdl2_walk_tail(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env
 		if((v.state & VDL2_ST_LOCKED) && vdl2_dec_state(v) != VDL2_DEC_IDLE) {
 			const int tsym = t + (VDL2_SPS - 1) - v.sclk;                  /* sample on which ++sclk reaches SPS */
 			if(tsym >= VDL2_WALK_BLOCK) { v.sclk += VDL2_WALK_BLOCK - t; break; }
-			const float2 d = VDL2_LDG(dec + (ptrdiff_t)tsym * (ptrdiff_t)stride);
-			const float phi = VDL2_LDG(phase + (ptrdiff_t)tsym * (ptrdiff_t)stride);
+			const float2 d = VDL2_LD(STAGED, dec + (ptrdiff_t)tsym * (ptrdiff_t)stride);
+			const float phi = VDL2_LD(STAGED, phase + (ptrdiff_t)tsym * (ptrdiff_t)stride);
 			v.sclk = 0;
 			vdl2_symbol(v, env, chan_idx, idx0 + (uint64_t)tsym, d.x, d.y, phi);
 			t = tsym + 1;
 		} else {
-			const float2 d = VDL2_LDG(dec + (ptrdiff_t)t * (ptrdiff_t)stride);
-			const float phi = VDL2_LDG(phase + (ptrdiff_t)t * (ptrdiff_t)stride);
-			const float mgt = VDL2_LDG(mag + (ptrdiff_t)t * (ptrdiff_t)stride);
+			const float2 d = VDL2_LD(STAGED, dec + (ptrdiff_t)t * (ptrdiff_t)stride);
+			const float phi = VDL2_LD(STAGED, phase + (ptrdiff_t)t * (ptrdiff_t)stride);
+			const float mgt = VDL2_LD(STAGED, mag + (ptrdiff_t)t * (ptrdiff_t)stride);
 			vdl2_demod_step_pm(v, ring, rs, env, chan_idx, idx0 + (uint64_t)t, d.x, d.y, phi, mgt, false, 0.f, 0.f);
 			t++;
 		}
 	}
 }
 
+template<bool STAGED = false>
 VDL2_HD void vdl2_walk_block_ring(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env &env, uint32_t chan_idx, uint64_t idx0,
 		const float2 *dec, const float *phase, const float *mag, size_t stride, vdl2_walk_pref &pf, bool has_next) {
 	const bool fast = !(v.state & VDL2_ST_LOCKED) && vdl2_dec_state(v) != VDL2_DEC_IDLE && v.sclk >= 0 && v.sclk < VDL2_SYNC_SKIP;
@@ -636,18 +640,18 @@ VDL2_HD void vdl2_walk_block_ring(vdl2_chan &v, float *ring, int rs, const vdl2_
 	for(int j = 0; j < 4; j++) mg[j] = pf.mg[j];
 	if(!have_pw && fast) {
 #pragma unroll
-		for(int t = 0; t < VDL2_WALK_BLOCK; t++) pw[t] = VDL2_LDG(phase + (ptrdiff_t)t * (ptrdiff_t)stride);
+		for(int t = 0; t < VDL2_WALK_BLOCK; t++) pw[t] = VDL2_LD(STAGED, phase + (ptrdiff_t)t * (ptrdiff_t)stride);
 	}
 	if(!have_mg && fast) {
 #pragma unroll
-		for(int j = 0; j < 4; j++) mg[j] = VDL2_LDG(mag + (ptrdiff_t)(first + VDL2_SYNC_SKIP * j) * (ptrdiff_t)stride);
+		for(int j = 0; j < 4; j++) mg[j] = VDL2_LD(STAGED, mag + (ptrdiff_t)(first + VDL2_SYNC_SKIP * j) * (ptrdiff_t)stride);
 	}
 	/* request the next block's inputs now; they arrive while this block is evaluated */
 	if(has_next) {
 #pragma unroll
-		for(int t = 0; t < VDL2_WALK_BLOCK; t++) pf.pw[t] = VDL2_LDG(phase + (ptrdiff_t)(VDL2_WALK_BLOCK + t) * (ptrdiff_t)stride);
+		for(int t = 0; t < VDL2_WALK_BLOCK; t++) pf.pw[t] = VDL2_LD(STAGED, phase + (ptrdiff_t)(VDL2_WALK_BLOCK + t) * (ptrdiff_t)stride);
 #pragma unroll
-		for(int j = 0; j < 4; j++) pf.mg[j] = VDL2_LDG(mag + (ptrdiff_t)(VDL2_WALK_BLOCK + first + VDL2_SYNC_SKIP * j) * (ptrdiff_t)stride);
+		for(int j = 0; j < 4; j++) pf.mg[j] = VDL2_LD(STAGED, mag + (ptrdiff_t)(VDL2_WALK_BLOCK + first + VDL2_SYNC_SKIP * j) * (ptrdiff_t)stride);
 		pf.first = first;
 		pf.valid = 1;
 	} else {
@@ -697,7 +701,7 @@ VDL2_HD void vdl2_walk_block_ring(vdl2_chan &v, float *ring, int rs, const vdl2_
 		}
 		if(go) resume = VDL2_WALK_BLOCK;
 	}
-	vdl2_walk_tail(v, ring, rs, env, chan_idx, idx0, dec, phase, mag, stride, resume);
+	vdl2_walk_tail<STAGED>(v, ring, rs, env, chan_idx, idx0, dec, phase, mag, stride, resume);
 }
 
 /* same, computing phase and magnitude in place (host simulation, unit tests) */

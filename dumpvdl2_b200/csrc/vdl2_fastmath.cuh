@@ -50,6 +50,22 @@
 #define VDL2_PIO2_HI 0x1.921fb54442d18p+0
 #define VDL2_PIO2_LO 0x1.1a62633145c07p-54
 
+/* polynomial and folding constants; on the device they sit in constant memory so that they reach the FP64 pipe as
+ * constant-bank operands instead of being assembled from two 32-bit immediates each */
+#define VDL2_FM_C0 -0x1.745d1745d1746p-4   /* -1/11 */
+#define VDL2_FM_C1 0x1.c71c71c71c71cp-4    /*  1/9  */
+#define VDL2_FM_C2 -0x1.2492492492492p-3   /* -1/7  */
+#define VDL2_FM_C3 0x1.999999999999ap-3    /*  1/5  */
+#define VDL2_FM_C4 -0x1.5555555555555p-2   /* -1/3  */
+#if defined(__CUDACC__)
+__constant__ double c_vdl2_fm[9] = { VDL2_FM_C0, VDL2_FM_C1, VDL2_FM_C2, VDL2_FM_C3, VDL2_FM_C4, VDL2_PIO2_HI, VDL2_PIO2_LO, VDL2_PI_HI, VDL2_PI_LO };
+#endif
+#if defined(__CUDA_ARCH__)
+#define VDL2_FM_K(i, v) c_vdl2_fm[i]
+#else
+#define VDL2_FM_K(i, v) (v)
+#endif
+
 VDL2_FM_HD double vdl2_fm_rcp_seed(double d) {
 #if defined(__CUDA_ARCH__)
 	double r;
@@ -97,14 +113,14 @@ VDL2_FM_HD float vdl2_phase_fast(float re, float im, const double *tab, int *slo
 	double t = num * r;
 	t = vdl2_fm_fma(vdl2_fm_fma(-den, t, num), r, t);       /* one correction: t within an ulp of num/den */
 	const double s = t * t;
-	double p = -0x1.745d1745d1746p-4;                       /* -1/11 */
-	p = vdl2_fm_fma(p, s, 0x1.c71c71c71c71cp-4);            /*  1/9  */
-	p = vdl2_fm_fma(p, s, -0x1.2492492492492p-3);           /* -1/7  */
-	p = vdl2_fm_fma(p, s, 0x1.999999999999ap-3);            /*  1/5  */
-	p = vdl2_fm_fma(p, s, -0x1.5555555555555p-2);           /* -1/3  */
+	double p = VDL2_FM_K(0, VDL2_FM_C0);
+	p = vdl2_fm_fma(p, s, VDL2_FM_K(1, VDL2_FM_C1));
+	p = vdl2_fm_fma(p, s, VDL2_FM_K(2, VDL2_FM_C2));
+	p = vdl2_fm_fma(p, s, VDL2_FM_K(3, VDL2_FM_C3));
+	p = vdl2_fm_fma(p, s, VDL2_FM_K(4, VDL2_FM_C4));
 	double a = A + vdl2_fm_fma(t * s, p, t);
-	if(ay > ax) a = (VDL2_PIO2_HI - a) + VDL2_PIO2_LO;
-	if(re < 0.0f) a = (VDL2_PI_HI - a) + VDL2_PI_LO;
+	if(ay > ax) a = (VDL2_FM_K(5, VDL2_PIO2_HI) - a) + VDL2_FM_K(6, VDL2_PIO2_LO);
+	if(re < 0.0f) a = (VDL2_FM_K(7, VDL2_PI_HI) - a) + VDL2_FM_K(8, VDL2_PI_LO);
 	/* distance of the double from the nearest float rounding boundary: the 29 bits the narrowing drops */
 	uint64_t bits;
 #if defined(__CUDA_ARCH__)

@@ -52,6 +52,7 @@ struct chunk_slot {
 	cudaEvent_t done = nullptr;
 	cudaEvent_t tk[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   /* front: 0,1,2  back: 3,6,4,5 */
 	bool busy = false, timed = false;
+	uint64_t seq = 0;
 	/* per-chunk arguments (pinned host copy, device copy made by the first node of the front graph) and the three
 	 * CUDA graphs of this slot per decimated-sample buffer: front {args copy, K0, K1}, K2a, back {K2, history, K3, finish} */
 	vdl2_chunk_args *h_args = nullptr, *d_args = nullptr;
@@ -77,12 +78,14 @@ struct vdl2gpu_ctx {
 	cudaEvent_t ev_input_ready = nullptr, ev_input_consumed = nullptr;
 	uint32_t n_ch = 0, n_chp = 0, max_pairs = 0, max_dec = 0, n_slots = 0, out_cap = 0, event_cap = 0;
 	uint32_t n_streams = 1, ch_per_stream = 0;          /* independent-streams mode: n_streams > 1, channels [s*C, (s+1)*C) on stream s */
+	bool lane_streams = false;                          /* C == 1: samples kept time-major across streams, one lane per stream in K1 */
+	uint32_t raw_bytes = 0;                             /* size of each slot's raw staging buffers (allocated on the first host submit) */
 	int k1_variant = 2, k2_variant = 2, k2a_mode = 1;   /* A/B knobs (VDL2GPU_K1_VARIANT, VDL2GPU_K2_VARIANT, VDL2GPU_K2A), read at create */
 	bool use_graphs = true;
 	uint64_t overflows_reported = 0;
 	host_tables tab;
 	vdl2_tables *d_tab = nullptr;
-	float4 *d_samples = nullptr;
+	float2 *d_samples = nullptr;
 	float2 *d_dec2[2] = { nullptr, nullptr };
 	float *d_phase = nullptr, *d_mag = nullptr, *d_hist_tmp = nullptr;
 	uint32_t *d_k1 = nullptr, *d_k2 = nullptr, *d_counters = nullptr, *d_ready = nullptr;
@@ -101,6 +104,8 @@ struct vdl2gpu_ctx {
 	double k_ms[5] = { 0, 0, 0, 0, 0 };                 /* K0, K1, K2a, K2 (+history copy), K3 (+finish) */
 	uint64_t k_launches[5] = { 0, 0, 0, 0, 0 };
 	uint32_t graph_nominal = 0;                         /* chunk shape (n_pairs) the graphs are kept for */
+	cudaEvent_t ev_t0 = nullptr;                        /* origin of the timeline (recorded by vdl2gpu_enable_timing) */
+	std::vector<float> timeline;                        /* 8 floats per timed chunk: chunk number, then the 7 stage boundaries in ms since ev_t0 */
 	vdl2gpu_stats stats;
 	std::vector<pending_frame> pending;
 	std::vector<std::vector<uint8_t>> blobs;
@@ -162,6 +167,7 @@ static int free_ctx(vdl2gpu_ctx *c) {
 	if(c->ev_input_ready) cudaEventDestroy(c->ev_input_ready);
 	if(c->ev_input_consumed) cudaEventDestroy(c->ev_input_consumed);
 	if(c->ev_drain) cudaEventDestroy(c->ev_drain);
+	if(c->ev_t0) cudaEventDestroy(c->ev_t0);
 	if(c->ev_k2a_done) cudaEventDestroy(c->ev_k2a_done);
 	for(int i = 0; i < 2; i++) { if(c->ev_k1_done[i]) cudaEventDestroy(c->ev_k1_done[i]); if(c->ev_back_done[i]) cudaEventDestroy(c->ev_back_done[i]); }
 	if(c->s_back && c->s_back != c->stream) cudaStreamDestroy(c->s_back);
@@ -191,9 +197,12 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	c->cfg = *cfg;
 	c->n_streams = cfg->n_streams ? cfg->n_streams : 1u;
 	c->cfg.n_streams = c->n_streams;
-	if(c->n_streams > 1) {
+	c->lane_streams = c->n_streams > 1 && c->n_streams == cfg->n_channels;     /* one stream per channel */
+	if(c->lane_streams) {
+		c->ch_per_stream = 1;
+	} else if(c->n_streams > 1) {
 		if(cfg->n_channels % c->n_streams != 0 || (cfg->n_channels / c->n_streams) % 32u != 0) {
-			snprintf(g_last_error, sizeof(g_last_error), "independent-streams mode needs n_channels = n_streams x C with C a multiple of 32 (got %u x %u streams)",
+			snprintf(g_last_error, sizeof(g_last_error), "independent-streams mode needs n_channels = n_streams x C with C = 1 or a multiple of 32 (got %u channels, %u streams)",
 					cfg->n_channels, c->n_streams);
 			return VDL2GPU_EINVAL;
 		}
@@ -242,7 +251,8 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	CU(cudaEventCreateWithFlags(&c->ev_drain, cudaEventDisableTiming));
 	CU(cudaMalloc(&c->d_tab, sizeof(vdl2_tables)));
 	CU(cudaMemcpy(c->d_tab, &c->tab.t, sizeof(vdl2_tables), cudaMemcpyHostToDevice));
-	CU(cudaMalloc(&c->d_samples, (size_t)c->n_streams * c->max_pairs * sizeof(float4)));
+	if(c->lane_streams) CU(cudaMalloc(&c->d_samples, (size_t)c->max_pairs * c->n_chp * sizeof(float2)));
+	else CU(cudaMalloc(&c->d_samples, (size_t)c->n_streams * c->max_pairs * sizeof(float2)));
 	for(int i = 0; i < 2; i++) {
 		CU(cudaMalloc(&c->d_dec2[i], (size_t)c->max_dec * c->n_chp * sizeof(float2)));
 		CU(cudaMemset(c->d_dec2[i], 0, (size_t)c->max_dec * c->n_chp * sizeof(float2)));
@@ -278,8 +288,8 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 
 	c->chunks.resize(n_inflight);
 	for(auto &s : c->chunks) {
-		CU(cudaHostAlloc((void **)&s.h_raw, (size_t)max_bytes * c->n_streams, cudaHostAllocDefault));
-		CU(cudaMalloc(&s.d_raw, (size_t)max_bytes * c->n_streams));
+		/* h_raw / d_raw (max_chunk_bytes x n_streams each) are allocated by the first vdl2gpu_submit: hosts that only
+		 * use vdl2gpu_submit_device never need them */
 		CU(cudaHostAlloc((void **)&s.h_args, sizeof(vdl2_chunk_args), cudaHostAllocDefault));
 		CU(cudaMalloc(&s.d_args, sizeof(vdl2_chunk_args)));
 		CU(cudaHostAlloc((void **)&s.h_out, sizeof(vdl2_out_header) + c->out_cap, cudaHostAllocMapped));
@@ -389,6 +399,15 @@ static void harvest(vdl2gpu_ctx *c, chunk_slot &s) {
 			float ms = 0.f;
 			if(cudaEventElapsedTime(&ms, s.tk[from[k]], s.tk[to[k]]) == cudaSuccess) { c->k_ms[k] += ms; c->k_launches[k]++; }
 		}
+		if(c->ev_t0 && c->timeline.size() < 8u * 4096u) {
+			static const int order[7] = { 0, 1, 2, 3, 6, 4, 5 };   /* front start, K0|K1, K1 end, back start, K2a|K2, K2|K3, K3 end */
+			c->timeline.push_back((float)s.seq);
+			for(int k = 0; k < 7; k++) {
+				float ms = -1.f;
+				if(cudaEventElapsedTime(&ms, c->ev_t0, s.tk[order[k]]) != cudaSuccess) { cudaGetLastError(); ms = -1.f; }
+				c->timeline.push_back(ms);
+			}
+		}
 		s.timed = false;
 	}
 	/* one copy out of the mapped region (header + the bytes K3 used), so the region can be handed back to the device at once */
@@ -427,6 +446,14 @@ static int deliver(vdl2gpu_ctx *c, vdl2gpu_frame_cb cb, void *user) {
 /* ------------------------------------------------------------------------------------------------
  * data path
  * ---------------------------------------------------------------------------------------------- */
+static int ensure_raw(vdl2gpu_ctx *c, chunk_slot &s) {
+	if(s.h_raw) return VDL2GPU_OK;
+	const size_t bytes = (size_t)c->cfg.max_chunk_bytes * c->n_streams;
+	CU(cudaHostAlloc((void **)&s.h_raw, bytes, cudaHostAllocDefault));
+	CU(cudaMalloc(&s.d_raw, bytes));
+	return VDL2GPU_OK;
+}
+
 static int acquire_slot(vdl2gpu_ctx *c, chunk_slot **out) {
 	chunk_slot &s = c->chunks[c->next_slot];
 	if(s.busy) {
@@ -450,7 +477,7 @@ static void fill_params(vdl2gpu_ctx *c, chunk_slot &s, int db, uint32_t n_pairs,
 	p1.lut = reinterpret_cast<const float4 *>(c->d_tab->lut);
 	p1.a0 = c->tab.t.A[0]; p1.a1 = c->tab.t.A[1]; p1.a2 = c->tab.t.A[2]; p1.b1 = c->tab.t.B[1]; p1.b2 = c->tab.t.B[2];
 	p1.one = 1.0f; p1.neg_one = -1.0f; p1.two = 2.0f;
-	p1.ch_per_stream = c->ch_per_stream; p1.stream_stride = c->max_pairs; p1.ca = ca;
+	p1.ch_per_stream = c->ch_per_stream; p1.stream_stride = c->lane_streams ? c->n_chp : c->max_pairs; p1.ca = ca;
 	p2.dec = d_dec; p2.phase = c->d_phase; p2.mag = c->d_mag; p2.hist_tmp = c->d_hist_tmp; p2.n_dec = n_dec; p2.n_ch = c->n_ch; p2.n_chp = c->n_chp; p2.dec_base = dec_base;
 	p2.state = c->d_k2; p2.ring = c->d_ring; p2.tables = c->d_tab; p2.max_ppm = c->cfg.max_ppm; p2.s27 = c->tab.s27;
 	p2.pool = c->d_pool; p2.free_list = c->d_free; p2.ready = c->d_ready; p2.ctl = c->d_ctl;
@@ -488,7 +515,9 @@ static int body_front(void *a) {
 	fill_params(c, *e->s, e->db, e->n_pairs, 0, (os - 1 + e->n_pairs) / os, 0, e->s->d_args, p1, p2, p3);
 	CU(cudaMemcpyAsync(e->s->d_args, e->s->h_args, sizeof(vdl2_chunk_args), cudaMemcpyHostToDevice, c->stream));
 	const uint32_t bpp = c->cfg.sample_fmt == VDL2GPU_FMT_S16_LE ? 4u : 2u;
-	KL(vdl2_launch_k0(nullptr, e->n_pairs, e->k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->n_streams,
+	if(c->lane_streams) KL(vdl2_launch_k0_lanes(nullptr, e->n_pairs, e->k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->n_streams,
+			e->n_pairs * bpp, c->n_chp, e->s->d_args, c->stream));
+	else KL(vdl2_launch_k0(nullptr, e->n_pairs, e->k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->n_streams,
 			e->n_pairs * bpp, c->max_pairs, e->s->d_args, c->stream));
 	KL(vdl2_launch_k1(&p1, (c->cfg.flags & VDL2GPU_FLAG_K1_SCALAR) ? 1 : 0, c->k1_variant, c->stream));
 	return 0;
@@ -540,7 +569,8 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	const int db = (int)(c->chunk_seq & 1u);                 /* decimated-sample buffer of this chunk */
 	const uint32_t bpp = c->cfg.sample_fmt == VDL2GPU_FMT_S16_LE ? 4u : 2u;
 	/* graph replay needs the history copy to be the single-kernel form for every chunk of this shape (n_dec >= 160) */
-	bool graph = c->use_graphs && !s.timed && !planar && c->s_back != c->stream && n_pairs / os >= VDL2_SYNC_BUFLEN;
+	s.seq = c->chunk_seq;
+	bool graph = c->use_graphs && !planar && c->s_back != c->stream && n_pairs / os >= VDL2_SYNC_BUFLEN;
 	if(graph && c->graph_nominal == 0) c->graph_nominal = n_pairs;
 	graph = graph && n_pairs == c->graph_nominal;            /* odd-sized chunks (the tail of a file) take the direct path */
 	if(graph && ensure_graphs(c, s, db, n_pairs, k0_fmt) != VDL2GPU_OK) { c->use_graphs = false; graph = false; }
@@ -554,18 +584,26 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	if(graph) {
 		s.h_args->raw = d_raw; s.h_args->dec_base = s.dec_base; s.h_args->n_pairs = n_pairs; s.h_args->cnt0 = c->decim_cnt;
 		s.h_args->n_dec = s.n_dec; s.h_args->pad = 0;
+		/* timed chunks: stage boundaries only (K0 counts into K1, K3 into K2) */
+		if(s.timed) { CU(cudaEventRecord(s.tk[0], c->stream)); CU(cudaEventRecord(s.tk[1], c->stream)); }
 		CU(cudaGraphLaunch(s.g_front[db], c->stream));
+		if(s.timed) CU(cudaEventRecord(s.tk[2], c->stream));
 		CU(cudaEventRecord(c->ev_input_consumed, c->stream));
 		CU(cudaEventRecord(c->ev_k1_done[db], c->stream));
 		CU(cudaStreamWaitEvent(c->s_back, c->ev_k1_done[db], 0));
+		if(s.timed) CU(cudaEventRecord(s.tk[3], c->s_back));
 		CU(cudaGraphLaunch(s.g_k2a[db], c->s_back));
 		CU(cudaEventRecord(c->ev_k2a_done, c->s_back));
+		if(s.timed) CU(cudaEventRecord(s.tk[6], c->s_back));
 		CU(cudaGraphLaunch(s.g_back[db], c->s_back));
 		CU(cudaEventRecord(c->ev_back_done[db], c->s_back));
+		if(s.timed) { CU(cudaEventRecord(s.tk[4], c->s_back)); CU(cudaEventRecord(s.tk[5], c->s_back)); }
 		c->stats.graph_launches += 3;
 	} else {
 		if(s.timed) CU(cudaEventRecord(s.tk[0], c->stream));
-		KL(vdl2_launch_k0(d_raw, n_pairs, k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->n_streams,
+		if(c->lane_streams) KL(vdl2_launch_k0_lanes(d_raw, n_pairs, k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->n_streams,
+				n_pairs * bpp, c->n_chp, nullptr, c->stream));
+		else KL(vdl2_launch_k0(d_raw, n_pairs, k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->n_streams,
 				n_pairs * bpp, c->max_pairs, nullptr, c->stream));
 		CU(cudaEventRecord(c->ev_input_consumed, c->stream));
 		if(s.timed) CU(cudaEventRecord(s.tk[1], c->stream));
@@ -612,6 +650,8 @@ extern "C" int vdl2gpu_submit(vdl2gpu_ctx *c, const void *iq, uint32_t len) {
 	chunk_slot *s;
 	int rc = acquire_slot(c, &s);
 	if(rc) return rc;
+	rc = ensure_raw(c, *s);
+	if(rc) return rc;
 	/* n_streams buffers of `len` bytes back to back; a ragged tail (len not a multiple of the sample size) is dropped
 	 * per stream, so the streams are repacked at n_pairs * bpp */
 	const size_t used = (size_t)n_pairs * bpp;
@@ -629,6 +669,8 @@ extern "C" int vdl2gpu_submit_planar_s16(vdl2gpu_ctx *c, const int16_t *xi, cons
 	CU(cudaSetDevice(c->device));
 	chunk_slot *s;
 	int rc = acquire_slot(c, &s);
+	if(rc) return rc;
+	rc = ensure_raw(c, *s);
 	if(rc) return rc;
 	memcpy(s->h_raw, xi, (size_t)n_pairs * 2);
 	memcpy(s->h_raw + (size_t)n_pairs * 2, xq, (size_t)n_pairs * 2);
@@ -829,7 +871,19 @@ extern "C" int vdl2gpu_read_events(vdl2gpu_ctx *c, vdl2gpu_event *out, uint32_t 
 extern "C" int vdl2gpu_enable_timing(vdl2gpu_ctx *c, int on) {
 	if(!c) return VDL2GPU_EINVAL;
 	c->timing = on != 0;
+	if(on && !c->ev_t0) {
+		CU(cudaSetDevice(c->device));
+		CU(cudaEventCreate(&c->ev_t0));
+		CU(cudaEventRecord(c->ev_t0, c->stream));
+	}
 	return VDL2GPU_OK;
+}
+
+extern "C" int vdl2gpu_get_timeline(vdl2gpu_ctx *c, float *out, uint32_t cap_rows) {
+	if(!c || !out) return VDL2GPU_EINVAL;
+	const uint32_t n = std::min<uint32_t>(cap_rows, (uint32_t)(c->timeline.size() / 8));
+	memcpy(out, c->timeline.data(), (size_t)n * 8 * sizeof(float));
+	return (int)n;
 }
 
 extern "C" int vdl2gpu_get_kernel_ms(vdl2gpu_ctx *c, double ms[5], uint64_t launches[5]) {
@@ -866,9 +920,9 @@ static int stub_tables(vdl2_tables **out) {
 }
 
 extern "C" int vdl2gpu_launch_convert(const void *raw, uint32_t n_pairs, uint32_t sample_fmt, const float *levels256,
-		float *samples4_out, void *stream) {
-	if(!raw || !samples4_out || sample_fmt > 1 || (sample_fmt == 0 && !levels256)) return VDL2GPU_EINVAL;
-	KL(vdl2_launch_k0(raw, n_pairs, sample_fmt, levels256, samples4_out, 1, 0, 0, nullptr, (cudaStream_t)stream));
+		float *samples_out, void *stream) {
+	if(!raw || !samples_out || sample_fmt > 1 || (sample_fmt == 0 && !levels256)) return VDL2GPU_EINVAL;
+	KL(vdl2_launch_k0(raw, n_pairs, sample_fmt, levels256, samples_out, 1, 0, 0, nullptr, (cudaStream_t)stream));
 	return VDL2GPU_OK;
 }
 
@@ -1037,15 +1091,15 @@ extern "C" int vdl2gpu_stage_levels(vdl2gpu_stage *st, const float **levels256_d
 }
 
 /* K1 == the per-sample loop of process_samples (src/demod.c:288-337) for every channel of the stage */
-extern "C" int vdl2gpu_launch_mix_iir_decimate(vdl2gpu_stage *st, const float *samples4, uint32_t n_pairs, float *dec_out,
+extern "C" int vdl2gpu_launch_mix_iir_decimate(vdl2gpu_stage *st, const float *samples, uint32_t n_pairs, float *dec_out,
 		uint32_t *n_dec_out, void *stream) {
-	if(!st || (n_pairs && (!samples4 || !dec_out))) return VDL2GPU_EINVAL;
+	if(!st || (n_pairs && (!samples || !dec_out))) return VDL2GPU_EINVAL;
 	const uint32_t os = st->cfg.oversample;
 	const uint32_t n_dec = (st->decim_cnt + n_pairs) / os;
 	if(n_dec > st->max_dec) return VDL2GPU_ETOOBIG;
 	vdl2_k1_params p1;
 	memset(&p1, 0, sizeof(p1));
-	p1.samples = reinterpret_cast<const float4 *>(samples4); p1.n_pairs = n_pairs; p1.oversample = os; p1.cnt0 = st->decim_cnt;
+	p1.samples = reinterpret_cast<const float2 *>(samples); p1.n_pairs = n_pairs; p1.oversample = os; p1.cnt0 = st->decim_cnt;
 	p1.n_ch = st->n_ch; p1.n_chp = st->n_chp; p1.dec = reinterpret_cast<float2 *>(dec_out); p1.state = st->d_k1;
 	p1.lut = reinterpret_cast<const float4 *>(st->d_tab->lut);
 	p1.a0 = st->tab.t.A[0]; p1.a1 = st->tab.t.A[1]; p1.a2 = st->tab.t.A[2]; p1.b1 = st->tab.t.B[1]; p1.b2 = st->tab.t.B[2];

@@ -22,16 +22,14 @@
 #include "vdl2_kernels.h"
 
 /* ------------------------------------------------------------------------------------------------
- * K0: sample conversion.  Output layout float4 {re, im, im, re} per complex sample: the packed K1
- * consumes (re,im) and (im,re) as two f32x2 operands, so the swap is paid once per sample here
- * instead of once per channel-sample there.
+ * K0: sample conversion.  Output: float2 {re, im} per complex sample (src/demod.c:339-365).
  * ---------------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(256) k0_convert(const uint8_t *__restrict__ raw0, uint32_t n_pairs_p, uint32_t fmt,
-		const float *__restrict__ levels, float4 *__restrict__ out0, uint32_t raw_stride, uint32_t out_stride,
+		const float *__restrict__ levels, float2 *__restrict__ out0, uint32_t raw_stride, uint32_t out_stride,
 		const vdl2_chunk_args *__restrict__ ca) {
 	const uint32_t n_pairs = ca ? ca->n_pairs : n_pairs_p;
 	const uint8_t *raw = (ca ? static_cast<const uint8_t *>(ca->raw) : raw0) + (size_t)blockIdx.y * raw_stride;   /* stream blockIdx.y */
-	float4 *out = out0 + (size_t)blockIdx.y * out_stride;
+	float2 *out = out0 + (size_t)blockIdx.y * out_stride;
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= n_pairs) return;
 	float re, im;
@@ -51,7 +49,35 @@ __global__ void __launch_bounds__(256) k0_convert(const uint8_t *__restrict__ ra
 		re = __fdiv_rn((float)pl[i], 32768.0f);
 		im = __fdiv_rn((float)pl[n_pairs + i], 32768.0f);
 	}
-	out[i] = make_float4(re, im, im, re);
+	out[i] = make_float2(re, im);
+}
+
+/* K0 for the one-stream-per-channel layout: raw[s][i] -> out[i][s] float2 {re, im}, i.e. TIME-major across streams, so
+ * that the 32 lanes of a K1 warp (32 different streams) read 256 contiguous bytes per sample.  32x32 tile through
+ * shared memory: reads run along the samples of a stream, writes along the streams of a sample. */
+__global__ void __launch_bounds__(1024) k0_convert_lanes(const uint8_t *__restrict__ raw0, uint32_t n_pairs_p, uint32_t fmt,
+		const float *__restrict__ levels, float2 *__restrict__ out, uint32_t n_streams, uint32_t raw_stride, uint32_t out_stride,
+		const vdl2_chunk_args *__restrict__ ca) {
+	__shared__ float2 tile[32][33];
+	const uint32_t n_pairs = ca ? ca->n_pairs : n_pairs_p;
+	const uint8_t *raw = ca ? static_cast<const uint8_t *>(ca->raw) : raw0;
+	const uint32_t tx = threadIdx.x, ty = threadIdx.y;
+	const uint32_t s_in = blockIdx.y * 32u + ty, i_in = blockIdx.x * 32u + tx;
+	float re = 0.f, im = 0.f;
+	if(s_in < n_streams && i_in < n_pairs) {
+		const uint8_t *r = raw + (size_t)s_in * raw_stride;
+		if(fmt == 0) {
+			uchar2 v = reinterpret_cast<const uchar2 *>(r)[i_in];
+			re = __ldg(&levels[v.x]); im = __ldg(&levels[v.y]);
+		} else {
+			short2 v = reinterpret_cast<const short2 *>(r)[i_in];
+			re = __fdiv_rn((float)v.x, 32768.0f); im = __fdiv_rn((float)v.y, 32768.0f);
+		}
+	}
+	tile[ty][tx] = make_float2(re, im);
+	__syncthreads();
+	const uint32_t i_out = blockIdx.x * 32u + ty, s_out = blockIdx.y * 32u + tx;
+	if(i_out < n_pairs && s_out < out_stride) out[(size_t)i_out * out_stride + s_out] = tile[tx][ty];
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -82,9 +108,9 @@ __device__ __forceinline__ void k1_store_state(const vdl2_k1_params &p, uint32_t
 	st[K1_PHI * s + ch] = phi & 0xFFFFFFu;
 }
 
-/* independent-streams mode: the block's 32 channels all belong to stream (first channel / ch_per_stream); a block
- * never straddles two streams because ch_per_stream is a multiple of the block size (checked by vdl2gpu_create) */
-__device__ __forceinline__ const float4 *k1_stream_of(const vdl2_k1_params &p, uint32_t first_ch) {
+/* independent-streams mode: all channels of a block belong to stream (first channel / ch_per_stream); a block never
+ * straddles two streams because ch_per_stream is a multiple of the block size (checked by the launcher) */
+__device__ __forceinline__ const float2 *k1_stream_of(const vdl2_k1_params &p, uint32_t first_ch) {
 	return p.ch_per_stream ? p.samples + (size_t)(first_ch / p.ch_per_stream) * p.stream_stride : p.samples;
 }
 
@@ -96,7 +122,7 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_scalar(vdl2_k1_para
 	const uint32_t ch = blockIdx.x * BLOCK + tid;
 	const bool active = ch < p.n_ch;
 	const uint32_t n_pairs = p.ca ? p.ca->n_pairs : p.n_pairs, cnt0 = p.ca ? p.ca->cnt0 : p.cnt0;
-	const float4 *samples = k1_stream_of(p, blockIdx.x * BLOCK);
+	const float2 *samples = k1_stream_of(p, blockIdx.x * BLOCK);
 	for(uint32_t i = tid; i < 257; i += BLOCK) s_lut[i] = p.lut[i];
 	float xr1 = 0, xr2 = 0, xi1 = 0, xi2 = 0, yr1 = 0, yr2 = 0, yi1 = 0, yi2 = 0;
 	uint32_t phi = 0, dphi = 0;
@@ -106,7 +132,7 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_scalar(vdl2_k1_para
 	for(uint32_t base = 0; base < n_pairs; base += K1_TILE) {
 		const uint32_t n = min((uint32_t)K1_TILE, n_pairs - base);
 		__syncthreads();
-		for(uint32_t i = tid; i < n; i += BLOCK) { float4 v = samples[base + i]; s_tile[i] = make_float2(v.x, v.y); }
+		for(uint32_t i = tid; i < n; i += BLOCK) s_tile[i] = samples[base + i];
 		__syncthreads();
 		if(!active) continue;
 		for(uint32_t k = 0; k < n; k++) {
@@ -156,37 +182,28 @@ __device__ __forceinline__ u64 f2_pack(float lo, float hi) { u64 r; asm("mov.b64
 __device__ __forceinline__ float f2_lo(u64 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
 __device__ __forceinline__ float f2_hi(u64 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
 #pragma nv_diag_default 550
+__device__ __forceinline__ float f1_fma(float a, float b, float c) { float r; asm("fma.rn.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 
-struct k1_packed_consts { u64 ONE, SGN, A0, A1, A2, B1, B2, TWO; };
+struct k1_packed_consts { u64 ONE, SGN, A0, A1, A2, B1, B2, TWO; float one, neg_one; };
 
-/* one input sample: s = {re, im, im, re}; returns the filtered (I,Q) pair */
-__device__ __forceinline__ u64 k1_packed_step(const float4 s, const float4 *s_lut, uint32_t &phi, const uint32_t dphi,
+/* mixer, src/demod.c:200-203: with P = (re, im) * cos and Q = (re, im) * sin (two packed products by a broadcast scalar)
+ *   x0 = (P.re - Q.im, P.im + Q.re) = (re*cos - im*sin, im*cos + re*sin),
+ * each product and each sum rounded once, as in the reference; the two sums are scalar fma(q, -+1, p) so that the
+ * sample never needs a swapped copy. */
+__device__ __forceinline__ u64 k1_mix(const float2 s, const u64 CS, const k1_packed_consts &c) {
+	const float cs = f2_lo(CS), sn = f2_hi(CS);
+	const u64 S2 = f2_pack(s.x, s.y);
+	const u64 P = f2_mul(S2, f2_pack(cs, cs)), Q = f2_mul(S2, f2_pack(sn, sn));
+	return f2_pack(f1_fma(f2_hi(Q), c.neg_one, f2_lo(P)), f1_fma(f2_lo(Q), c.one, f2_hi(P)));
+}
+
+/* one input sample through NCO, mixer and filter; returns the filtered (I,Q) pair */
+__device__ __forceinline__ u64 k1_packed_step(const float2 s, const float4 e, uint32_t &phi, const uint32_t dphi,
 		u64 &x1, u64 &x2, u64 &y1, u64 &y2, const k1_packed_consts &c) {
-	const float4 e = s_lut[(phi >> 16) & 0xFFu];
 	const float fr = (float)(phi & 0xFFFFu);
 	phi += dphi;
 	const u64 CS = f2_fma(f2_mul(f2_pack(e.z, e.w), f2_pack(fr, fr)), c.ONE, f2_pack(e.x, e.y));   /* (cos, sin) */
-	const float cs = f2_lo(CS), sn = f2_hi(CS);
-	const u64 P = f2_mul(f2_pack(s.x, s.y), f2_pack(cs, cs));      /* (re*c, im*c) */
-	const u64 Q = f2_mul(f2_pack(s.z, s.w), f2_pack(sn, sn));      /* (im*s, re*s) */
-	const u64 x0 = f2_fma(Q, c.SGN, P);                            /* (re*c - im*s, im*c + re*s) */
-	const u64 t = f2_fma(f2_mul(c.A1, x1), c.ONE, f2_mul(c.A2, x2));
-	const u64 r = f2_fma(f2_mul(c.A0, x0), c.ONE, t);
-	const u64 u = f2_fma(f2_mul(c.B1, y1), c.ONE, f2_mul(c.B2, y2));
-	const u64 y0 = f2_fma(r, c.ONE, u);
-	x2 = x1; x1 = x0; y2 = y1; y1 = y0;
-	return y0;
-}
-
-/* the same step with the table entry, the phase fraction and the sample already in registers (the batched
- * body loads a whole batch first so that no shared-memory latency sits inside the arithmetic) */
-__device__ __forceinline__ u64 k1_packed_math(const float4 s, const float4 e, const float fr,
-		u64 &x1, u64 &x2, u64 &y1, u64 &y2, const k1_packed_consts &c) {
-	const u64 CS = f2_fma(f2_mul(f2_pack(e.z, e.w), f2_pack(fr, fr)), c.ONE, f2_pack(e.x, e.y));
-	const float cs = f2_lo(CS), sn = f2_hi(CS);
-	const u64 P = f2_mul(f2_pack(s.x, s.y), f2_pack(cs, cs));
-	const u64 Q = f2_mul(f2_pack(s.z, s.w), f2_pack(sn, sn));
-	const u64 x0 = f2_fma(Q, c.SGN, P);
+	const u64 x0 = k1_mix(s, CS, c);
 	const u64 t = f2_fma(f2_mul(c.A1, x1), c.ONE, f2_mul(c.A2, x2));
 	const u64 r = f2_fma(f2_mul(c.A0, x0), c.ONE, t);
 	const u64 u = f2_fma(f2_mul(c.B1, y1), c.ONE, f2_mul(c.B2, y2));
@@ -196,7 +213,7 @@ __device__ __forceinline__ u64 k1_packed_math(const float4 s, const float4 e, co
 }
 
 /* TMA (bulk asynchronous copy) staging of the sample stream: one elected lane asks the copy engine for the next
- * tile (cp.async.bulk global -> shared, completion counted in bytes on an mbarrier) while the warp works on the
+ * tile (cp.async.bulk global -> shared, completion counted in bytes on an mbarrier) while the block works on the
  * current one; two tiles in flight hide the L2 round trip completely.  SASS: UBLKCP + SYNCS. */
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -213,20 +230,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 			:: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-#define K1P_TILE_GROUPS(OS) (640 / (OS))        /* 640 samples = 10 KB of float4 per tile: leaves room for K2's blocks on the same SM */
+#define K1P_TILE_GROUPS(OS) (640 / (OS))        /* 640 samples = 5 KB of float2 per tile */
 
+/* BLOCK = 128: the four warps of an SM's four sub-partitions share one block, i.e. one copy of the sample tiles and of
+ * the NCO table.  The table is then kept EIGHT times (33 KB), copy c holding entry i at float4 index 8 i + c, and lane l
+ * reads copy l mod 8: the eight lanes of a quarter-warp always hit eight different 16-byte bank groups, so the look-up
+ * is conflict-free whatever the 32 phases are (4 wavefronts per LDS.128, the minimum for 512 bytes).  With a single
+ * copy, 32 unrelated phases cost ~10 wavefronts per look-up and the four warps of an SM saturate its shared-memory
+ * pipe (measured: 6.6 ms instead of 5.1 ms per launch once the channels of a warp sit on different frequencies).
+ * BLOCK = 32 keeps one warp per block and a single table copy; the launcher uses it when a 128-channel block would
+ * straddle two streams in independent-streams mode. */
 template<int OS, int BLOCK, int BATCH, bool SYM>
 __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_params p) {
 	constexpr int TG = K1P_TILE_GROUPS(OS);
-	__shared__ float4 s_lut[257];
-	__shared__ __align__(128) float4 s_tiles[2][TG * OS];
+	constexpr int NLUT = BLOCK >= 128 ? 8 : 1;                    /* table copies */
+	__shared__ float4 s_lut[257 * NLUT];
+	__shared__ __align__(128) float2 s_tiles[2][TG * OS];
 	__shared__ __align__(8) uint64_t s_bar[2];
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ch = blockIdx.x * BLOCK + tid;
 	const bool active = ch < p.n_ch;
 	const uint32_t n_pairs = p.ca ? p.ca->n_pairs : p.n_pairs, cnt0 = p.ca ? p.ca->cnt0 : p.cnt0;
-	const float4 *samples = k1_stream_of(p, blockIdx.x * BLOCK);
-	for(uint32_t i = tid; i < 257; i += BLOCK) s_lut[i] = p.lut[i];
+	const float2 *samples = k1_stream_of(p, blockIdx.x * BLOCK);
+	for(uint32_t i = tid; i < 257 * NLUT; i += BLOCK) s_lut[i] = p.lut[i / NLUT];
+	const float4 *lut = s_lut + (NLUT > 1 ? (tid & (NLUT - 1)) : 0);       /* this lane's copy; entry i at lut[i * NLUT] */
 	if(tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
 	float xr1 = 0, xr2 = 0, xi1 = 0, xi2 = 0, yr1 = 0, yr2 = 0, yi1 = 0, yi2 = 0;
 	uint32_t phi = 0, dphi = 0;
@@ -236,6 +263,7 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	c.ONE = f2_pack(p.one, p.one); c.SGN = f2_pack(p.neg_one, p.one);
 	c.A0 = f2_pack(p.a0, p.a0); c.A1 = f2_pack(p.a1, p.a1); c.A2 = f2_pack(p.a2, p.a2);
 	c.B1 = f2_pack(p.b1, p.b1); c.B2 = f2_pack(p.b2, p.b2); c.TWO = f2_pack(p.two, p.two);
+	c.one = p.one; c.neg_one = p.neg_one;
 	/* SYM: the feed-forward taps of this filter design are {A0, 2*A0, A0} (checked on the host).  A1*x[n-1] and
 	 * A2*x[n-2] are then exactly 2*(A0*x[n-1]) and A0*x[n-2], products the previous two steps already formed
 	 * (doubling is exact; no operand can be subnormal here), so two multiplies per sample go away:
@@ -248,7 +276,7 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	const uint32_t head = min(n_pairs, (OS - cnt0 % OS) % OS);
 	if(active) {
 		for(; pos < head; pos++) {
-			u64 y0 = k1_packed_step(samples[pos], s_lut, phi, dphi, x1, x2, y1, y2, c);
+			u64 y0 = k1_packed_step(samples[pos], lut[((phi >> 16) & 0xFFu) * NLUT], phi, dphi, x1, x2, y1, y2, c);
 			if(++cnt == OS) { cnt = 0; p.dec[(size_t)m * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0)); m++; }
 		}
 	}
@@ -264,26 +292,27 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	if(tid == 0) {
 		for(uint32_t t = 0; t < 2 && t < n_tiles; t++) {
 			const uint32_t ngt = min((uint32_t)TG, n_groups - t * TG);
-			tma_load_tile(s_tiles[t], samples + pos + (size_t)t * TG * OS, ngt * OS * (uint32_t)sizeof(float4), &s_bar[t]);
+			tma_load_tile(s_tiles[t], samples + pos + (size_t)t * TG * OS, ngt * OS * (uint32_t)sizeof(float2), &s_bar[t]);
 		}
 	}
 	for(uint32_t g0 = 0, tile = 0; g0 < n_groups; g0 += TG, tile++) {
 		const uint32_t ng = min((uint32_t)TG, n_groups - g0);
-		const float4 *s_tile = s_tiles[tile & 1u];
+		const float2 *s_tile = s_tiles[tile & 1u];
 		mbar_wait(&s_bar[tile & 1u], (tile >> 1) & 1u);
 		if(active) {
 			for(uint32_t g = 0; g < ng; g++) {
-				const float4 *sp = &s_tile[g * OS];
+				const float2 *sp = &s_tile[g * OS];
 				u64 y0 = 0;
 				if(BATCH == 0) {
 #pragma unroll
 					for(int k = 0; k < OS; k++)
-						y0 = k1_packed_step(sp[k], s_lut, phi, dphi, x1, x2, y1, y2, c);
+						y0 = k1_packed_step(sp[k], lut[((phi >> 16) & 0xFFu) * NLUT], phi, dphi, x1, x2, y1, y2, c);
 				} else {
 					/* software pipeline written out over the unrolled group: loads run LA samples ahead of the
 					 * mixer, the mixer MA samples ahead of the filter recurrence */
 					constexpr int LA = BATCH, MA = BATCH / 2;
-					float4 S[OS], E[OS];
+					float2 S[OS];
+					float4 E[OS];
 					float FR[OS];
 					u64 X0[OS];
 #pragma unroll
@@ -291,16 +320,13 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 						const int kl = k + LA, km = k + MA;
 						if(kl < OS) {
 							const uint32_t ph = phi + (uint32_t)kl * dphi;
-							E[kl] = s_lut[(ph >> 16) & 0xFFu];
+							E[kl] = lut[((ph >> 16) & 0xFFu) * NLUT];
 							FR[kl] = (float)(ph & 0xFFFFu);
 							S[kl] = sp[kl];
 						}
 						if(km >= 0 && km < OS) {
 							const u64 CS = f2_fma(f2_mul(f2_pack(E[km].z, E[km].w), f2_pack(FR[km], FR[km])), c.ONE, f2_pack(E[km].x, E[km].y));
-							const float cs = f2_lo(CS), sn = f2_hi(CS);
-							const u64 P = f2_mul(f2_pack(S[km].x, S[km].y), f2_pack(cs, cs));
-							const u64 Q = f2_mul(f2_pack(S[km].z, S[km].w), f2_pack(sn, sn));
-							X0[km] = f2_fma(Q, c.SGN, P);
+							X0[km] = k1_mix(S[km], CS, c);
 						}
 						if(k >= 0) {
 							const u64 x0 = X0[k];
@@ -325,16 +351,146 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 		}
 		m += ng;
 		pos += ng * OS;
-		__syncthreads();                                           /* every lane is done with this buffer */
+		__syncthreads();                                           /* every warp is done with this buffer */
 		if(tid == 0 && tile + 2 < n_tiles) {
 			const uint32_t ngn = min((uint32_t)TG, n_groups - (tile + 2) * TG);
-			tma_load_tile(s_tiles[tile & 1u], samples + pos + (size_t)TG * OS, ngn * OS * (uint32_t)sizeof(float4), &s_bar[tile & 1u]);
+			tma_load_tile(s_tiles[tile & 1u], samples + pos + (size_t)TG * OS, ngn * OS * (uint32_t)sizeof(float2), &s_bar[tile & 1u]);
 		}
 	}
 	/* tail: fewer than OS samples left */
 	if(active) {
 		for(; pos < n_pairs; pos++) {
-			u64 y0 = k1_packed_step(samples[pos], s_lut, phi, dphi, x1, x2, y1, y2, c);
+			u64 y0 = k1_packed_step(samples[pos], lut[((phi >> 16) & 0xFFu) * NLUT], phi, dphi, x1, x2, y1, y2, c);
+			if(++cnt == OS) { cnt = 0; p.dec[(size_t)m * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0)); m++; }
+		}
+		k1_store_state(p, ch, f2_lo(x1), f2_lo(x2), f2_hi(x1), f2_hi(x2), f2_lo(y1), f2_lo(y2), f2_hi(y1), f2_hi(y2), phi);
+	}
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K1, one stream per channel ("independent streams", every channel thread of the reference streams its own sample
+ * buffer: src/demod.c:302-310).  samples = float2[n_pairs][stride] time-major across streams (k0_convert_lanes), so a
+ * block of 128 channels reads 1 KB of contiguous bytes per sample: the algorithmic 8 B per channel-sample are real HBM
+ * traffic here.  Rows are fetched by TMA bulk copies (one 1 KB cp.async.bulk per sample row) into a double-buffered
+ * shared-memory tile of 40 rows per buffer; with one block per SM ~80 KB per SM (12 MB over the GPU) are in flight,
+ * above the bandwidth-delay product of HBM.  Arithmetic and NCO table layout as in the packed kernel.
+ * ---------------------------------------------------------------------------------------------- */
+#define K1L_BLOCK 128
+#define K1L_TILE_ROWS 40
+#define K1L_SMEM_BYTES (257 * 8 * 16 + 2 * K1L_TILE_ROWS * K1L_BLOCK * 8 + 16)
+
+template<int OS, bool SYM>
+__global__ void __launch_bounds__(K1L_BLOCK) k1_mix_iir_decimate_lanes(vdl2_k1_params p) {
+	constexpr int TG = K1L_TILE_ROWS / OS;                 /* groups per tile */
+	constexpr int LA = 10, MA = 5;
+	constexpr int NLUT = 8;
+	extern __shared__ __align__(128) unsigned char k1l_smem[];
+	float2 *s_tiles = reinterpret_cast<float2 *>(k1l_smem);                                            /* [2][TG*OS][128] */
+	float4 *s_lut = reinterpret_cast<float4 *>(k1l_smem + 2 * K1L_TILE_ROWS * K1L_BLOCK * 8);           /* [257][8] */
+	uint64_t *s_bar = reinterpret_cast<uint64_t *>(k1l_smem + 2 * K1L_TILE_ROWS * K1L_BLOCK * 8 + 257 * 8 * 16);
+	const uint32_t tid = threadIdx.x;
+	const uint32_t ch = blockIdx.x * K1L_BLOCK + tid;
+	const bool active = ch < p.n_ch;
+	const uint32_t n_pairs = p.ca ? p.ca->n_pairs : p.n_pairs, cnt0 = p.ca ? p.ca->cnt0 : p.cnt0;
+	const size_t stride = p.stream_stride;                 /* float2 elements between consecutive samples */
+	const float2 *samples = p.samples + (size_t)blockIdx.x * K1L_BLOCK;      /* this block's 128 columns */
+	for(uint32_t i = tid; i < 257 * NLUT; i += K1L_BLOCK) s_lut[i] = p.lut[i / NLUT];
+	const float4 *lut = s_lut + (tid & (NLUT - 1));
+	if(tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+	float xr1 = 0, xr2 = 0, xi1 = 0, xi2 = 0, yr1 = 0, yr2 = 0, yi1 = 0, yi2 = 0;
+	uint32_t phi = 0, dphi = 0;
+	if(active) k1_load_state(p, ch, xr1, xr2, xi1, xi2, yr1, yr2, yi1, yi2, phi, dphi);
+	u64 x1 = f2_pack(xr1, xi1), x2 = f2_pack(xr2, xi2), y1 = f2_pack(yr1, yi1), y2 = f2_pack(yr2, yi2);
+	k1_packed_consts c;
+	c.ONE = f2_pack(p.one, p.one); c.SGN = f2_pack(p.neg_one, p.one);
+	c.A0 = f2_pack(p.a0, p.a0); c.A1 = f2_pack(p.a1, p.a1); c.A2 = f2_pack(p.a2, p.a2);
+	c.B1 = f2_pack(p.b1, p.b1); c.B2 = f2_pack(p.b2, p.b2); c.TWO = f2_pack(p.two, p.two);
+	c.one = p.one; c.neg_one = p.neg_one;
+	/* the last block may reach past the allocated columns when n_chp is not a multiple of 128: clamp the column */
+	const uint32_t col = min(tid, (uint32_t)(p.stream_stride - 1 - (size_t)blockIdx.x * K1L_BLOCK));
+	__syncthreads();
+
+	uint32_t cnt = cnt0, m = 0, pos = 0;
+	const uint32_t head = min(n_pairs, (OS - cnt0 % OS) % OS);
+	if(active) {
+		for(; pos < head; pos++) {
+			u64 y0 = k1_packed_step(samples[(size_t)pos * stride + col], lut[((phi >> 16) & 0xFFu) * NLUT], phi, dphi, x1, x2, y1, y2, c);
+			if(++cnt == OS) { cnt = 0; p.dec[(size_t)m * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0)); m++; }
+		}
+	}
+	pos = head;
+	m = (cnt0 + head) / OS;
+	cnt = (cnt0 + head) % OS;
+	u64 P1 = f2_mul(c.A0, x1), P2 = f2_mul(c.A0, x2);
+	const uint32_t n_groups = (n_pairs - pos) / OS;
+	const uint32_t n_tiles = (n_groups + TG - 1) / TG;
+	/* bytes of one row that exist in the sample plane for this block (a full 1 KB except in a ragged last block) */
+	const uint32_t row_bytes = (uint32_t)min((size_t)K1L_BLOCK, stride - (size_t)blockIdx.x * K1L_BLOCK) * 8u;
+	/* thread 0 arms the barrier with the tile's byte count, then threads 0..rows-1 request one row each */
+	auto request_tile = [&](uint32_t t, uint32_t buf) {
+		const uint32_t rows = min((uint32_t)TG, n_groups - t * TG) * OS;
+		if(tid == 0)
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&s_bar[buf])), "r"(rows * row_bytes) : "memory");
+		__syncthreads();
+		const float2 *src = samples + (size_t)(head + (size_t)t * TG * OS) * stride;
+		for(uint32_t r = tid; r < rows; r += K1L_BLOCK)
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+					:: "r"(smem_u32(&s_tiles[((size_t)buf * TG * OS + r) * K1L_BLOCK])), "l"(src + (size_t)r * stride), "r"(row_bytes), "r"(smem_u32(&s_bar[buf])) : "memory");
+	};
+	for(uint32_t t = 0; t < 2 && t < n_tiles; t++) request_tile(t, t);
+	for(uint32_t g0 = 0, tile = 0; g0 < n_groups; g0 += TG, tile++) {
+		const uint32_t ng = min((uint32_t)TG, n_groups - g0);
+		const float2 *s_tile = s_tiles + (size_t)(tile & 1u) * TG * OS * K1L_BLOCK + tid;
+		mbar_wait(&s_bar[tile & 1u], (tile >> 1) & 1u);
+		if(active) {
+			for(uint32_t g = 0; g < ng; g++) {
+				const float2 *sp = &s_tile[g * OS * K1L_BLOCK];
+				u64 y0 = 0;
+				float2 S[OS];
+				float4 E[OS];
+				float FR[OS];
+				u64 X0[OS];
+#pragma unroll
+				for(int k = -LA; k < OS; k++) {
+					const int kl = k + LA, km = k + MA;
+					if(kl < OS) {
+						const uint32_t ph = phi + (uint32_t)kl * dphi;
+						E[kl] = lut[((ph >> 16) & 0xFFu) * NLUT];
+						FR[kl] = (float)(ph & 0xFFFFu);
+						S[kl] = sp[kl * K1L_BLOCK];
+					}
+					if(km >= 0 && km < OS) {
+						const u64 CS = f2_fma(f2_mul(f2_pack(E[km].z, E[km].w), f2_pack(FR[km], FR[km])), c.ONE, f2_pack(E[km].x, E[km].y));
+						X0[km] = k1_mix(S[km], CS, c);
+					}
+					if(k >= 0) {
+						const u64 x0 = X0[k];
+						u64 r;
+						if(SYM) {
+							const u64 P0 = f2_mul(c.A0, x0);
+							r = f2_fma(P0, c.ONE, f2_fma(P1, c.TWO, P2));
+							P2 = P1; P1 = P0;
+						} else {
+							const u64 t = f2_fma(f2_mul(c.A1, x1), c.ONE, f2_mul(c.A2, x2));
+							r = f2_fma(f2_mul(c.A0, x0), c.ONE, t);
+						}
+						const u64 u = f2_fma(f2_mul(c.B1, y1), c.ONE, f2_mul(c.B2, y2));
+						y0 = f2_fma(r, c.ONE, u);
+						x2 = x1; x1 = x0; y2 = y1; y1 = y0;
+					}
+				}
+				phi += (uint32_t)OS * dphi;
+				p.dec[(size_t)(m + g) * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0));
+			}
+		}
+		m += ng;
+		pos += ng * OS;
+		__syncthreads();                                           /* every warp is done with this buffer */
+		if(tile + 2 < n_tiles) request_tile(tile + 2, tile & 1u);
+	}
+	if(active) {
+		for(; pos < n_pairs; pos++) {
+			u64 y0 = k1_packed_step(samples[(size_t)pos * stride + col], lut[((phi >> 16) & 0xFFu) * NLUT], phi, dphi, x1, x2, y1, y2, c);
 			if(++cnt == OS) { cnt = 0; p.dec[(size_t)m * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0)); m++; }
 		}
 		k1_store_state(p, ch, f2_lo(x1), f2_lo(x2), f2_hi(x1), f2_hi(x2), f2_lo(y1), f2_lo(y2), f2_hi(y1), f2_hi(y2), phi);
@@ -355,13 +511,15 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
  * ~22 FP64 operations) whose float result is the correctly rounded fl32(atan2); only when it reports that the double
  * lies within 2^-44 of a float rounding boundary, or for zero / non-finite / extreme inputs (about one sample in
  * 3e5), the libdevice routine decides, as it does for every sample when FAST is off. */
+__constant__ double c_atan_tab[VDL2_ATAN_TABLE_DOUBLES] = VDL2_ATAN_TABLE_INIT;
+
 template<bool FAST>
 __global__ void __launch_bounds__(256) k2a_phase_mag(const float2 *__restrict__ dec, float *__restrict__ phase,
 		float *__restrict__ mag, uint32_t n_elems_p, uint32_t n_chp, const vdl2_chunk_args *__restrict__ ca) {
 	__shared__ double s_atan[VDL2_ATAN_TABLE_DOUBLES];
 	if(FAST) {
-		const double tab[VDL2_ATAN_TABLE_DOUBLES] = VDL2_ATAN_TABLE_INIT;
-		if(threadIdx.x < VDL2_ATAN_TABLE_DOUBLES) s_atan[threadIdx.x] = tab[threadIdx.x];
+		/* the break-point table is indexed per lane: shared memory (a __constant__ look-up with divergent indices serialises) */
+		if(threadIdx.x < VDL2_ATAN_TABLE_DOUBLES) s_atan[threadIdx.x] = c_atan_tab[threadIdx.x];
 		__syncthreads();
 	}
 	const uint32_t n_elems = ca ? ca->n_dec * n_chp : n_elems_p;
@@ -399,17 +557,23 @@ __device__ __forceinline__ void k2_cp_async4(float *smem_dst, const float *gsrc)
 	const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void k2_cp_async8(float2 *smem_dst, const float2 *gsrc) {
+	const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void k2_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void k2_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 /* MODE: 0 sync attempts from the phase plane, TwoSum unwrap; 1 phase plane, table unwrap (default); 2 phase ring,
  * block inputs loaded one block ahead into registers; 3 phase ring, block inputs staged one block ahead in shared
- * memory by cp.async (experimental, VDL2GPU_K2_VARIANT=4: written at the end of round 1, not yet run on hardware) */
+ * memory by cp.async (VDL2GPU_K2_VARIANT=4); 4 phase ring, ALL block inputs (phase, magnitude, decimated samples)
+ * staged one block ahead by cp.async (VDL2GPU_K2_VARIANT=5) */
 template<int BLOCK, bool BLOCKED, int MODE>
 __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	__shared__ float s_ring[VDL2_SYNC_BUFLEN * BLOCK];
 	__shared__ float s_consts[33];
 	__shared__ __align__(8) uint32_t s_unwrap[MODE ? VDL2_UNWRAP_STATES * 6 : 2];
+	static_assert(MODE >= 0 && MODE <= 4, "walk mode");
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ch = blockIdx.x * BLOCK + tid;
 	if(tid < 16) { s_consts[tid] = p.tables->pr_phase[tid]; s_consts[16 + tid] = p.tables->lr_X[tid]; }
@@ -453,7 +617,40 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	const uint64_t dec_base = p.ca ? p.ca->dec_base : p.dec_base;
 	uint32_t m = 0;
 	if(BLOCKED) {
-		if(MODE == 3) {
+		if(MODE == 4) {
+			/* Everything a block of 12 samples can need - its 12 phases, 12 magnitudes and 12 decimated samples - is staged one
+			 * block ahead in shared memory by cp.async (36 LDGSTS per lane and block): neither the searching path nor the
+			 * symbol slicing of a channel that is inside a burst ever waits for global memory, whatever mix of states the 32
+			 * channels of the warp are in. */
+			__shared__ float s_st[2][2 * VDL2_WALK_BLOCK][BLOCK];          /* rows 0..11 phase, 12..23 magnitude */
+			__shared__ float2 s_sd[2][VDL2_WALK_BLOCK][BLOCK];
+			auto stage = [&](uint32_t buf, size_t o) {
+#pragma unroll
+				for(int t = 0; t < VDL2_WALK_BLOCK; t++) {
+					k2_cp_async4(&s_st[buf][t][tid], phs + o + (size_t)t * s);
+					k2_cp_async4(&s_st[buf][VDL2_WALK_BLOCK + t][tid], mgs + o + (size_t)t * s);
+					k2_cp_async8(&s_sd[buf][t][tid], dec + o + (size_t)t * s);
+				}
+				k2_cp_async_commit();
+			};
+			uint32_t b = 0;
+			if(m + VDL2_WALK_BLOCK <= n_dec) stage(0, 0);
+#pragma unroll 1
+			for(; m + VDL2_WALK_BLOCK <= n_dec; m += VDL2_WALK_BLOCK, b ^= 1u) {
+				k2_cp_async_wait_all();
+				if(m + 2 * VDL2_WALK_BLOCK <= n_dec) stage(b ^ 1u, (size_t)(m + VDL2_WALK_BLOCK) * s);
+				vdl2_walk_pref pf;
+				const int first = vdl2_walk_first(v);
+#pragma unroll
+				for(int t = 0; t < VDL2_WALK_BLOCK; t++) pf.pw[t] = s_st[b][t][tid];
+#pragma unroll
+				for(int j = 0; j < 4; j++) pf.mg[j] = s_st[b][VDL2_WALK_BLOCK + first + VDL2_SYNC_SKIP * j][tid];
+				pf.first = first; pf.valid = 1;
+				vdl2_walk_block_ring<true>(v, ring, BLOCK, env, ch, dec_base + m, &s_sd[b][0][tid], &s_st[b][0][tid],
+						&s_st[b][VDL2_WALK_BLOCK][tid], BLOCK, pf, false);
+			}
+			k2_cp_async_wait_all();
+		} else if(MODE == 3) {
 			/* stage[buf][k][lane]: k = 0..11 the block's phases, 12..15 the magnitudes at the predicted attempt offsets */
 			__shared__ float s_stage[2 * 16 * BLOCK];
 			float *stg = s_stage + tid;
@@ -687,7 +884,8 @@ __global__ void k_rs_verify(uint8_t *blocks, const int32_t *fec_octets, uint32_t
 /* ------------------------------------------------------------------------------------------------
  * launch stubs
  * ---------------------------------------------------------------------------------------------- */
-#define K1_BLOCK 32
+#define K1_BLOCK 128     /* four warps = the four sub-partitions of an SM share the sample tiles and the 8-copy NCO table */
+#define K1_BLOCK1 32     /* one warp per block: independent streams with fewer than 128 channels per stream */
 #define K2_BLOCK 32
 
 /* One shared-memory carve-out for every kernel of the chain, so that an SM never has to drain to re-partition
@@ -712,10 +910,24 @@ extern "C" int vdl2_kernels_init_device(int device) {
 		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK, 0, false>, pct);
 		vdl2_set_carveout(k1_mix_iir_decimate_packed<13, K1_BLOCK, 10, true>, pct);
 		vdl2_set_carveout(k1_mix_iir_decimate_packed<13, K1_BLOCK, 10, false>, pct);
-		vdl2_set_carveout(k1_mix_iir_decimate_scalar<K1_BLOCK>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK1, 10, true>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK1, 10, false>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK1, 10, true>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK1, 10, false>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_scalar<K1_BLOCK1>, pct);
 		vdl2_set_carveout(k0_convert, pct);
+		vdl2_set_carveout(k0_convert_lanes, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_lanes<20, true>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_lanes<20, false>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_lanes<10, true>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_lanes<10, false>, pct);
+		cudaFuncSetAttribute(k1_mix_iir_decimate_lanes<20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1L_SMEM_BYTES);
+		cudaFuncSetAttribute(k1_mix_iir_decimate_lanes<20, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1L_SMEM_BYTES);
+		cudaFuncSetAttribute(k1_mix_iir_decimate_lanes<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1L_SMEM_BYTES);
+		cudaFuncSetAttribute(k1_mix_iir_decimate_lanes<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1L_SMEM_BYTES);
 		vdl2_set_carveout(k2a_phase_mag<true>, pct);
 		vdl2_set_carveout(k2a_phase_mag<false>, pct);
+		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 4>, pct);
 		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 3>, pct);
 		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 2>, pct);
 		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 1>, pct);
@@ -729,31 +941,58 @@ extern "C" int vdl2_kernels_init_device(int device) {
 	return (int)cudaGetLastError();
 }
 
-extern "C" int vdl2_launch_k0(const void *raw, uint32_t n_pairs, uint32_t fmt, const float *levels, float *out4, uint32_t n_streams,
+extern "C" int vdl2_launch_k0(const void *raw, uint32_t n_pairs, uint32_t fmt, const float *levels, float *out2, uint32_t n_streams,
 		uint32_t raw_stride, uint32_t out_stride, const vdl2_chunk_args *ca, cudaStream_t st) {
 	if(n_pairs == 0 || n_streams == 0) return 0;
 	k0_convert<<<dim3((n_pairs + 255) / 256, n_streams), 256, 0, st>>>(static_cast<const uint8_t *>(raw), n_pairs, fmt, levels,
-			reinterpret_cast<float4 *>(out4), raw_stride, out_stride, ca);
+			reinterpret_cast<float2 *>(out2), raw_stride, out_stride, ca);
 	return (int)cudaGetLastError();
 }
 
-/* variant: 0 un-pipelined packed kernel, 4 no symmetric-tap specialisation, anything else the default */
+extern "C" int vdl2_launch_k0_lanes(const void *raw, uint32_t n_pairs, uint32_t fmt, const float *levels, float *out2, uint32_t n_streams,
+		uint32_t raw_stride, uint32_t out_stride, const vdl2_chunk_args *ca, cudaStream_t st) {
+	if(n_pairs == 0 || n_streams == 0) return 0;
+	k0_convert_lanes<<<dim3((n_pairs + 31) / 32, (out_stride + 31) / 32), dim3(32, 32), 0, st>>>(static_cast<const uint8_t *>(raw), n_pairs, fmt,
+			levels, reinterpret_cast<float2 *>(out2), n_streams, raw_stride, out_stride, ca);
+	return (int)cudaGetLastError();
+}
+
+template<int OS, int BLOCK>
+static void k1_launch_packed(const vdl2_k1_params *p, int variant, bool sym, cudaStream_t st) {
+	const uint32_t blocks = (p->n_ch + BLOCK - 1) / BLOCK;
+	if(variant == 0 && BLOCK == K1_BLOCK) k1_mix_iir_decimate_packed<OS, K1_BLOCK, 0, false><<<blocks, BLOCK, 0, st>>>(*p);
+	else if(sym) k1_mix_iir_decimate_packed<OS, BLOCK, 10, true><<<blocks, BLOCK, 0, st>>>(*p);
+	else k1_mix_iir_decimate_packed<OS, BLOCK, 10, false><<<blocks, BLOCK, 0, st>>>(*p);
+}
+
+/* variant: 0 un-pipelined packed kernel, 4 no symmetric-tap specialisation, 8 one warp per block (single NCO table copy),
+ * anything else the default (four warps per block, eight table copies) */
 extern "C" int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, int variant, cudaStream_t st) {
 	if(p->n_pairs == 0 || p->n_ch == 0) return 0;
-	const uint32_t blocks = (p->n_ch + K1_BLOCK - 1) / K1_BLOCK;
 	const bool sym = (p->a1 == 2.0f * p->a0) && (p->a2 == p->a0) && variant != 4;
+	if(p->ch_per_stream == 1) {                       /* one stream per channel: samples are float2[n_pairs][stream_stride] */
+		const uint32_t blocks = (p->n_ch + K1L_BLOCK - 1) / K1L_BLOCK;
+		if(p->oversample == 20) {
+			if(sym) k1_mix_iir_decimate_lanes<20, true><<<blocks, K1L_BLOCK, K1L_SMEM_BYTES, st>>>(*p);
+			else k1_mix_iir_decimate_lanes<20, false><<<blocks, K1L_BLOCK, K1L_SMEM_BYTES, st>>>(*p);
+		} else if(p->oversample == 10) {
+			if(sym) k1_mix_iir_decimate_lanes<10, true><<<blocks, K1L_BLOCK, K1L_SMEM_BYTES, st>>>(*p);
+			else k1_mix_iir_decimate_lanes<10, false><<<blocks, K1L_BLOCK, K1L_SMEM_BYTES, st>>>(*p);
+		} else return (int)cudaErrorInvalidValue;
+		return (int)cudaGetLastError();
+	}
+	/* a 128-channel block must not straddle two streams */
+	const bool wide = variant != 8 && (p->ch_per_stream == 0 || p->ch_per_stream % K1_BLOCK == 0);
 	if(!force_scalar && p->oversample == 20) {
-		if(variant == 0) k1_mix_iir_decimate_packed<20, K1_BLOCK, 0, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
-		else if(sym) k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
-		else k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		if(wide) k1_launch_packed<20, K1_BLOCK>(p, variant, sym, st); else k1_launch_packed<20, K1_BLOCK1>(p, variant, sym, st);
 	} else if(!force_scalar && p->oversample == 10) {
-		if(variant == 0) k1_mix_iir_decimate_packed<10, K1_BLOCK, 0, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
-		else if(sym) k1_mix_iir_decimate_packed<10, K1_BLOCK, 10, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
-		else k1_mix_iir_decimate_packed<10, K1_BLOCK, 10, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
-	} else if(!force_scalar && p->oversample == 13 && variant != 0) {      /* 1.365 Msps (Mirics, src/mirics.h:23) */
-		if(sym) k1_mix_iir_decimate_packed<13, K1_BLOCK, 10, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
-		else k1_mix_iir_decimate_packed<13, K1_BLOCK, 10, false><<<blocks, K1_BLOCK, 0, st>>>(*p);
-	} else k1_mix_iir_decimate_scalar<K1_BLOCK><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		if(wide) k1_launch_packed<10, K1_BLOCK>(p, variant, sym, st); else k1_launch_packed<10, K1_BLOCK1>(p, variant, sym, st);
+	} else if(!force_scalar && p->oversample == 13 && variant != 0 && wide) {      /* 1.365 Msps (Mirics, src/mirics.h:23) */
+		k1_launch_packed<13, K1_BLOCK>(p, variant, sym, st);
+	} else {
+		const uint32_t blocks = (p->n_ch + K1_BLOCK1 - 1) / K1_BLOCK1;
+		k1_mix_iir_decimate_scalar<K1_BLOCK1><<<blocks, K1_BLOCK1, 0, st>>>(*p);
+	}
 	return (int)cudaGetLastError();
 }
 
@@ -767,7 +1006,8 @@ extern "C" int vdl2_launch_k2a(const vdl2_k2_params *p, cudaStream_t st) {
 }
 
 /* variant: 0 per-sample walk; 1 blocked, phase plane, TwoSum unwrap; 3 blocked, phase ring, block inputs one block
- * ahead in registers; 4 the same with cp.async staging; anything else (2) the default: blocked, phase plane, table unwrap */
+ * ahead in registers; 4 the same with cp.async staging; 5 phase ring with every block input staged by cp.async;
+ * anything else (2): blocked, phase plane, table unwrap */
 extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
 	if(p->n_dec == 0 || p->n_ch == 0) return 0;
 	const uint32_t blocks = (p->n_ch + K2_BLOCK - 1) / K2_BLOCK;
@@ -776,6 +1016,7 @@ extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
 	else if(variant == 1) k2_sync_slice<K2_BLOCK, true, 0><<<blocks, K2_BLOCK, 0, st>>>(*p);
 	else if(variant == 3) k2_sync_slice<K2_BLOCK, true, 2><<<blocks, K2_BLOCK, 0, st>>>(*p);
 	else if(variant == 4) k2_sync_slice<K2_BLOCK, true, 3><<<blocks, K2_BLOCK, 0, st>>>(*p);
+	else if(variant == 5) k2_sync_slice<K2_BLOCK, true, 4><<<blocks, K2_BLOCK, 0, st>>>(*p);
 	else k2_sync_slice<K2_BLOCK, true, 1><<<blocks, K2_BLOCK, 0, st>>>(*p);
 	return (int)cudaGetLastError();
 }

@@ -18,7 +18,7 @@ typedef struct {
 } vdl2_chunk_args;
 
 typedef struct {
-	const float4 *samples;       /* K0 output: {re, im, im, re} per complex sample; stream s at samples + s * stream_stride */
+	const float2 *samples;       /* K0 output: {re, im} per complex sample; stream s at samples + s * stream_stride */
 	uint32_t n_pairs;
 	uint32_t oversample;
 	uint32_t cnt0;               /* decimation counter on entry (src/demod.c:289,322), same for all channels */
@@ -28,8 +28,9 @@ typedef struct {
 	const float4 *lut;           /* 257 x {cos, sin, dcos*2^-16, dsin*2^-16} */
 	float a0, a1, a2, b1, b2;
 	float one, neg_one, two;     /* run-time 1.0f / -1.0f / 2.0f (see k1_mix_iir_decimate_packed) */
-	uint32_t ch_per_stream;      /* independent-streams mode: channels [s*C, (s+1)*C) read stream s; 0 = one stream for all */
-	uint32_t stream_stride;      /* float4 elements between consecutive streams in `samples` */
+	uint32_t ch_per_stream;      /* independent-streams mode: channels [s*C, (s+1)*C) read stream s; 0 = one stream for all;
+	                              * 1 = one stream per channel: `samples` is float2[n_pairs][stream_stride], time-major across streams */
+	uint32_t stream_stride;      /* float2 elements between consecutive streams in `samples` (ch_per_stream == 1: per sample row) */
 	const vdl2_chunk_args *ca;   /* NULL, or device pointer overriding n_pairs / cnt0 */
 } vdl2_k1_params;
 
@@ -75,8 +76,11 @@ extern "C" {
 #endif
 /* once per device (thread-safe): the shared-memory carve-out every kernel of the chain asks for */
 int vdl2_kernels_init_device(int device);
-/* n_streams streams of n_pairs samples each: raw stream s at raw + s * raw_stride bytes, output at out4 + s * out_stride float4 */
-int vdl2_launch_k0(const void *raw, uint32_t n_pairs, uint32_t fmt, const float *levels, float *out4, uint32_t n_streams,
+/* n_streams streams of n_pairs samples each: raw stream s at raw + s * raw_stride bytes, output at out2 + s * out_stride float2 */
+int vdl2_launch_k0(const void *raw, uint32_t n_pairs, uint32_t fmt, const float *levels, float *out2, uint32_t n_streams,
+		uint32_t raw_stride, uint32_t out_stride, const vdl2_chunk_args *ca, cudaStream_t st);
+/* one stream per channel: raw[s][i] -> out2[i][out_stride] float2, time-major across streams */
+int vdl2_launch_k0_lanes(const void *raw, uint32_t n_pairs, uint32_t fmt, const float *levels, float *out2, uint32_t n_streams,
 		uint32_t raw_stride, uint32_t out_stride, const vdl2_chunk_args *ca, cudaStream_t st);
 int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, int variant, cudaStream_t st);
 int vdl2_launch_copy_hist(const vdl2_k2_params *p, cudaStream_t st);

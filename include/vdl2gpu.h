@@ -67,7 +67,9 @@ typedef struct {
 	uint32_t flags;              /* VDL2GPU_FLAG_* */
 	uint32_t n_inflight;         /* chunks in flight before submit blocks (back-pressure); 0 = 4 */
 	uint32_t n_streams;          /* independent IQ streams (0 = 1).  With S > 1 the n_channels = S x C channels are split
-	                              * stream-major: channels [s*C, (s+1)*C) demodulate stream s; C must be a multiple of 32 */
+	                              * stream-major: channels [s*C, (s+1)*C) demodulate stream s; C must be a multiple of 32,
+	                              * or 1 (one stream per channel: every channel reads its own IQ buffer, as every
+	                              * channel thread of the reference does, src/demod.c:302-310) */
 	uint32_t reserved[4];
 } vdl2gpu_config;
 
@@ -213,20 +215,24 @@ int vdl2gpu_read_dec(vdl2gpu_ctx *ctx, float *out, size_t cap_floats, uint32_t *
 /* drain trace events (VDL2GPU_FLAG_TRACE).  Synchronises.  Returns the number copied. */
 int vdl2gpu_read_events(vdl2gpu_ctx *ctx, vdl2gpu_event *out, uint32_t cap);
 /* device time (ms) spent in each kernel for the chunks completed so far, measured with CUDA events on
- * the library's streams when timing was enabled with vdl2gpu_enable_timing(ctx, 1) (timed chunks are launched
- * kernel by kernel, not as graphs).  Order: K0, K1, K2a, K2 (+history copy), K3 (+finish). */
+ * the library's streams when timing was enabled with vdl2gpu_enable_timing(ctx, 1).
+ * Order: K0, K1, K2a, K2 (+history copy), K3 (+finish). */
 int vdl2gpu_enable_timing(vdl2gpu_ctx *ctx, int on);
 int vdl2gpu_get_kernel_ms(vdl2gpu_ctx *ctx, double ms[5], uint64_t launches[5]);
+/* stage boundaries of the timed chunks harvested so far, 8 floats per chunk: chunk number, then ms since
+ * vdl2gpu_enable_timing(ctx, 1) of: front start, K0|K1, K1 end, back start, K2a|K2, K2|K3, K3 end (with graph replay
+ * only the stage boundaries are known: K0 counts into K1 and K3 into K2).  Returns the number of rows copied. */
+int vdl2gpu_get_timeline(vdl2gpu_ctx *ctx, float *out, uint32_t cap_rows);
 
 /* ---- raw launch stubs (extern "C", plain pointers; used by the micro-parity tests and by hosts that
  *      manage device memory themselves).  All pointers are DEVICE pointers unless stated otherwise; `stream` is a
  *      cudaStream_t.  The launch stubs only enqueue kernels: no allocation, no synchronisation.
  *      (vdl2gpu_launch_rs_verify builds its GF tables on the first call on a device.) ---- */
-/* K0: raw cu8/cs16 -> float samples in the layout K1 consumes, {re, im, im, re} per complex sample
- * (src/demod.c:339-365: process_buf_uchar / process_buf_short).  levels256 = the 256-entry table of
- * process_buf_uchar_init (src/demod.c:349-354), only read for VDL2GPU_FMT_U8. */
+/* K0: raw cu8/cs16 -> float samples {re, im} per complex sample, the reference's sbuf (src/demod.c:339-365:
+ * process_buf_uchar / process_buf_short).  levels256 = the 256-entry table of process_buf_uchar_init
+ * (src/demod.c:349-354), only read for VDL2GPU_FMT_U8. */
 int vdl2gpu_launch_convert(const void *raw, uint32_t n_pairs, uint32_t sample_fmt, const float *levels256,
-		float *samples4_out /* [n_pairs][4] */, void *stream);
+		float *samples_out /* [n_pairs][2] */, void *stream);
 /* K4: FCS residue of n frames stored back to back (src/crc.c:21-64 as used at src/avlc.c:177) */
 int vdl2gpu_launch_fcs_crc16(const uint8_t *frames, const uint32_t *offsets, const uint32_t *lens,
 		uint32_t n_frames, uint16_t *residues_out, void *stream);
@@ -257,7 +263,7 @@ int vdl2gpu_stage_levels(vdl2gpu_stage *stage, const float **levels256_dev);
 /* K1: NCO mix + 2-pole Chebyshev IIR + decimation == the sample loop of process_samples (src/demod.c:288-337, with
  * sincosf_lut :58-72, multiply :200-203, chebyshev_lpf_2pole :74-79) for every channel.  Filter, NCO and decimation
  * state persist in the stage across calls.  *n_dec_out (host) receives the number of rows written to dec_out. */
-int vdl2gpu_launch_mix_iir_decimate(vdl2gpu_stage *stage, const float *samples4 /* [n_pairs][4] */, uint32_t n_pairs,
+int vdl2gpu_launch_mix_iir_decimate(vdl2gpu_stage *stage, const float *samples /* [n_pairs][2] */, uint32_t n_pairs,
 		float *dec_out /* [n_dec][row_stride][2] */, uint32_t *n_dec_out, void *stream);
 /* K2a + K2: demod() (src/demod.c:222-286: phase ring, got_sync :105-198, D8PSK slicing) and the header part of
  * decode_vdl2_burst (src/decode.c:198-258) over n_dec decimated samples of every channel; completed bursts are

@@ -46,6 +46,8 @@ def run(env, order, channels, n_run, d_chunks, offs, flags=0):
         for i in range(16):
             g.submit_device(d_chunks[i % n].data_ptr(), bench.CHUNK_BYTES, stream.cuda_stream)
         g.flush_count()
+        if os.environ.get("VDL2GPU_SWEEP_TIMELINE"):
+            g.enable_timing(True)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -61,6 +63,11 @@ def run(env, order, channels, n_run, d_chunks, offs, flags=0):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / (2 * n_run)
         st = g.stats()
+        if os.environ.get("VDL2GPU_SWEEP_TIMELINE"):
+            tl = g.timeline()
+            if len(tl) > 24:
+                rows = tl[16:24]
+                out["timeline_ms"] = [[round(float(x - rows[0][1]), 3) for x in r[1:]] for r in rows]
         out.update(pipelined_ms_per_chunk=round(ms, 4), g_chsamples_per_s=round(channels * bench.CHUNK_PAIRS / ms / 1e6, 1),
                    frames=frames, host_us_per_chunk=round(t_host / (2 * n_run) * 1e6, 1), graph_launches=st["graph_launches"],
                    overflows=st["pool_overflows"] + st["out_overflows"])
@@ -83,8 +90,9 @@ def main():
     chunks, offs, _ = bench.make_stream(4.0)
     d_chunks = torch.from_numpy(chunks).cuda()
     variants = [("default", {}, 0), ("no_graph", {}, vd.FLAG_NO_GRAPH), ("k2a_libm", dict(VDL2GPU_K2A=0), 0),
-                ("k2_ring_regs", dict(VDL2GPU_K2_VARIANT=3), 0), ("k2_ring_cpasync", dict(VDL2GPU_K2_VARIANT=4), 0),
-                ("k2_twosum", dict(VDL2GPU_K2_VARIANT=1), 0)]
+                ("k2_plane", dict(VDL2GPU_K2_VARIANT=2), 0), ("k2_ring_cpasync", dict(VDL2GPU_K2_VARIANT=4), 0),
+                ("k2_ring_staged", dict(VDL2GPU_K2_VARIANT=5), 0), ("k1_one_warp", dict(VDL2GPU_K1_VARIANT=8), 0),
+                ("default_again", {}, 0), ("no_graph_again", {}, vd.FLAG_NO_GRAPH)]
     extra = os.environ.get("VDL2GPU_SWEEP_EXTRA")          # "name:KEY=V,KEY=V;name2:..."
     if extra:
         for item in extra.split(";"):
