@@ -801,28 +801,60 @@ VDL2_HD void vdl2_rs_build_rootmul(uint8_t *rootmul, const uint8_t *gexp, const 
 	}
 }
 
-VDL2_HD int vdl2_rs_verify(uint8_t *data, int fec_octets, const uint8_t *gexp, const uint8_t *glog, const uint8_t *rootmul) {
-	enum { NR = VDL2_RS_N - VDL2_RS_K, FCR = 120 };
-	if(fec_octets == 0) return 0;
-	const int no_eras = NR - fec_octets;
-	uint8_t S[NR];
-	int any = 0;
-	{
-		uint32_t s0 = data[0], s1 = s0, s2 = s0, s3 = s0, s4 = s0, s5 = s0;
-		for(int j = 1; j < VDL2_RS_N; j++) {
-			const uint32_t d = data[j];
-			s0 = rootmul[s0] ^ d;
-			s1 = rootmul[256 + s1] ^ d;
-			s2 = rootmul[512 + s2] ^ d;
-			s3 = rootmul[768 + s3] ^ d;
-			s4 = rootmul[1024 + s4] ^ d;
-			s5 = rootmul[1280 + s5] ^ d;
-		}
-		S[0] = (uint8_t)s0; S[1] = (uint8_t)s1; S[2] = (uint8_t)s2; S[3] = (uint8_t)s3; S[4] = (uint8_t)s4; S[5] = (uint8_t)s5;
-		any = (int)(s0 | s1 | s2 | s3 | s4 | s5);
+/* The decoder in three steps so that a warp can share the two long loops (syndromes over 255 symbols, Chien search
+ * over 255 positions) while the short algebra in between stays with one lane:
+ *   vdl2_rs_syndromes          S[0..5], serial Horner                          decode_rs.h:82-93
+ *   vdl2_rs_syndrome_partial   the same sums, lane l of 32 covering symbols 8l..8l+7 (XOR of the 32 results = S)
+ *   vdl2_rs_locator            erasure-seeded Berlekamp-Massey -> lambda, deg  decode_rs.h:112-213
+ *   vdl2_rs_chien_serial       roots in increasing position order              decode_rs.h:216-239
+ *   vdl2_rs_chien_lane         lane l of 32 tests positions l+1, l+33, ...     (same set, same order once merged)
+ *   vdl2_rs_forney             omega, error values, correction                 decode_rs.h:240-291
+ * vdl2_rs_verify chains the serial forms; K3 uses the lane forms (vdl2_kernels.cu) and must return the same. */
+enum { VDL2_RS_NR = VDL2_RS_N - VDL2_RS_K, VDL2_RS_FCR = 120 };
+
+VDL2_HD int vdl2_rs_syndromes(const uint8_t *data, const uint8_t *rootmul, uint8_t *S) {
+	uint32_t s0 = data[0], s1 = s0, s2 = s0, s3 = s0, s4 = s0, s5 = s0;
+	for(int j = 1; j < VDL2_RS_N; j++) {
+		const uint32_t d = data[j];
+		s0 = rootmul[s0] ^ d;
+		s1 = rootmul[256 + s1] ^ d;
+		s2 = rootmul[512 + s2] ^ d;
+		s3 = rootmul[768 + s3] ^ d;
+		s4 = rootmul[1024 + s4] ^ d;
+		s5 = rootmul[1280 + s5] ^ d;
 	}
-	if(!any) return 0;
-	uint8_t lambda[NR + 1] = { 1, 0, 0, 0, 0, 0, 0 };
+	S[0] = (uint8_t)s0; S[1] = (uint8_t)s1; S[2] = (uint8_t)s2; S[3] = (uint8_t)s3; S[4] = (uint8_t)s4; S[5] = (uint8_t)s5;
+	return (int)(s0 | s1 | s2 | s3 | s4 | s5);
+}
+
+/* lane's share of the six syndromes, packed one per byte (S[i] in bits 8i..8i+7): Horner over its own symbols
+ * (8 lane .. 8 lane + 7, the last lane has 7), then moved to the weight of its segment:
+ * S_i = sum_j d_j a_i^(254-j), a_i = alpha^(120+i), so the segment ending at symbol e is multiplied by a_i^(254-e). */
+VDL2_HD uint64_t vdl2_rs_syndrome_partial(const uint8_t *data, uint32_t lane, const uint8_t *gexp, const uint8_t *glog, const uint8_t *rootmul) {
+	const uint32_t first = 8u * lane, last = (first + 7u < (uint32_t)VDL2_RS_N - 1u) ? first + 7u : (uint32_t)VDL2_RS_N - 1u;
+	uint32_t t[6] = { 0, 0, 0, 0, 0, 0 };
+	for(uint32_t j = first; j <= last; j++) {
+		const uint32_t d = data[j];
+#pragma unroll
+		for(int i = 0; i < 6; i++) t[i] = rootmul[256 * i + t[i]] ^ d;
+	}
+	const uint32_t e = (uint32_t)VDL2_RS_N - 1u - last;
+	uint64_t out = 0;
+#pragma unroll
+	for(int i = 0; i < 6; i++) {
+		const uint32_t sh = ((uint32_t)(VDL2_RS_FCR + i) * e) % 255u;
+		const uint32_t v = t[i] ? gexp[(uint32_t)glog[t[i]] + sh] : 0u;
+		out |= (uint64_t)v << (8 * i);
+	}
+	return out;
+}
+
+/* erasure locator + Berlekamp-Massey; returns deg(lambda) */
+VDL2_HD int vdl2_rs_locator(const uint8_t *S, int fec_octets, const uint8_t *gexp, const uint8_t *glog, uint8_t *lambda) {
+	enum { NR = VDL2_RS_NR };
+	const int no_eras = NR - fec_octets;
+	for(int i = 0; i <= NR; i++) lambda[i] = 0;
+	lambda[0] = 1;
 	if(no_eras > 0) {
 		/* erasures are the untransmitted parity octets RS_K+fec .. 254 (src/rs.c:40-43) */
 		lambda[1] = vdl2_gf_alpha(gexp, 254 - (VDL2_RS_K + fec_octets));
@@ -858,27 +890,50 @@ VDL2_HD int vdl2_rs_verify(uint8_t *data, int fec_octets, const uint8_t *gexp, c
 	}
 	int deg = 0;
 	for(int i = 0; i <= NR; i++) if(lambda[i]) deg = i;
-	int root[NR], loc[NR], count = 0;
-	{
-		/* Chien search, decode_rs.h:216-239: reg[j] = log(lambda_j) + i*j mod 255, advanced by j per step */
-		int reg[NR + 1];
-		for(int j = 1; j <= NR; j++) reg[j] = lambda[j] ? (int)glog[lambda[j]] : -1;
-		for(int i = 1; i <= 255; i++) {
-			uint8_t q = 1;
-			for(int j = deg; j > 0; j--) {
-				if(reg[j] >= 0) {
-					reg[j] += j;
-					if(reg[j] >= 255) reg[j] -= 255;
-					q ^= gexp[reg[j]];
-				}
+	return deg;
+}
+
+/* Chien search, decode_rs.h:216-239: reg[j] = log(lambda_j) + i*j mod 255, advanced by j per step; stops at deg roots */
+VDL2_HD int vdl2_rs_chien_serial(const uint8_t *lambda, int deg, const uint8_t *gexp, const uint8_t *glog, int *root) {
+	enum { NR = VDL2_RS_NR };
+	int reg[NR + 1], count = 0;
+	for(int j = 1; j <= NR; j++) reg[j] = lambda[j] ? (int)glog[lambda[j]] : -1;
+	for(int i = 1; i <= 255; i++) {
+		uint8_t q = 1;
+		for(int j = deg; j > 0; j--) {
+			if(reg[j] >= 0) {
+				reg[j] += j;
+				if(reg[j] >= 255) reg[j] -= 255;
+				q ^= gexp[reg[j]];
 			}
-			if(q != 0) continue;
-			root[count] = i;
-			loc[count] = i - 1;
-			if(++count == deg) break;
 		}
+		if(q != 0) continue;
+		root[count] = i;
+		if(++count == deg) break;
 	}
-	if(deg != count) return -1;
+	return count;
+}
+
+/* the same test for the positions i = lane + 1 + 32 k (k = 0..7, i <= 255): bit k of the result = "i is a root".  A
+ * polynomial of degree deg has at most deg roots, so the serial search's early exit never hides one. */
+VDL2_HD uint32_t vdl2_rs_chien_lane(const uint8_t *lambda, int deg, uint32_t lane, const uint8_t *gexp, const uint8_t *glog) {
+	enum { NR = VDL2_RS_NR };
+	uint32_t mask = 0;
+	for(uint32_t k = 0; k < 8; k++) {
+		const uint32_t i = lane + 1u + 32u * k;
+		if(i > 255u) break;
+		uint32_t q = 1;
+		for(int j = 1; j <= deg && j <= NR; j++)
+			if(lambda[j]) q ^= gexp[((uint32_t)glog[lambda[j]] + i * (uint32_t)j) % 255u];
+		if(q == 0) mask |= 1u << k;
+	}
+	return mask;
+}
+
+/* omega, error values (Forney) and correction for the `count` roots found (decode_rs.h:240-291); returns count */
+VDL2_HD int vdl2_rs_forney(uint8_t *data, const uint8_t *S, const uint8_t *lambda, int deg, const int *root, int count,
+		const uint8_t *gexp, const uint8_t *glog) {
+	enum { NR = VDL2_RS_NR, FCR = VDL2_RS_FCR };
 	const int deg_omega = deg - 1;
 	uint8_t omega[NR + 1] = { 0, 0, 0, 0, 0, 0, 0 };
 	for(int i = 0; i <= deg_omega; i++) {
@@ -898,16 +953,48 @@ VDL2_HD int vdl2_rs_verify(uint8_t *data, int fec_octets, const uint8_t *gexp, c
 		if(num1 != 0) {
 			/* decode_rs.h:289 uses log(0) = 255, so a zero denominator divides by alpha^0 */
 			int e = (int)glog[num1] + (int)glog[num2] + 255 - (den ? (int)glog[den] : 255);
-			data[loc[j]] ^= gexp[e % 255];
+			data[root[j] - 1] ^= gexp[e % 255];          /* loc = root - 1 (prim = 1) */
 		}
 	}
 	return count;
 }
 
+VDL2_HD int vdl2_rs_verify(uint8_t *data, int fec_octets, const uint8_t *gexp, const uint8_t *glog, const uint8_t *rootmul) {
+	enum { NR = VDL2_RS_NR };
+	if(fec_octets == 0) return 0;
+	uint8_t S[NR], lambda[NR + 1];
+	if(!vdl2_rs_syndromes(data, rootmul, S)) return 0;
+	const int deg = vdl2_rs_locator(S, fec_octets, gexp, glog, lambda);
+	int root[NR + 1];
+	const int count = vdl2_rs_chien_serial(lambda, deg, gexp, glog, root);
+	if(deg != count) return -1;
+	return vdl2_rs_forney(data, S, lambda, deg, root, count, gexp, glog);
+}
+
+/* Octet-at-a-time table for the unstuffer: entry [ones][octet] (ones = 0..6, the run of one-bits before the octet)
+ * says whether the eight bits of the octet can be taken as they are - no stuffed zero to delete, no flag, no abort -
+ * and what the run of ones is afterwards: bit 7 = plain, bits 0..2 = run length after the octet.  Built by stepping
+ * the bit rules of vdl2_burst_unstuff itself. */
+#define VDL2_UNSTUFF_TABLE_BYTES (7 * 256)
+VDL2_HD void vdl2_unstuff_build_table(uint8_t *table, uint32_t tid, uint32_t nthr) {
+	for(uint32_t k = tid; k < VDL2_UNSTUFF_TABLE_BYTES; k += nthr) {
+		int ones = (int)(k >> 8), plain = 1;
+		const uint32_t b = k & 255u;
+		for(int i = 0; i < 8 && plain; i++) {
+			const uint32_t bit = (b >> i) & 1u;
+			if(bit == 0) { if(ones >= 5) plain = 0; else ones = 0; }      /* stuffed zero (5) or closing flag (6) */
+			else if(++ones > 6) plain = 0;                                /* seven ones */
+		}
+		table[k] = (uint8_t)(plain ? (0x80 | ones) : 0);
+	}
+}
+
 /* serialise corrected octets, cut to datalen bits, split on HDLC flags with zero-bit deletion:
  * src/decode.c:325-370 + src/bitstream.c:109-150.  Single caller.  Returns status; frames found before a
- * late error stay (the reference has already pushed them). */
-VDL2_HD int vdl2_burst_unstuff(vdl2_burst_work &w) {
+ * late error stay (the reference has already pushed them).
+ * `utab` (vdl2_unstuff_build_table, or NULL) lets whole input octets that contain no stuffing, flag or abort event
+ * for the current run of ones be appended in one step; an octet the table does not clear goes through the bit rules. */
+VDL2_HD int vdl2_burst_unstuff(vdl2_burst_work &w, const uint8_t *utab = nullptr) {
 	const uint32_t total_bits = (8u * w.datalen_octets < w.datalen_bits) ? 8u * w.datalen_octets : w.datalen_bits;
 	uint32_t pos = 0, row = 0, col = 0, cur = 0;     /* input: corrected octets row by row, LSB first */
 	uint32_t out_base = 0;
@@ -920,6 +1007,20 @@ VDL2_HD int vdl2_burst_unstuff(vdl2_burst_work &w) {
 			if((pos & 7u) == 0) {
 				cur = w.tab[row][col];
 				if(++col == VDL2_RS_K) { col = 0; row++; }
+				if(utab != nullptr && pos + 8u <= total_bits) {
+					const uint32_t e = utab[((uint32_t)ones << 8) | cur];
+					if(e & 0x80u) {
+						/* eight plain bits: exactly one output octet completes (the one holding bit j | 7) */
+						const uint32_t both = acc | (cur << (j & 7u));
+						const uint32_t ob = out_base + (j >> 3);
+						if(ob >= sizeof(w.frames)) return w.status = VDL2_ERR_BITSTREAM;
+						w.frames[ob] = (uint8_t)both;
+						acc = both >> 8;
+						ones = (int)(e & 7u);
+						j += 8; pos += 8;
+						continue;
+					}
+				}
 			}
 			const uint32_t bit = (cur >> (pos & 7u)) & 1u;
 			if(bit == 0 && ones == 5) { ones = 0; pos++; continue; }         /* stuffed zero */

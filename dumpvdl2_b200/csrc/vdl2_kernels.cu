@@ -743,12 +743,46 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
  * ---------------------------------------------------------------------------------------------- */
 #define K3_BLOCK 128
 
+/* RS(255,249) errors-and-erasures decode of one block by one warp (src/rs.c:32-49 -> decode_rs.h:71-298): the lanes
+ * share the two long loops - syndromes (each lane sums 8 of the 255 symbols, XOR butterfly over the warp) and the Chien
+ * search (each lane tests 8 of the 255 positions, roots collected in position order with ballots) - and all evaluate
+ * the short Berlekamp-Massey recursion redundantly; lane 0 applies the corrections.  Same return value and same
+ * corrected block as the serial vdl2_rs_verify (stepped lane by lane against the oracle in tests/test_hostsim.py). */
+__device__ __forceinline__ int k3_rs_block(uint8_t *data, int fec_octets, const uint8_t *gexp, const uint8_t *glog,
+		const uint8_t *rootmul, uint32_t lane) {
+	if(fec_octets == 0) return 0;
+	uint64_t part = vdl2_rs_syndrome_partial(data, lane, gexp, glog, rootmul);
+#pragma unroll
+	for(int off = 16; off > 0; off >>= 1) part ^= __shfl_xor_sync(0xFFFFFFFFu, part, off);
+	if(part == 0) return 0;
+	uint8_t S[VDL2_RS_NR], lambda[VDL2_RS_NR + 1];
+#pragma unroll
+	for(int i = 0; i < VDL2_RS_NR; i++) S[i] = (uint8_t)(part >> (8 * i));
+	const int deg = vdl2_rs_locator(S, fec_octets, gexp, glog, lambda);
+	const uint32_t mask = vdl2_rs_chien_lane(lambda, deg, lane, gexp, glog);
+	int root[VDL2_RS_NR + 1], count = 0;
+	for(uint32_t k = 0; k < 8; k++) {
+		uint32_t b = __ballot_sync(0xFFFFFFFFu, (mask >> k) & 1u);
+		while(b) {
+			const int l = __ffs((int)b) - 1;
+			b &= b - 1u;
+			if(count <= VDL2_RS_NR) root[count < VDL2_RS_NR ? count : VDL2_RS_NR] = l + 1 + 32 * (int)k;
+			count++;
+		}
+	}
+	if(deg != count) return -1;
+	if(lane == 0) vdl2_rs_forney(data, S, lambda, deg, root, count, gexp, glog);
+	__syncwarp();
+	return count;
+}
+
 __global__ void __launch_bounds__(K3_BLOCK) k3_burst_fec(vdl2_k3_params p) {
 	__shared__ vdl2_burst_work w;
 	__shared__ uint8_t s_gexp[512];
 	__shared__ uint8_t s_glog[256];
 	__shared__ uint8_t s_rootmul[6 * 256];
 	__shared__ uint16_t s_crctab[256];
+	__shared__ uint8_t s_utab[VDL2_UNSTUFF_TABLE_BYTES];
 	__shared__ uint16_t s_foff[VDL2_MAX_FRAMES];
 	__shared__ uint32_t s_out_off;
 	const uint32_t tid = threadIdx.x;
@@ -759,6 +793,7 @@ __global__ void __launch_bounds__(K3_BLOCK) k3_burst_fec(vdl2_k3_params p) {
 	__syncthreads();
 	vdl2_rs_build_rootmul(s_rootmul, s_gexp, s_glog, tid, K3_BLOCK);
 	vdl2_crc16_build_table(s_crctab, tid, K3_BLOCK);
+	vdl2_unstuff_build_table(s_utab, tid, K3_BLOCK);
 	for(uint32_t b = blockIdx.x; b < n_ready; b += gridDim.x) {
 		__syncthreads();
 		const uint32_t slot_idx = p.ready[b];
@@ -769,9 +804,10 @@ __global__ void __launch_bounds__(K3_BLOCK) k3_burst_fec(vdl2_k3_params p) {
 		if(w.status == VDL2_BURST_OK) {
 			vdl2_burst_unpack(w, slot->words, p.tables->lfsr_words, tid, K3_BLOCK);
 			__syncthreads();
-			if(tid < w.num_blocks) {
-				int nfec = (tid == w.num_blocks - 1) ? (int)w.last_fec : (VDL2_RS_N - VDL2_RS_K);
-				w.rs_ret[tid] = vdl2_rs_verify(w.tab[tid], nfec, s_gexp, s_glog, s_rootmul);
+			for(uint32_t r = tid >> 5; r < w.num_blocks; r += K3_BLOCK / 32) {          /* one warp per RS block */
+				const int nfec = (r == w.num_blocks - 1) ? (int)w.last_fec : (VDL2_RS_N - VDL2_RS_K);
+				const int ret = k3_rs_block(w.tab[r], nfec, s_gexp, s_glog, s_rootmul, tid & 31u);
+				if((tid & 31u) == 0) w.rs_ret[r] = ret;
 			}
 			__syncthreads();
 			if(tid == 0) {
@@ -786,7 +822,7 @@ __global__ void __launch_bounds__(K3_BLOCK) k3_burst_fec(vdl2_k3_params p) {
 					}
 					if(ret > 0) w.fec_corr += ret - (VDL2_RS_N - VDL2_RS_K - nfec);
 				}
-				if(w.status == VDL2_BURST_OK) vdl2_burst_unstuff(w);
+				if(w.status == VDL2_BURST_OK) vdl2_burst_unstuff(w, s_utab);
 				uint32_t off = 0;
 				for(uint32_t k = 0; k < w.n_frames; k++) { s_foff[k] = (uint16_t)off; off += w.flen[k]; }
 			}

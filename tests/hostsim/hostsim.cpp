@@ -21,6 +21,25 @@ static const uint8_t *rootmul_table(const host_tables *h) {
 	if(!ready) { vdl2_rs_build_rootmul(tab, h->t.gf_exp, h->t.gf_log, 0, 1); ready = true; }
 	return tab;
 }
+static const uint8_t *unstuff_table() {
+	static uint8_t tab[VDL2_UNSTUFF_TABLE_BYTES];
+	static bool ready = false;
+	if(!ready) { vdl2_unstuff_build_table(tab, 0, 1); ready = true; }
+	return tab;
+}
+/* the unstuffer twice: bit rules only, and with the octet table the kernel uses; any difference in status, frame
+ * lengths or frame octets is reported as -100 by the callers */
+static int g_unstuff_disagree = 0;
+static void unstuff_both(vdl2_burst_work &w) {
+	static vdl2_burst_work ref;
+	ref = w;
+	vdl2_burst_unstuff(ref);
+	vdl2_burst_unstuff(w, unstuff_table());
+	bool same = ref.status == w.status && ref.n_frames == w.n_frames && ref.frame_bytes == w.frame_bytes;
+	for(uint32_t k = 0; same && k < w.n_frames; k++) same = ref.flen[k] == w.flen[k];
+	if(same && memcmp(ref.frames, w.frames, w.frame_bytes) != 0) same = false;
+	if(!same) g_unstuff_disagree++;
+}
 static const uint16_t *crc_table() {
 	static uint16_t tab[256];
 	static bool ready = false;
@@ -181,7 +200,7 @@ int hostsim_k2k3(const float *dec /*[n_dec][n_ch][2]*/, uint32_t n_dec, uint32_t
 					if(ret < 0) { w->status = VDL2_ERR_FEC_BAD; for(uint32_t q = r + 1; q < w->num_blocks; q++) w->rs_ret[q] = -128; break; }
 					if(ret > 0) w->fec_corr += ret - (6 - nfec);
 				}
-				if(w->status == VDL2_BURST_OK) vdl2_burst_unstuff(*w);
+				if(w->status == VDL2_BURST_OK) unstuff_both(*w);
 				uint32_t off = 0;
 				for(uint32_t k = 0; k < w->n_frames; k++) { w->fcrc[k] = vdl2_crc16_tab(&w->frames[off], w->flen[k], crc_table()); off += w->flen[k]; }
 			}
@@ -209,6 +228,7 @@ int hostsim_k2k3(const float *dec /*[n_dec][n_ch][2]*/, uint32_t n_dec, uint32_t
 	*n_events = ctl.n_events < event_cap ? ctl.n_events : event_cap;
 	int ovf = (int)ctl.pool_overflows;
 	delete w; delete h;
+	if(g_unstuff_disagree) return -100;
 	return ovf;
 }
 
@@ -232,8 +252,9 @@ int hostsim_k3(const uint8_t *bits, uint32_t nbits, uint32_t datalen_bits, uint8
 			if(w.rs_ret[r] < 0) { w.status = VDL2_ERR_FEC_BAD; for(uint32_t q = r + 1; q < w.num_blocks; q++) w.rs_ret[q] = -128; break; }
 			if(w.rs_ret[r] > 0) w.fec_corr += w.rs_ret[r] - (6 - nfec);
 		}
-		if(w.status == VDL2_BURST_OK) vdl2_burst_unstuff(w);
+		if(w.status == VDL2_BURST_OK) unstuff_both(w);
 	}
+	if(g_unstuff_disagree) return -100;
 	*n_frames = w.n_frames; *fec_corr = w.fec_corr;
 	for(int r = 0; r < 9; r++) rs_ret9[r] = (int8_t)w.rs_ret[r];
 	uint32_t off = 0;
@@ -251,6 +272,27 @@ int hostsim_rs_verify(uint8_t *block255, int fec_octets) {
 	static host_tables *h = nullptr;
 	if(!h) { h = new host_tables(); memset(h, 0, sizeof(*h)); make_gf(h->t); }
 	return vdl2_rs_verify(block255, fec_octets, h->t.gf_exp, h->t.gf_log, rootmul_table(h));
+}
+/* the warp-cooperative form K3 runs (vdl2_kernels.cu: k3_rs_block), with the 32 lanes emulated by a loop: syndromes
+ * as the XOR of the lanes' partial sums, Chien search as the lanes' position masks merged in position order */
+int hostsim_rs_verify_lanes(uint8_t *block255, int fec_octets) {
+	static host_tables *h = nullptr;
+	if(!h) { h = new host_tables(); memset(h, 0, sizeof(*h)); make_gf(h->t); }
+	if(fec_octets == 0) return 0;
+	uint64_t acc = 0;
+	for(uint32_t lane = 0; lane < 32; lane++) acc ^= vdl2_rs_syndrome_partial(block255, lane, h->t.gf_exp, h->t.gf_log, rootmul_table(h));
+	if(acc == 0) return 0;
+	uint8_t S[6], lambda[7];
+	for(int i = 0; i < 6; i++) S[i] = (uint8_t)(acc >> (8 * i));
+	const int deg = vdl2_rs_locator(S, fec_octets, h->t.gf_exp, h->t.gf_log, lambda);
+	uint32_t masks[32];
+	for(uint32_t lane = 0; lane < 32; lane++) masks[lane] = vdl2_rs_chien_lane(lambda, deg, lane, h->t.gf_exp, h->t.gf_log);
+	int root[256], count = 0;
+	for(uint32_t k = 0; k < 8; k++)
+		for(uint32_t lane = 0; lane < 32; lane++)
+			if(masks[lane] & (1u << k)) root[count++] = (int)(lane + 1u + 32u * k);
+	if(deg != count) return -1;
+	return vdl2_rs_forney(block255, S, lambda, deg, root, count, h->t.gf_exp, h->t.gf_log);
 }
 uint32_t hostsim_header_fix(uint32_t word, uint32_t *syndrome) {
 	uint32_t s = vdl2_header_syndrome(word);

@@ -32,6 +32,7 @@ def lib():
                                    "-I", _CSRC, "-o", so, deps[0]])
         _LIB = C.CDLL(so)
         _LIB.hostsim_rs_verify.argtypes = [C.c_void_p, C.c_int]
+        _LIB.hostsim_rs_verify_lanes.argtypes = [C.c_void_p, C.c_int]
         _LIB.hostsim_crc16.restype = C.c_uint16
         _LIB.hostsim_crc16.argtypes = [C.c_void_p, C.c_uint32]
         _LIB.hostsim_header_fix.restype = C.c_uint32
