@@ -1,5 +1,5 @@
 /*
- * vdl2_fastmath.cuh — (float)atan2((double)im, (double)re) and hypotf() of a decimated sample without the
+ * vdl2_fastmath.cuh — (float)atan2((double)im, (double)re) and hypotf(re, im) of a decimated sample without the
  * general-purpose libm routines.
  *
  * The reference obtains a sample's phase as `atan2(im, re)` in double and narrows it to float on store
@@ -107,7 +107,11 @@ VDL2_FM_HD float vdl2_phase_fast(float re, float im, const double *tab, int *slo
 	const double dmx = (double)mx, dmn = (double)mn;
 	const double num = vdl2_fm_fma(-c, dmx, dmn);          /* exact */
 	const double den = vdl2_fm_fma(c, dmn, dmx);           /* exact */
+#ifdef VDL2_FM_RCP_SEED_OVERRIDE
+	double r = VDL2_FM_RCP_SEED_OVERRIDE(den);        /* tools/check_fastmath.cpp: a deliberately perturbed seed */
+#else
 	double r = vdl2_fm_rcp_seed(den);
+#endif
 	r = vdl2_fm_fma(r, vdl2_fm_fma(-den, r, 1.0), r);
 	r = vdl2_fm_fma(r, vdl2_fm_fma(-den, r, 1.0), r);
 	double t = num * r;
@@ -138,6 +142,49 @@ VDL2_FM_HD float vdl2_phase_fast(float re, float im, const double *tab, int *slo
 #else
 	return copysignf(f, im);
 #endif
+}
+
+/* hypotf(re, im) as glibc evaluates it for finite arguments, (float)sqrt((double)re*re + (double)im*im) (src/demod.c:238):
+ * the sum is formed exactly as there (both squares are exact in double, one rounding), the square root by two Newton
+ * steps on the hardware seed (error < 2 ulp of the double) and the same rounding-boundary test as above decides
+ * whether the narrowed float can be trusted; otherwise *slow is set and the caller takes the IEEE square root. */
+VDL2_FM_HD double vdl2_fm_rsqrt_seed(double d) {
+#if defined(__CUDA_ARCH__)
+	double r;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));     /* MUFU.RSQ64H */
+	return r;
+#else
+	return (double)(1.0f / sqrtf((float)d));
+#endif
+}
+
+VDL2_FM_HD float vdl2_mag_fast(float re, float im, int *slow) {
+	const float ax = fabsf(re), ay = fabsf(im);
+	const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+	if(!(ax <= 1.0e18f && ay <= 1.0e18f && mx >= 1.0e-18f)) { *slow = 1; return 0.0f; }     /* NaN, inf, zero, extremes */
+	const double dmx = (double)mx, dmn = (double)mn;
+	const double s = vdl2_fm_fma(dmx, dmx, dmn * dmn);         /* == fl64(re^2 + im^2): both squares are exact */
+#ifdef VDL2_FM_RSQRT_SEED_OVERRIDE
+	const double y = VDL2_FM_RSQRT_SEED_OVERRIDE(s);
+#else
+	const double y = vdl2_fm_rsqrt_seed(s);
+#endif
+	double g = s * y, h = 0.5 * y;
+	double e = vdl2_fm_fma(-g, h, 0.5);
+	g = vdl2_fm_fma(g, e, g); h = vdl2_fm_fma(h, e, h);
+	e = vdl2_fm_fma(-g, h, 0.5);
+	g = vdl2_fm_fma(g, e, g); h = vdl2_fm_fma(h, e, h);
+	g = vdl2_fm_fma(vdl2_fm_fma(-g, g, s), h, g);              /* residual correction: g within an ulp of sqrt(s) */
+	uint64_t bits;
+#if defined(__CUDA_ARCH__)
+	bits = (uint64_t)__double_as_longlong(g);
+#else
+	memcpy(&bits, &g, 8);
+#endif
+	const uint32_t drop = (uint32_t)bits & 0x1FFFFFFFu;
+	const uint32_t dist = drop > 0x10000000u ? drop - 0x10000000u : 0x10000000u - drop;
+	*slow = dist < 512u ? 1 : 0;
+	return (float)g;
 }
 
 #endif

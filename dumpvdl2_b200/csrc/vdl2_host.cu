@@ -80,7 +80,7 @@ struct vdl2gpu_ctx {
 	uint32_t n_streams = 1, ch_per_stream = 0;          /* independent-streams mode: n_streams > 1, channels [s*C, (s+1)*C) on stream s */
 	bool lane_streams = false;                          /* C == 1: samples kept time-major across streams, one lane per stream in K1 */
 	uint32_t raw_bytes = 0;                             /* size of each slot's raw staging buffers (allocated on the first host submit) */
-	int k1_variant = 2, k2_variant = 2, k2a_mode = 1;   /* A/B knobs (VDL2GPU_K1_VARIANT, VDL2GPU_K2_VARIANT, VDL2GPU_K2A), read at create */
+	int k1_variant = 2, k2_variant = 5, k2a_mode = 1;   /* A/B knobs (VDL2GPU_K1_VARIANT, VDL2GPU_K2_VARIANT, VDL2GPU_K2A), read at create */
 	bool use_graphs = true;
 	uint64_t overflows_reported = 0;
 	host_tables tab;
@@ -307,10 +307,6 @@ extern "C" int vdl2gpu_create(const vdl2gpu_config *cfg, vdl2gpu_ctx **out) {
 		snprintf(g_last_error, sizeof(g_last_error), "bad vdl2gpu_config (sample_rate must be 105000*oversample)");
 		return VDL2GPU_EINVAL;
 	}
-	if((uint64_t)(cfg->max_chunk_bytes ? cfg->max_chunk_bytes : (1u << 20)) * (cfg->n_streams ? cfg->n_streams : 1u) >= (1ull << 32)) {
-		snprintf(g_last_error, sizeof(g_last_error), "n_streams x max_chunk_bytes must stay below 4 GiB");
-		return VDL2GPU_ETOOBIG;
-	}
 	vdl2gpu_ctx *c = new vdl2gpu_ctx();
 	int rc = create_impl(cfg, c);
 	if(rc != VDL2GPU_OK) { free_ctx(c); *out = nullptr; return rc; }
@@ -449,6 +445,10 @@ static int deliver(vdl2gpu_ctx *c, vdl2gpu_frame_cb cb, void *user) {
 static int ensure_raw(vdl2gpu_ctx *c, chunk_slot &s) {
 	if(s.h_raw) return VDL2GPU_OK;
 	const size_t bytes = (size_t)c->cfg.max_chunk_bytes * c->n_streams;
+	if(bytes >= ((size_t)1 << 32)) {          /* the host path stages all streams of a chunk in one pinned buffer */
+		snprintf(g_last_error, sizeof(g_last_error), "vdl2gpu_submit: n_streams x max_chunk_bytes must stay below 4 GiB (use vdl2gpu_submit_device)");
+		return VDL2GPU_ETOOBIG;
+	}
 	CU(cudaHostAlloc((void **)&s.h_raw, bytes, cudaHostAllocDefault));
 	CU(cudaMalloc(&s.d_raw, bytes));
 	return VDL2GPU_OK;
@@ -970,7 +970,7 @@ struct vdl2gpu_stage {
 	uint32_t decim_cnt = 0;
 	uint64_t total_dec = 0;
 	uint32_t events_read = 0;
-	int k1_variant = 2, k2_variant = 2, k2a_mode = 1;
+	int k1_variant = 2, k2_variant = 5, k2a_mode = 1;
 	vdl2_tables *d_tab = nullptr;
 	uint32_t *d_k1 = nullptr, *d_k2 = nullptr, *d_counters = nullptr, *d_ready = nullptr;
 	float *d_ring = nullptr, *d_phase = nullptr, *d_mag = nullptr, *d_hist_tmp = nullptr;

@@ -17,6 +17,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <mutex>
+#include <type_traits>
 #include "vdl2_core.cuh"
 #include "vdl2_fastmath.cuh"
 #include "vdl2_kernels.h"
@@ -230,7 +231,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 			:: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-#define K1P_TILE_GROUPS(OS) (640 / (OS))        /* 640 samples = 5 KB of float2 per tile */
+#define K1P_TILE_GROUPS(OS) ((640 / (OS)) & ~1)  /* <= 640 samples = 5 KB of float2 per tile; an even number of groups keeps every
+                                                  * tile an even number of samples = a multiple of 16 bytes for the bulk copy */
 
 /* BLOCK = 128: the four warps of an SM's four sub-partitions share one block, i.e. one copy of the sample tiles and of
  * the NCO table.  The table is then kept EIGHT times (33 KB), copy c holding entry i at float4 index 8 i + c, and lane l
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	constexpr int TG = K1P_TILE_GROUPS(OS);
 	constexpr int NLUT = BLOCK >= 128 ? 8 : 1;                    /* table copies */
 	__shared__ float4 s_lut[257 * NLUT];
-	__shared__ __align__(128) float2 s_tiles[2][TG * OS];
+	__shared__ __align__(128) float2 s_tiles[2][TG * OS + 2];
 	__shared__ __align__(8) uint64_t s_bar[2];
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ch = blockIdx.x * BLOCK + tid;
@@ -288,16 +290,26 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	/* body: whole groups, staged through shared memory tile by tile */
 	const uint32_t n_groups = (n_pairs - pos) / OS;
 	const uint32_t n_tiles = (n_groups + TG - 1) / TG;
-	/* prologue: the first two tiles are requested at once; tile t lands in buffer t & 1, its mbarrier phase is (t >> 1) & 1 */
-	if(tid == 0) {
-		for(uint32_t t = 0; t < 2 && t < n_tiles; t++) {
-			const uint32_t ngt = min((uint32_t)TG, n_groups - t * TG);
-			tma_load_tile(s_tiles[t], samples + pos + (size_t)t * TG * OS, ngt * OS * (uint32_t)sizeof(float2), &s_bar[t]);
-		}
-	}
+	/* The bulk copy wants 16-byte aligned addresses and sizes, a sample is 8 bytes: when the first body sample sits on an
+	 * odd element (odd decimation phase on entry), every tile is fetched from one sample earlier and read from element 1
+	 * on (`mis`); an odd trailing sample of the last tile is copied by hand.  Tile t lands in buffer t & 1, its mbarrier
+	 * phase is (t >> 1) & 1. */
+	const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(samples + pos) >> 3) & 1u);
+	auto request_tile = [&](uint32_t t, uint32_t buf) {              /* thread 0 only */
+		const uint32_t n = min((uint32_t)TG, n_groups - t * TG) * OS + mis;
+		const float2 *src = samples + head + (size_t)t * TG * OS - mis;
+		tma_load_tile(s_tiles[buf], src, (n & ~1u) * (uint32_t)sizeof(float2), &s_bar[buf]);
+		if(n & 1u) s_tiles[buf][n - 1] = src[n - 1];
+	};
+	if(tid == 0)
+		for(uint32_t t = 0; t < 2 && t < n_tiles; t++) request_tile(t, t);
+	__syncthreads();
+	/* the tile loop, compiled twice: with the tile known to start on element 0 the compiler fetches two samples per
+	 * LDS.128; the misaligned case (odd decimation phase on entry) reads from element 1 with 64-bit loads */
+	auto tile_loop = [&](auto MIS) {
 	for(uint32_t g0 = 0, tile = 0; g0 < n_groups; g0 += TG, tile++) {
 		const uint32_t ng = min((uint32_t)TG, n_groups - g0);
-		const float2 *s_tile = s_tiles[tile & 1u];
+		const float2 *s_tile = s_tiles[tile & 1u] + decltype(MIS)::value;
 		mbar_wait(&s_bar[tile & 1u], (tile >> 1) & 1u);
 		if(active) {
 			for(uint32_t g = 0; g < ng; g++) {
@@ -352,11 +364,10 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 		m += ng;
 		pos += ng * OS;
 		__syncthreads();                                           /* every warp is done with this buffer */
-		if(tid == 0 && tile + 2 < n_tiles) {
-			const uint32_t ngn = min((uint32_t)TG, n_groups - (tile + 2) * TG);
-			tma_load_tile(s_tiles[tile & 1u], samples + pos + (size_t)TG * OS, ngn * OS * (uint32_t)sizeof(float2), &s_bar[tile & 1u]);
-		}
+		if(tid == 0 && tile + 2 < n_tiles) request_tile(tile + 2, tile & 1u);
 	}
+	};
+	if(mis) tile_loop(std::integral_constant<int, 1>{}); else tile_loop(std::integral_constant<int, 0>{});
 	/* tail: fewer than OS samples left */
 	if(active) {
 		for(; pos < n_pairs; pos++) {
@@ -508,9 +519,10 @@ __global__ void __launch_bounds__(K1L_BLOCK) k1_mix_iir_decimate_lanes(vdl2_k1_p
  * (time, channel) element: the double-precision atan2/sqrt run at full occupancy here instead of inside the
  * sequential per-channel walk of K2.
  * FAST: the phase comes from vdl2_phase_fast (vdl2_fastmath.cuh: 9 break points, one division, degree-5 polynomial,
- * ~22 FP64 operations) whose float result is the correctly rounded fl32(atan2); only when it reports that the double
- * lies within 2^-44 of a float rounding boundary, or for zero / non-finite / extreme inputs (about one sample in
- * 3e5), the libdevice routine decides, as it does for every sample when FAST is off. */
+ * ~22 FP64 operations) whose float result is the correctly rounded fl32(atan2), the magnitude from vdl2_mag_fast
+ * (exact sum of squares, Newton square root); only when one of them reports that its double lies within 2^-44 of a
+ * float rounding boundary, or for zero / non-finite / extreme inputs (about one sample in 3e5), the libdevice
+ * routine / the IEEE square root decide, as they do for every sample when FAST is off. */
 __constant__ double c_atan_tab[VDL2_ATAN_TABLE_DOUBLES] = VDL2_ATAN_TABLE_INIT;
 
 template<bool FAST>
@@ -526,16 +538,19 @@ __global__ void __launch_bounds__(256) k2a_phase_mag(const float2 *__restrict__ 
 	uint32_t i = blockIdx.x * 256u + threadIdx.x;
 	if(i >= n_elems) return;
 	const float2 d = dec[i];
-	float ph;
+	float ph, mg;
 	if(FAST) {
-		int slow;
-		ph = vdl2_phase_fast(d.x, d.y, s_atan, &slow);
-		if(slow) ph = vdl2_phase_of(d.x, d.y);
+		int slow_p, slow_m;
+		ph = vdl2_phase_fast(d.x, d.y, s_atan, &slow_p);
+		mg = vdl2_mag_fast(d.x, d.y, &slow_m);
+		if(slow_p) ph = vdl2_phase_of(d.x, d.y);
+		if(slow_m) mg = vdl2_mag_of(d.x, d.y);
 	} else {
 		ph = vdl2_phase_of(d.x, d.y);
+		mg = vdl2_mag_of(d.x, d.y);
 	}
 	phase[i] = ph;
-	mag[i] = vdl2_mag_of(d.x, d.y);
+	mag[i] = mg;
 }
 
 /* carry the last 160 phase rows over to the front of the plane for the next chunk: rows [n_dec, n_dec+160) -> [0, 160) */
@@ -568,11 +583,21 @@ __device__ __forceinline__ void k2_cp_async_wait_all() { asm volatile("cp.async.
  * block inputs loaded one block ahead into registers; 3 phase ring, block inputs staged one block ahead in shared
  * memory by cp.async (VDL2GPU_K2_VARIANT=4); 4 phase ring, ALL block inputs (phase, magnitude, decimated samples)
  * staged one block ahead by cp.async (VDL2GPU_K2_VARIANT=5) */
+/* staging floats per thread: mode 4 two buffers of (12 phase + 12 magnitude + 12 float2 samples), mode 3 two buffers of 16 */
+#define K2_STAGE_FLOATS(MODE) ((MODE) == 4 ? 2 * (2 * VDL2_WALK_BLOCK + 2 * VDL2_WALK_BLOCK) : (MODE) == 3 ? 2 * 16 : 0)
+#define K2_SMEM_BYTES(BLOCK, MODE) ((VDL2_SYNC_BUFLEN + K2_STAGE_FLOATS(MODE)) * (BLOCK) * 4 + 36 * 4 + VDL2_UNWRAP_STATES * 6 * 4)
+
 template<int BLOCK, bool BLOCKED, int MODE>
 __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
-	__shared__ float s_ring[VDL2_SYNC_BUFLEN * BLOCK];
-	__shared__ float s_consts[33];
-	__shared__ __align__(8) uint32_t s_unwrap[MODE ? VDL2_UNWRAP_STATES * 6 : 2];
+	/* dynamic shared memory (K2_SMEM_BYTES): phase ring [160][BLOCK], staging area (modes 3 and 4), constants, unwrap table.
+	 * BLOCK = 128: the four warps of a block sit on the four sub-partitions of one SM, one each, exactly like K1's, so
+	 * that a K1 block and a K2 block always fit side by side (a 250-register warp takes half a sub-partition's register
+	 * file: with one-warp blocks two of them could land on the same sub-partition and lock the other kernel out). */
+	extern __shared__ __align__(16) unsigned char k2_smem[];
+	float *s_ring = reinterpret_cast<float *>(k2_smem);
+	float *s_stage_area = s_ring + VDL2_SYNC_BUFLEN * BLOCK;                     /* K2_STAGE_FLOATS(MODE) * BLOCK floats */
+	float *s_consts = s_stage_area + K2_STAGE_FLOATS(MODE) * BLOCK;
+	uint32_t *s_unwrap = reinterpret_cast<uint32_t *>(s_consts + 36);
 	static_assert(MODE >= 0 && MODE <= 4, "walk mode");
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ch = blockIdx.x * BLOCK + tid;
@@ -622,8 +647,8 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 			 * block ahead in shared memory by cp.async (36 LDGSTS per lane and block): neither the searching path nor the
 			 * symbol slicing of a channel that is inside a burst ever waits for global memory, whatever mix of states the 32
 			 * channels of the warp are in. */
-			__shared__ float s_st[2][2 * VDL2_WALK_BLOCK][BLOCK];          /* rows 0..11 phase, 12..23 magnitude */
-			__shared__ float2 s_sd[2][VDL2_WALK_BLOCK][BLOCK];
+			float (*s_st)[2 * VDL2_WALK_BLOCK][BLOCK] = reinterpret_cast<float (*)[2 * VDL2_WALK_BLOCK][BLOCK]>(s_stage_area);   /* [2]: rows 0..11 phase, 12..23 magnitude */
+			float2 (*s_sd)[VDL2_WALK_BLOCK][BLOCK] = reinterpret_cast<float2 (*)[VDL2_WALK_BLOCK][BLOCK]>(s_stage_area + 2 * 2 * VDL2_WALK_BLOCK * BLOCK);
 			auto stage = [&](uint32_t buf, size_t o) {
 #pragma unroll
 				for(int t = 0; t < VDL2_WALK_BLOCK; t++) {
@@ -652,8 +677,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 			k2_cp_async_wait_all();
 		} else if(MODE == 3) {
 			/* stage[buf][k][lane]: k = 0..11 the block's phases, 12..15 the magnitudes at the predicted attempt offsets */
-			__shared__ float s_stage[2 * 16 * BLOCK];
-			float *stg = s_stage + tid;
+			float *stg = s_stage_area + tid;                         /* [2][16][BLOCK] */
 			int first_cur = 0;                                   /* attempt offset the buffer about to be consumed was staged for */
 			uint32_t b = 0;
 			if(m + VDL2_WALK_BLOCK <= n_dec) {
@@ -922,7 +946,7 @@ __global__ void k_rs_verify(uint8_t *blocks, const int32_t *fec_octets, uint32_t
  * ---------------------------------------------------------------------------------------------- */
 #define K1_BLOCK 128     /* four warps = the four sub-partitions of an SM share the sample tiles and the 8-copy NCO table */
 #define K1_BLOCK1 32     /* one warp per block: independent streams with fewer than 128 channels per stream */
-#define K2_BLOCK 32
+#define K2_BLOCK 128     /* four warps per block, one per sub-partition: see k2_sync_slice */
 
 /* One shared-memory carve-out for every kernel of the chain, so that an SM never has to drain to re-partition
  * its L1/shared memory when kernels of two chunks are resident together (the default two-stream pipeline, see
@@ -963,12 +987,10 @@ extern "C" int vdl2_kernels_init_device(int device) {
 		cudaFuncSetAttribute(k1_mix_iir_decimate_lanes<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1L_SMEM_BYTES);
 		vdl2_set_carveout(k2a_phase_mag<true>, pct);
 		vdl2_set_carveout(k2a_phase_mag<false>, pct);
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 4>, pct);
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 3>, pct);
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 2>, pct);
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 1>, pct);
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, true, 0>, pct);
-		vdl2_set_carveout(k2_sync_slice<K2_BLOCK, false, 0>, pct);
+#define K2_SETUP(BLOCKED, MODE) do { vdl2_set_carveout(k2_sync_slice<K2_BLOCK, BLOCKED, MODE>, pct); \
+		cudaFuncSetAttribute(k2_sync_slice<K2_BLOCK, BLOCKED, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_BYTES(K2_BLOCK, MODE)); } while(0)
+		K2_SETUP(true, 4); K2_SETUP(true, 3); K2_SETUP(true, 2); K2_SETUP(true, 1); K2_SETUP(true, 0); K2_SETUP(false, 0);
+#undef K2_SETUP
 		vdl2_set_carveout(k_copy_rows, pct);
 		vdl2_set_carveout(k_copy_hist, pct);
 		vdl2_set_carveout(k3_burst_fec, pct);
@@ -1041,19 +1063,21 @@ extern "C" int vdl2_launch_k2a(const vdl2_k2_params *p, cudaStream_t st) {
 	return (int)cudaGetLastError();
 }
 
-/* variant: 0 per-sample walk; 1 blocked, phase plane, TwoSum unwrap; 3 blocked, phase ring, block inputs one block
- * ahead in registers; 4 the same with cp.async staging; 5 phase ring with every block input staged by cp.async;
- * anything else (2): blocked, phase plane, table unwrap */
+/* variant: 0 per-sample walk; 1 blocked, phase plane, TwoSum unwrap; 2 blocked, phase plane, table unwrap; 3 blocked,
+ * phase ring, block inputs one block ahead in registers; 4 the same with cp.async staging; anything else (5, the
+ * default): phase ring with every block input (phase, magnitude, samples) staged one block ahead by cp.async */
 extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
 	if(p->n_dec == 0 || p->n_ch == 0) return 0;
 	const uint32_t blocks = (p->n_ch + K2_BLOCK - 1) / K2_BLOCK;
 	const uint32_t variant = p->variant;
-	if(variant == 0) k2_sync_slice<K2_BLOCK, false, 0><<<blocks, K2_BLOCK, 0, st>>>(*p);
-	else if(variant == 1) k2_sync_slice<K2_BLOCK, true, 0><<<blocks, K2_BLOCK, 0, st>>>(*p);
-	else if(variant == 3) k2_sync_slice<K2_BLOCK, true, 2><<<blocks, K2_BLOCK, 0, st>>>(*p);
-	else if(variant == 4) k2_sync_slice<K2_BLOCK, true, 3><<<blocks, K2_BLOCK, 0, st>>>(*p);
-	else if(variant == 5) k2_sync_slice<K2_BLOCK, true, 4><<<blocks, K2_BLOCK, 0, st>>>(*p);
-	else k2_sync_slice<K2_BLOCK, true, 1><<<blocks, K2_BLOCK, 0, st>>>(*p);
+#define K2_GO(BLOCKED, MODE) k2_sync_slice<K2_BLOCK, BLOCKED, MODE><<<blocks, K2_BLOCK, K2_SMEM_BYTES(K2_BLOCK, MODE), st>>>(*p)
+	if(variant == 0) K2_GO(false, 0);
+	else if(variant == 1) K2_GO(true, 0);
+	else if(variant == 2) K2_GO(true, 1);
+	else if(variant == 3) K2_GO(true, 2);
+	else if(variant == 4) K2_GO(true, 3);
+	else K2_GO(true, 4);                       /* default (5, or any unknown value) */
+#undef K2_GO
 	return (int)cudaGetLastError();
 }
 

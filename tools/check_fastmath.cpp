@@ -16,14 +16,15 @@
 #include <atomic>
 
 static thread_local double g_seed_err = 0.0;
-#define vdl2_fm_rcp_seed vdl2_fm_rcp_seed_unused
+static inline double perturbed_rcp(double d) { return (double)(1.0f / (float)d) * (1.0 + g_seed_err); }
+static inline double perturbed_rsqrt(double d) { return (double)(1.0f / sqrtf((float)d)) * (1.0 + g_seed_err); }
+#define VDL2_FM_RCP_SEED_OVERRIDE(d) perturbed_rcp(d)
+#define VDL2_FM_RSQRT_SEED_OVERRIDE(d) perturbed_rsqrt(d)
 #include "vdl2_fastmath.cuh"
-#undef vdl2_fm_rcp_seed
-static inline double vdl2_fm_rcp_seed(double d) { return (double)(1.0f / (float)d) * (1.0 + g_seed_err); }
 // second copy of the routine bound to the perturbed seed
 
 static const double TAB[VDL2_ATAN_TABLE_DOUBLES] = VDL2_ATAN_TABLE_INIT;
-static std::atomic<uint64_t> n_total{0}, n_slow{0}, n_bad{0}, n_slow_mode[8];
+static std::atomic<uint64_t> n_total{0}, n_slow{0}, n_bad{0}, n_slow_mode[8], n_mag_slow{0}, n_mag_bad{0};
 
 static void worker(int id, uint64_t n) {
 	std::mt19937_64 rng(0x56444C32ull + id);
@@ -59,6 +60,13 @@ static void worker(int id, uint64_t n) {
 		int slow = 0;
 		const float got = vdl2_phase_fast(re, im, TAB, &slow);
 		const float want = (float)atan2((double)im, (double)re);
+		{
+			int ms = 0;
+			const float gm = vdl2_mag_fast(re, im, &ms);
+			const float wm = (float)sqrt((double)re * (double)re + (double)im * (double)im);
+			if(ms) n_mag_slow++;
+			else { uint32_t a, b; memcpy(&a, &gm, 4); memcpy(&b, &wm, 4); if(a != b) { if(n_mag_bad++ < 20) printf("MAG MISMATCH re=%a im=%a got=%a want=%a\n", re, im, gm, wm); } }
+		}
 		if(slow) { slow_c++; n_slow_mode[mode]++; continue; }
 		uint32_t a, b; memcpy(&a, &got, 4); memcpy(&b, &want, 4);
 		if(a != b) {
@@ -87,6 +95,7 @@ int main(int argc, char **argv) {
 	}
 	printf("samples %llu  slow %llu (%.3g)  mismatches %llu  special mismatches %d\n", (unsigned long long)n_total.load(),
 			(unsigned long long)n_slow.load(), (double)n_slow.load() / (double)n_total.load(), (unsigned long long)n_bad.load(), sp_bad);
+	printf("hypot: slow %llu (%.3g) mismatches %llu\n", (unsigned long long)n_mag_slow.load(), (double)n_mag_slow.load() / (double)n_total.load(), (unsigned long long)n_mag_bad.load());
 	for(int m = 0; m < 8; m++) printf("  mode %d slow rate %.3g\n", m, (double)n_slow_mode[m].load() / ((double)n_total.load() / 8));
-	return (n_bad.load() || sp_bad) ? 1 : 0;
+	return (n_bad.load() || sp_bad || n_mag_bad.load()) ? 1 : 0;
 }
