@@ -61,3 +61,34 @@ def test_config5_16384_channels_replica_consistency():
     for slot in range(64):                  # ... and all replicas of every slot against each other (counters)
         block = cnt[slot * 256:(slot + 1) * 256]
         assert (block == block[0]).all() and np.array_equal(block[0], ocnt[slot])
+
+
+def test_config3_256_channels_full_10_seconds():
+    """BASELINE config 3 as specified: 10 s of 2.1 Msps cu8, 256 channels = 64 slots x 4 replicas, Poisson
+    bursts 2/s/slot, Es/N0 20 dB, seed 0x56444C33.  The oracle decodes the 64 slot channels; every one of the 256 GPU
+    channels must carry exactly its slot's frames, metadata and counters."""
+    c = cases.case_replicas(n_slots=64, n_rep=1, duration=10.0, seed=0x56444C33, rate_hz=2.0)
+    o = util.run_oracle(c)
+    want = {}
+    for f in o.frames():
+        want.setdefault(f.channel, []).append(f)
+    n_rep = 4
+    freqs = [f for f in c["freqs"] for _ in range(n_rep)]
+    g = vd.Vdl2Channels(FS, 20, vd.FMT_U8, CENTER, freqs, max_chunk_bytes=c["chunk"])
+    g.process_chunked(util.case_bytes(c), c["chunk"])
+    got = {}
+    for f in g.flush():
+        got.setdefault(f.channel, []).append(f)
+    st = g.stats()
+    assert st["pool_overflows"] == 0 and st["out_overflows"] == 0
+    n = 0
+    for ch in range(64 * n_rep):
+        mine = got.get(ch, [])
+        for f in mine:
+            f.channel = ch // n_rep
+        util.assert_frames_equal(mine, want.get(ch // n_rep, []), f"channel {ch}")
+        n += len(mine)
+    assert n == n_rep * len(o.frames()) and n > 1500
+    cnt, ocnt = g.channel_counters(), o.counters()
+    for ch in range(64 * n_rep):
+        assert np.array_equal(cnt[ch], ocnt[ch // n_rep])
