@@ -87,6 +87,7 @@ def load_library():
     L.vdl2gpu_enable_timing.argtypes = [C.c_void_p, C.c_int]
     L.vdl2gpu_get_kernel_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.vdl2gpu_get_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.vdl2gpu_debug_block_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.vdl2gpu_strerror.restype = C.c_char_p
     L.vdl2gpu_strerror.argtypes = [C.c_int]
     L.vdl2gpu_last_error.restype = C.c_char_p
@@ -316,6 +317,12 @@ class Vdl2Channels:
         """rows of [chunk, front start, K0|K1, K1 end, back start, K2a|K2, K2|K3, K3 end] (ms) for the timed chunks"""
         a = np.zeros((cap, 8), np.float32)
         n = _check(self.L, self.L.vdl2gpu_get_timeline(self.h, a.ctypes.data, cap), "vdl2gpu_get_timeline")
+        return a[:n]
+
+    def block_trace(self, cap=1 << 16):
+        """rows of [kernel, block, smid, 0, start_ns, end_ns] (needs VDL2GPU_BLOCK_TRACE=1 when the object was created)"""
+        a = np.zeros((cap, 6), np.uint64)
+        n = _check(self.L, self.L.vdl2gpu_debug_block_trace(self.h, a.ctypes.data, cap), "vdl2gpu_debug_block_trace")
         return a[:n]
 
     def kernel_ms(self):

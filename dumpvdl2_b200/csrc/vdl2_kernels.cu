@@ -22,6 +22,18 @@
 #include "vdl2_fastmath.cuh"
 #include "vdl2_kernels.h"
 
+/* block scheduling trace: where and when a block ran (diagnostic, off unless the context was created with VDL2GPU_BLOCK_TRACE=1) */
+__device__ __forceinline__ uint64_t vdl2_globaltimer() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ uint32_t vdl2_smid() { uint32_t s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
+__device__ __forceinline__ int vdl2_trace_begin(vdl2_block_trace *t, uint32_t kernel) {
+	if(t == nullptr) return -1;
+	const uint32_t k = atomicAdd(&t->n, 1u);
+	if(k >= t->cap) return -1;
+	t->rec[k].kernel = kernel; t->rec[k].block = blockIdx.x; t->rec[k].smid = vdl2_smid(); t->rec[k].t_start = vdl2_globaltimer(); t->rec[k].t_end = 0;
+	return (int)k;
+}
+__device__ __forceinline__ void vdl2_trace_end(vdl2_block_trace *t, int k) { if(k >= 0) t->rec[k].t_end = vdl2_globaltimer(); }
+
 /* ------------------------------------------------------------------------------------------------
  * K0: sample conversion.  Output: float2 {re, im} per complex sample (src/demod.c:339-365).
  * ---------------------------------------------------------------------------------------------- */
@@ -109,6 +121,14 @@ __device__ __forceinline__ void k1_store_state(const vdl2_k1_params &p, uint32_t
 	st[K1_PHI * s + ch] = phi & 0xFFFFFFu;
 }
 
+/* slot (index into every per-channel array) -> public channel number and activity: a warp holds `lanes` channels in its
+ * first `lanes` lanes */
+__device__ __forceinline__ bool vdl2_slot_channel(uint32_t slot, uint32_t lanes, uint32_t n_ch, uint32_t &chan) {
+	const uint32_t lane = slot & 31u;
+	chan = (slot >> 5) * lanes + lane;
+	return lane < lanes && chan < n_ch;
+}
+
 /* independent-streams mode: all channels of a block belong to stream (first channel / ch_per_stream); a block never
  * straddles two streams because ch_per_stream is a multiple of the block size (checked by the launcher) */
 __device__ __forceinline__ const float2 *k1_stream_of(const vdl2_k1_params &p, uint32_t first_ch) {
@@ -121,7 +141,8 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_scalar(vdl2_k1_para
 	__shared__ float2 s_tile[K1_TILE];
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ch = blockIdx.x * BLOCK + tid;
-	const bool active = ch < p.n_ch;
+	uint32_t chan;
+	const bool active = vdl2_slot_channel(ch, p.lanes, p.n_ch, chan);
 	const uint32_t n_pairs = p.ca ? p.ca->n_pairs : p.n_pairs, cnt0 = p.ca ? p.ca->cnt0 : p.cnt0;
 	const float2 *samples = k1_stream_of(p, blockIdx.x * BLOCK);
 	for(uint32_t i = tid; i < 257; i += BLOCK) s_lut[i] = p.lut[i];
@@ -250,8 +271,10 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	__shared__ __align__(128) float2 s_tiles[2][TG * OS + 2];
 	__shared__ __align__(8) uint64_t s_bar[2];
 	const uint32_t tid = threadIdx.x;
+	const int trace_k = tid == 0 ? vdl2_trace_begin(p.trace_blocks, 1) : -1;
 	const uint32_t ch = blockIdx.x * BLOCK + tid;
-	const bool active = ch < p.n_ch;
+	uint32_t chan;
+	const bool active = vdl2_slot_channel(ch, p.lanes, p.n_ch, chan);
 	const uint32_t n_pairs = p.ca ? p.ca->n_pairs : p.n_pairs, cnt0 = p.ca ? p.ca->cnt0 : p.cnt0;
 	const float2 *samples = k1_stream_of(p, blockIdx.x * BLOCK);
 	for(uint32_t i = tid; i < 257 * NLUT; i += BLOCK) s_lut[i] = p.lut[i / NLUT];
@@ -376,6 +399,7 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 		}
 		k1_store_state(p, ch, f2_lo(x1), f2_lo(x2), f2_hi(x1), f2_hi(x2), f2_lo(y1), f2_lo(y2), f2_hi(y1), f2_hi(y2), phi);
 	}
+	if(tid == 0) vdl2_trace_end(p.trace_blocks, trace_k);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -401,7 +425,8 @@ __global__ void __launch_bounds__(K1L_BLOCK) k1_mix_iir_decimate_lanes(vdl2_k1_p
 	uint64_t *s_bar = reinterpret_cast<uint64_t *>(k1l_smem + 2 * K1L_TILE_ROWS * K1L_BLOCK * 8 + 257 * 8 * 16);
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ch = blockIdx.x * K1L_BLOCK + tid;
-	const bool active = ch < p.n_ch;
+	uint32_t chan;
+	const bool active = vdl2_slot_channel(ch, p.lanes, p.n_ch, chan);
 	const uint32_t n_pairs = p.ca ? p.ca->n_pairs : p.n_pairs, cnt0 = p.ca ? p.ca->cnt0 : p.cnt0;
 	const size_t stride = p.stream_stride;                 /* float2 elements between consecutive samples */
 	const float2 *samples = p.samples + (size_t)blockIdx.x * K1L_BLOCK;      /* this block's 128 columns */
@@ -527,7 +552,7 @@ __constant__ double c_atan_tab[VDL2_ATAN_TABLE_DOUBLES] = VDL2_ATAN_TABLE_INIT;
 
 template<bool FAST>
 __global__ void __launch_bounds__(256) k2a_phase_mag(const float2 *__restrict__ dec, float *__restrict__ phase,
-		float *__restrict__ mag, uint32_t n_elems_p, uint32_t n_chp, const vdl2_chunk_args *__restrict__ ca) {
+		float *__restrict__ mag, uint32_t n_elems_p, uint32_t n_chp, uint32_t lanes, const vdl2_chunk_args *__restrict__ ca) {
 	__shared__ double s_atan[VDL2_ATAN_TABLE_DOUBLES];
 	if(FAST) {
 		/* the break-point table is indexed per lane: shared memory (a __constant__ look-up with divergent indices serialises) */
@@ -536,7 +561,7 @@ __global__ void __launch_bounds__(256) k2a_phase_mag(const float2 *__restrict__ 
 	}
 	const uint32_t n_elems = ca ? ca->n_dec * n_chp : n_elems_p;
 	uint32_t i = blockIdx.x * 256u + threadIdx.x;
-	if(i >= n_elems) return;
+	if(i >= n_elems || (i & 31u) >= lanes) return;            /* n_chp is a multiple of 32: i & 31 is the lane of the slot */
 	const float2 d = dec[i];
 	float ph, mg;
 	if(FAST) {
@@ -600,12 +625,14 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	uint32_t *s_unwrap = reinterpret_cast<uint32_t *>(s_consts + 36);
 	static_assert(MODE >= 0 && MODE <= 4, "walk mode");
 	const uint32_t tid = threadIdx.x;
+	const int trace_k = tid == 0 ? vdl2_trace_begin(p.trace_blocks, 2) : -1;
 	const uint32_t ch = blockIdx.x * BLOCK + tid;
 	if(tid < 16) { s_consts[tid] = p.tables->pr_phase[tid]; s_consts[16 + tid] = p.tables->lr_X[tid]; }
 	if(tid == 0) s_consts[32] = p.tables->lr_denom;
 	if(MODE) for(uint32_t i = tid; i < VDL2_UNWRAP_STATES * 6; i += BLOCK) s_unwrap[i] = p.tables->unwrap_lut[i];
 	__syncthreads();
-	if(ch >= p.n_ch) return;
+	uint32_t chan;                                    /* public channel number (events, burst records); ch = slot */
+	if(!vdl2_slot_channel(ch, p.lanes, p.n_ch, chan)) return;
 	const uint32_t s = p.n_chp;
 	uint32_t *st = p.state;
 	vdl2_chan v;
@@ -671,7 +698,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 #pragma unroll
 				for(int j = 0; j < 4; j++) pf.mg[j] = s_st[b][VDL2_WALK_BLOCK + first + VDL2_SYNC_SKIP * j][tid];
 				pf.first = first; pf.valid = 1;
-				vdl2_walk_block_ring<true>(v, ring, BLOCK, env, ch, dec_base + m, &s_sd[b][0][tid], &s_st[b][0][tid],
+				vdl2_walk_block_ring<true>(v, ring, BLOCK, env, chan, dec_base + m, &s_sd[b][0][tid], &s_st[b][0][tid],
 						&s_st[b][VDL2_WALK_BLOCK][tid], BLOCK, pf, false);
 			}
 			k2_cp_async_wait_all();
@@ -712,7 +739,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 					first_cur = fn;
 				}
 				k2_cp_async_commit();
-				vdl2_walk_block_ring(v, ring, BLOCK, env, ch, dec_base + m, dec + o, phs + o, mgs + o, s, pf, false);
+				vdl2_walk_block_ring(v, ring, BLOCK, env, chan, dec_base + m, dec + o, phs + o, mgs + o, s, pf, false);
 			}
 			k2_cp_async_wait_all();
 		} else if(MODE == 2) {
@@ -725,14 +752,14 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 #pragma unroll 1
 			for(; m + VDL2_WALK_BLOCK <= n_dec; m += VDL2_WALK_BLOCK) {
 				const size_t o = (size_t)m * s;
-				vdl2_walk_block_ring(v, ring, BLOCK, env, ch, dec_base + m, dec + o, phs + o, mgs + o, s, pf,
+				vdl2_walk_block_ring(v, ring, BLOCK, env, chan, dec_base + m, dec + o, phs + o, mgs + o, s, pf,
 						m + 2 * VDL2_WALK_BLOCK <= n_dec);
 			}
 		} else {
 #pragma unroll 1
 			for(; m + VDL2_WALK_BLOCK <= n_dec; m += VDL2_WALK_BLOCK) {
 				const size_t o = (size_t)m * s;
-				vdl2_walk_block<MODE == 1>(v, ring, BLOCK, env, ch, dec_base + m, dec + o, phs + o, mgs + o, s);
+				vdl2_walk_block<MODE == 1>(v, ring, BLOCK, env, chan, dec_base + m, dec + o, phs + o, mgs + o, s);
 			}
 		}
 	}
@@ -740,7 +767,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	for(; m < n_dec; m++) {
 		const size_t o = (size_t)m * s;
 		const float2 d = __ldg(&dec[o]);
-		vdl2_demod_step_pm(v, ring, BLOCK, env, ch, dec_base + m, d.x, d.y, __ldg(&phs[o]), __ldg(&mgs[o]), false, 0.f, 0.f);
+		vdl2_demod_step_pm(v, ring, BLOCK, env, chan, dec_base + m, d.x, d.y, __ldg(&phs[o]), __ldg(&mgs[o]), false, 0.f, 0.f);
 	}
 
 #pragma unroll 4
@@ -760,6 +787,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	st[K2_SYNC_LO * s + ch] = (uint32_t)v.sync_dec_index; st[K2_SYNC_HI * s + ch] = (uint32_t)(v.sync_dec_index >> 32);
 	st[K2_CNT_SYNC * s + ch] = v.cnt_sync; st[K2_CNT_HDR_GOOD * s + ch] = v.cnt_hdr_good;
 	st[K2_PURE_RUN * s + ch] = v.pure_run;
+	if(tid == 0) vdl2_trace_end(p.trace_blocks, trace_k);       /* thread 0's own end: an approximation of the block's */
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -987,9 +1015,11 @@ extern "C" int vdl2_kernels_init_device(int device) {
 		cudaFuncSetAttribute(k1_mix_iir_decimate_lanes<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1L_SMEM_BYTES);
 		vdl2_set_carveout(k2a_phase_mag<true>, pct);
 		vdl2_set_carveout(k2a_phase_mag<false>, pct);
-#define K2_SETUP(BLOCKED, MODE) do { vdl2_set_carveout(k2_sync_slice<K2_BLOCK, BLOCKED, MODE>, pct); \
-		cudaFuncSetAttribute(k2_sync_slice<K2_BLOCK, BLOCKED, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_BYTES(K2_BLOCK, MODE)); } while(0)
-		K2_SETUP(true, 4); K2_SETUP(true, 3); K2_SETUP(true, 2); K2_SETUP(true, 1); K2_SETUP(true, 0); K2_SETUP(false, 0);
+#define K2_SETUP(BLK, BLOCKED, MODE) do { vdl2_set_carveout(k2_sync_slice<BLK, BLOCKED, MODE>, pct); \
+		cudaFuncSetAttribute(k2_sync_slice<BLK, BLOCKED, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_BYTES(BLK, MODE)); } while(0)
+		K2_SETUP(K2_BLOCK, true, 4); K2_SETUP(K2_BLOCK, true, 3); K2_SETUP(K2_BLOCK, true, 2); K2_SETUP(K2_BLOCK, true, 1);
+		K2_SETUP(K2_BLOCK, true, 0); K2_SETUP(K2_BLOCK, false, 0);
+		K2_SETUP(32, true, 4); K2_SETUP(32, true, 1);
 #undef K2_SETUP
 		vdl2_set_carveout(k_copy_rows, pct);
 		vdl2_set_carveout(k_copy_hist, pct);
@@ -1058,8 +1088,8 @@ extern "C" int vdl2_launch_k2a(const vdl2_k2_params *p, cudaStream_t st) {
 	if(p->n_dec == 0 || p->n_ch == 0) return 0;
 	const uint32_t n_elems = p->n_dec * p->n_chp;
 	const uint32_t hist = VDL2_SYNC_BUFLEN * p->n_chp;
-	if(p->k2a_mode) k2a_phase_mag<true><<<(n_elems + 255u) / 256u, 256, 0, st>>>(p->dec, p->phase + hist, p->mag, n_elems, p->n_chp, p->ca);
-	else k2a_phase_mag<false><<<(n_elems + 255u) / 256u, 256, 0, st>>>(p->dec, p->phase + hist, p->mag, n_elems, p->n_chp, p->ca);
+	if(p->k2a_mode) k2a_phase_mag<true><<<(n_elems + 255u) / 256u, 256, 0, st>>>(p->dec, p->phase + hist, p->mag, n_elems, p->n_chp, p->lanes ? p->lanes : 32u, p->ca);
+	else k2a_phase_mag<false><<<(n_elems + 255u) / 256u, 256, 0, st>>>(p->dec, p->phase + hist, p->mag, n_elems, p->n_chp, p->lanes ? p->lanes : 32u, p->ca);
 	return (int)cudaGetLastError();
 }
 
@@ -1068,8 +1098,14 @@ extern "C" int vdl2_launch_k2a(const vdl2_k2_params *p, cudaStream_t st) {
  * default): phase ring with every block input (phase, magnitude, samples) staged one block ahead by cp.async */
 extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
 	if(p->n_dec == 0 || p->n_ch == 0) return 0;
-	const uint32_t blocks = (p->n_ch + K2_BLOCK - 1) / K2_BLOCK;
-	const uint32_t variant = p->variant;
+	uint32_t blocks = (p->n_ch + K2_BLOCK - 1) / K2_BLOCK;
+	const uint32_t variant = p->variant & 0xFFu;
+	if(p->variant & 0x100u) {                     /* A/B: one warp per block (VDL2GPU_K2_VARIANT = 256 + variant) */
+		blocks = (p->n_ch + 31u) / 32u;
+		if(variant == 2) k2_sync_slice<32, true, 1><<<blocks, 32, K2_SMEM_BYTES(32, 1), st>>>(*p);
+		else k2_sync_slice<32, true, 4><<<blocks, 32, K2_SMEM_BYTES(32, 4), st>>>(*p);
+		return (int)cudaGetLastError();
+	}
 #define K2_GO(BLOCKED, MODE) k2_sync_slice<K2_BLOCK, BLOCKED, MODE><<<blocks, K2_BLOCK, K2_SMEM_BYTES(K2_BLOCK, MODE), st>>>(*p)
 	if(variant == 0) K2_GO(false, 0);
 	else if(variant == 1) K2_GO(true, 0);

@@ -17,12 +17,27 @@ typedef struct {
 	uint32_t pad;
 } vdl2_chunk_args;
 
+/* optional per-block scheduling trace (VDL2GPU_BLOCK_TRACE=1): every block of K1 and K2 appends one record */
+typedef struct {
+	uint32_t kernel;             /* 1 = K1, 2 = K2 */
+	uint32_t block;
+	uint32_t smid;
+	uint32_t pad;
+	uint64_t t_start, t_end;     /* %globaltimer, ns */
+} vdl2_block_rec;
+typedef struct {
+	uint32_t n, cap;
+	vdl2_block_rec rec[1];
+} vdl2_block_trace;
+
 typedef struct {
 	const float2 *samples;       /* K0 output: {re, im} per complex sample; stream s at samples + s * stream_stride */
 	uint32_t n_pairs;
 	uint32_t oversample;
 	uint32_t cnt0;               /* decimation counter on entry (src/demod.c:289,322), same for all channels */
-	uint32_t n_ch, n_chp;
+	uint32_t n_ch, n_chp;        /* channels; per-channel array stride = channel SLOTS (n_chp >= n_ch, multiple of 32) */
+	uint32_t lanes;              /* channels per warp (1..32): channel c sits in slot (c / lanes) * 32 + c % lanes, so that the
+	                              * warps of the channel kernels can be spread over every SM sub-partition (see vdl2_host.cu) */
 	float2 *dec;                 /* [n_dec][n_chp] */
 	uint32_t *state;             /* [K1_NFIELDS][n_chp] */
 	const float4 *lut;           /* 257 x {cos, sin, dcos*2^-16, dsin*2^-16} */
@@ -32,6 +47,7 @@ typedef struct {
 	                              * 1 = one stream per channel: `samples` is float2[n_pairs][stream_stride], time-major across streams */
 	uint32_t stream_stride;      /* float2 elements between consecutive streams in `samples` (ch_per_stream == 1: per sample row) */
 	const vdl2_chunk_args *ca;   /* NULL, or device pointer overriding n_pairs / cnt0 */
+	vdl2_block_trace *trace_blocks;
 } vdl2_k1_params;
 
 typedef struct {
@@ -41,6 +57,7 @@ typedef struct {
 	float *hist_tmp;             /* [160][n_chp] scratch for the history shift of short chunks */
 	uint32_t n_dec;
 	uint32_t n_ch, n_chp;
+	uint32_t lanes;              /* channels per warp, as in vdl2_k1_params */
 	uint64_t dec_base;           /* absolute index of dec[0] */
 	uint32_t *state;             /* [K2_NFIELDS][n_chp] */
 	float *ring;                 /* [160][n_chp] */
@@ -57,6 +74,7 @@ typedef struct {
 	uint32_t variant;            /* walk variant, see vdl2_launch_k2 */
 	uint32_t k2a_mode;           /* 0: libdevice atan2 for every sample; 1: vdl2_phase_fast with the Ziv fall-back */
 	const vdl2_chunk_args *ca;   /* NULL, or device pointer overriding n_dec / dec_base */
+	vdl2_block_trace *trace_blocks;
 } vdl2_k2_params;
 
 typedef struct {

@@ -223,6 +223,9 @@ int vdl2gpu_get_kernel_ms(vdl2gpu_ctx *ctx, double ms[5], uint64_t launches[5]);
  * vdl2gpu_enable_timing(ctx, 1) of: front start, K0|K1, K1 end, back start, K2a|K2, K2|K3, K3 end (with graph replay
  * only the stage boundaries are known: K0 counts into K1 and K3 into K2).  Returns the number of rows copied. */
 int vdl2gpu_get_timeline(vdl2gpu_ctx *ctx, float *out, uint32_t cap_rows);
+/* diagnostic (context created with VDL2GPU_BLOCK_TRACE=1 in the environment): where and when every block of K1 / K2 ran,
+ * 6 x uint64 per record {kernel (1 K1, 2 K2), block, SM id, 0, start ns, end ns}.  Synchronises. */
+int vdl2gpu_debug_block_trace(vdl2gpu_ctx *ctx, uint64_t *out, uint32_t cap_records);
 
 /* ---- raw launch stubs (extern "C", plain pointers; used by the micro-parity tests and by hosts that
  *      manage device memory themselves).  All pointers are DEVICE pointers unless stated otherwise; `stream` is a

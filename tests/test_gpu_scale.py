@@ -92,3 +92,15 @@ def test_config3_256_channels_full_10_seconds():
     cnt, ocnt = g.channel_counters(), o.counters()
     for ch in range(64 * n_rep):
         assert np.array_equal(cnt[ch], ocnt[ch // n_rep])
+
+
+def test_balanced_slot_mapping_10048_channels():
+    """More than half a machine's worth of channels are spread over all SM sub-partitions (ceil(n / 592) channels per
+    warp instead of 32; here 17): channel numbers in frames and counters must be unaffected by the slot layout."""
+    want, got, st, cnt, ocnt, bursts = _run(64, 157, 0.4, 22.0, 0x56444C36)
+    assert st["pool_overflows"] == 0 and st["out_overflows"] == 0
+    n_frames = sum(len(v) for v in want.values())
+    assert n_frames > 20 and st["msg_good"] == 157 * n_frames
+    for ch in range(64 * 157):
+        assert sorted(got.get(ch, [])) == sorted(want.get(ch // 157, [])), f"channel {ch}"
+        assert np.array_equal(cnt[ch], ocnt[ch // 157])
