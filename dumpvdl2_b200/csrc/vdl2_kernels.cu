@@ -1047,7 +1047,7 @@ extern "C" int vdl2_launch_k0_lanes(const void *raw, uint32_t n_pairs, uint32_t 
 
 template<int OS, int BLOCK>
 static void k1_launch_packed(const vdl2_k1_params *p, int variant, bool sym, cudaStream_t st) {
-	const uint32_t blocks = (p->n_ch + BLOCK - 1) / BLOCK;
+	const uint32_t blocks = (p->n_chp + BLOCK - 1) / BLOCK;
 	if(variant == 0 && BLOCK == K1_BLOCK) k1_mix_iir_decimate_packed<OS, K1_BLOCK, 0, false><<<blocks, BLOCK, 0, st>>>(*p);
 	else if(sym) k1_mix_iir_decimate_packed<OS, BLOCK, 10, true><<<blocks, BLOCK, 0, st>>>(*p);
 	else k1_mix_iir_decimate_packed<OS, BLOCK, 10, false><<<blocks, BLOCK, 0, st>>>(*p);
@@ -1059,7 +1059,7 @@ extern "C" int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, int var
 	if(p->n_pairs == 0 || p->n_ch == 0) return 0;
 	const bool sym = (p->a1 == 2.0f * p->a0) && (p->a2 == p->a0) && variant != 4;
 	if(p->ch_per_stream == 1) {                       /* one stream per channel: samples are float2[n_pairs][stream_stride] */
-		const uint32_t blocks = (p->n_ch + K1L_BLOCK - 1) / K1L_BLOCK;
+		const uint32_t blocks = (p->n_chp + K1L_BLOCK - 1) / K1L_BLOCK;
 		if(p->oversample == 20) {
 			if(sym) k1_mix_iir_decimate_lanes<20, true><<<blocks, K1L_BLOCK, K1L_SMEM_BYTES, st>>>(*p);
 			else k1_mix_iir_decimate_lanes<20, false><<<blocks, K1L_BLOCK, K1L_SMEM_BYTES, st>>>(*p);
@@ -1078,7 +1078,7 @@ extern "C" int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, int var
 	} else if(!force_scalar && p->oversample == 13 && variant != 0 && wide) {      /* 1.365 Msps (Mirics, src/mirics.h:23) */
 		k1_launch_packed<13, K1_BLOCK>(p, variant, sym, st);
 	} else {
-		const uint32_t blocks = (p->n_ch + K1_BLOCK1 - 1) / K1_BLOCK1;
+		const uint32_t blocks = (p->n_chp + K1_BLOCK1 - 1) / K1_BLOCK1;
 		k1_mix_iir_decimate_scalar<K1_BLOCK1><<<blocks, K1_BLOCK1, 0, st>>>(*p);
 	}
 	return (int)cudaGetLastError();
@@ -1098,10 +1098,10 @@ extern "C" int vdl2_launch_k2a(const vdl2_k2_params *p, cudaStream_t st) {
  * default): phase ring with every block input (phase, magnitude, samples) staged one block ahead by cp.async */
 extern "C" int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st) {
 	if(p->n_dec == 0 || p->n_ch == 0) return 0;
-	uint32_t blocks = (p->n_ch + K2_BLOCK - 1) / K2_BLOCK;
+	uint32_t blocks = (p->n_chp + K2_BLOCK - 1) / K2_BLOCK;
 	const uint32_t variant = p->variant & 0xFFu;
 	if(p->variant & 0x100u) {                     /* A/B: one warp per block (VDL2GPU_K2_VARIANT = 256 + variant) */
-		blocks = (p->n_ch + 31u) / 32u;
+		blocks = (p->n_chp + 31u) / 32u;
 		if(variant == 2) k2_sync_slice<32, true, 1><<<blocks, 32, K2_SMEM_BYTES(32, 1), st>>>(*p);
 		else k2_sync_slice<32, true, 4><<<blocks, 32, K2_SMEM_BYTES(32, 4), st>>>(*p);
 		return (int)cudaGetLastError();

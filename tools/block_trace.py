@@ -31,14 +31,14 @@ launches = []
 for kern in (1, 2):
     r = t[t[:, 0] == kern]
     r = r[np.argsort(r[:, 4])]
-    n = 128
+    n = int(r[:, 1].max()) + 1 if len(r) else 1
     for i in range(0, len(r) - n + 1, n):
         blk = r[i:i + n]
         sm = blk[:, 2].astype(int)
         per_sm = np.bincount(sm, minlength=148)
         launches.append(dict(kernel="K1" if kern == 1 else "K2", start_ms=(int(blk[:, 4].min()) - t0) / 1e6, first_end_ms=(int(blk[:, 5].min()) - t0) / 1e6,
                              end_ms=(int(blk[:, 5].max()) - t0) / 1e6, start_spread_ms=(int(blk[:, 4].max()) - int(blk[:, 4].min())) / 1e6,
-                             sms_used=int((per_sm > 0).sum()), max_blocks_per_sm=int(per_sm.max()),
+                             blocks=n, sms_used=int((per_sm > 0).sum()), max_blocks_per_sm=int(per_sm.max()),
                              mean_block_ms=float((blk[:, 5] - blk[:, 4]).mean()) / 1e6))
 launches.sort(key=lambda x: x["start_ms"])
 for l in launches[8:40]:
