@@ -77,7 +77,7 @@ struct vdl2gpu_ctx {
 	uint64_t chunk_seq = 0;
 	cudaEvent_t ev_input_ready = nullptr, ev_input_consumed = nullptr;
 	uint32_t n_ch = 0, n_chp = 0, max_pairs = 0, max_dec = 0, n_slots = 0, out_cap = 0, event_cap = 0;
-	uint32_t lanes = 32;                                /* channels per warp of the channel kernels (slot mapping, see create_impl) */
+	uint32_t lanes = 32, full_warps = 0xFFFFFFFFu;      /* channel slot mapping (see create_impl) */
 	int n_sms = 148;
 	uint32_t n_streams = 1, ch_per_stream = 0;          /* independent-streams mode: n_streams > 1, channels [s*C, (s+1)*C) on stream s */
 	bool lane_streams = false;                          /* C == 1: samples kept time-major across streams, one lane per stream in K1 */
@@ -120,9 +120,15 @@ static uint32_t dphi_for(uint32_t centerfreq, uint32_t freq, uint32_t rate) {   
 	return (uint32_t)(int)(((float)centerfreq - (float)freq) / (float)rate * 256.0f * 65536.0f);
 }
 
-static void initial_state(const vdl2gpu_config &cfg, const uint32_t *freqs, uint32_t n_ch, uint32_t n_chp, uint32_t lanes,
+static void initial_state(const vdl2gpu_config &cfg, const uint32_t *freqs, uint32_t n_ch, uint32_t n_chp, uint32_t lanes, uint32_t full_warps,
 		std::vector<uint32_t> &k1, std::vector<uint32_t> &k2);
-static inline uint32_t slot_of(uint32_t ch, uint32_t lanes) { return (ch / lanes) * 32u + ch % lanes; }
+/* channel -> slot: the first full_warps warps hold `lanes` channels each, the others lanes - 1 */
+static inline uint32_t slot_of(uint32_t ch, uint32_t lanes, uint32_t full_warps) {
+	const uint32_t head = full_warps * lanes;
+	if(ch < head) return (ch / lanes) * 32u + ch % lanes;
+	const uint32_t c = ch - head;
+	return (full_warps + c / (lanes - 1u)) * 32u + c % (lanes - 1u);
+}
 
 extern "C" int vdl2gpu_abi_version(void) { return VDL2GPU_ABI_VERSION; }
 
@@ -227,20 +233,22 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	c->n_ch = cfg->n_channels;
 	c->n_chp = (c->n_ch + 31u) & ~31u;
 	c->n_sms = prop.multiProcessorCount;
-	c->lanes = 32;
+	c->lanes = 32; c->full_warps = 0xFFFFFFFFu;
 	/* Slot mapping.  K1 and K2 run four-warp blocks, one warp per SM sub-partition, and a chunk's K2 overlaps the next
 	 * chunk's K1.  The block scheduler places a new block on the SM with the most free resources: when a grid leaves SMs
 	 * empty (128 blocks on 148 SMs at 16384 channels), the OTHER kernel's blocks pile up on those SMs two and three deep
 	 * instead of sitting beside the first kernel's blocks, one per SM, and run two to three times slower (measured with
 	 * the per-block trace, tools/block_trace.py).  So when the channels fill more than half of the machine's
-	 * sub-partitions, they are spread over ALL of them: every warp holds ceil(n_ch / (4 x SMs)) channels instead of 32,
-	 * each of the two kernels launches exactly one block per SM, and every SM looks the same to the scheduler. */
+	 * sub-partitions, they are dealt out evenly over ALL of them: every warp holds floor or ceil of n_ch / (4 x SMs)
+	 * channels instead of 32 (27 or 28 at 16384 channels on 148 SMs), each of the two kernels launches exactly one block
+	 * per SM, every block lives for the whole kernel, and every SM looks the same to the scheduler. */
 	if(cfg->n_streams <= 1) {
 		const uint32_t warps_all = 4u * (uint32_t)c->n_sms;
 		if(c->n_ch > 16u * warps_all && c->n_ch <= 32u * warps_all) {
 			const char *e = getenv("VDL2GPU_BALANCE");
 			if(!e || atoi(e)) {
 				c->lanes = (c->n_ch + warps_all - 1u) / warps_all;
+				c->full_warps = c->n_ch - (c->lanes - 1u) * warps_all;       /* warps with `lanes` channels; the rest have lanes - 1 */
 				c->n_chp = warps_all * 32u;
 			}
 		}
@@ -306,7 +314,7 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	CU(cudaMemset(c->d_pool, 0, (size_t)c->n_slots * sizeof(vdl2_burst_slot)));
 
 	std::vector<uint32_t> k1, k2;
-	initial_state(c->cfg, c->freqs.data(), c->n_ch, c->n_chp, c->lanes, k1, k2);
+	initial_state(c->cfg, c->freqs.data(), c->n_ch, c->n_chp, c->lanes, c->full_warps, k1, k2);
 	CU(cudaMemcpy(c->d_k1, k1.data(), k1.size() * 4, cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(c->d_k2, k2.data(), k2.size() * 4, cudaMemcpyHostToDevice));
 	std::vector<int32_t> fl(c->n_slots);
@@ -504,13 +512,13 @@ static void fill_params(vdl2gpu_ctx *c, chunk_slot &s, int db, uint32_t n_pairs,
 		const vdl2_chunk_args *ca, vdl2_k1_params &p1, vdl2_k2_params &p2, vdl2_k3_params &p3) {
 	float2 *d_dec = c->d_dec2[db];
 	p1.samples = c->d_samples; p1.n_pairs = n_pairs; p1.oversample = c->cfg.oversample; p1.cnt0 = cnt0;
-	p1.n_ch = c->n_ch; p1.n_chp = c->n_chp; p1.lanes = c->lanes; p1.dec = d_dec; p1.state = c->d_k1;
+	p1.n_ch = c->n_ch; p1.n_chp = c->n_chp; p1.lanes = c->lanes; p1.full_warps = c->full_warps; p1.dec = d_dec; p1.state = c->d_k1;
 	p1.lut = reinterpret_cast<const float4 *>(c->d_tab->lut);
 	p1.a0 = c->tab.t.A[0]; p1.a1 = c->tab.t.A[1]; p1.a2 = c->tab.t.A[2]; p1.b1 = c->tab.t.B[1]; p1.b2 = c->tab.t.B[2];
 	p1.one = 1.0f; p1.neg_one = -1.0f; p1.two = 2.0f;
 	p1.trace_blocks = c->d_block_trace; p2.trace_blocks = c->d_block_trace;
 	p1.ch_per_stream = c->ch_per_stream; p1.stream_stride = c->lane_streams ? c->n_chp : c->max_pairs; p1.ca = ca;
-	p2.dec = d_dec; p2.phase = c->d_phase; p2.mag = c->d_mag; p2.hist_tmp = c->d_hist_tmp; p2.n_dec = n_dec; p2.n_ch = c->n_ch; p2.n_chp = c->n_chp; p2.lanes = c->lanes; p2.dec_base = dec_base;
+	p2.dec = d_dec; p2.phase = c->d_phase; p2.mag = c->d_mag; p2.hist_tmp = c->d_hist_tmp; p2.n_dec = n_dec; p2.n_ch = c->n_ch; p2.n_chp = c->n_chp; p2.lanes = c->lanes; p2.full_warps = c->full_warps; p2.dec_base = dec_base;
 	p2.state = c->d_k2; p2.ring = c->d_ring; p2.tables = c->d_tab; p2.max_ppm = c->cfg.max_ppm; p2.s27 = c->tab.s27;
 	p2.pool = c->d_pool; p2.free_list = c->d_free; p2.ready = c->d_ready; p2.ctl = c->d_ctl;
 	p2.events = c->d_events; p2.event_cap = c->event_cap; p2.trace = (c->cfg.flags & VDL2GPU_FLAG_TRACE) ? 1u : 0u;
@@ -836,7 +844,7 @@ extern "C" int vdl2gpu_get_stats(vdl2gpu_ctx *c, vdl2gpu_stats *out) {
 	int rc = read_counters(c, k3, sync, hdr);
 	if(rc) return rc;
 	uint64_t a = 0, b = 0;
-	for(uint32_t ch = 0; ch < c->n_ch; ch++) { a += sync[slot_of(ch, c->lanes)]; b += hdr[slot_of(ch, c->lanes)]; }
+	for(uint32_t ch = 0; ch < c->n_ch; ch++) { a += sync[slot_of(ch, c->lanes, c->full_warps)]; b += hdr[slot_of(ch, c->lanes, c->full_warps)]; }
 	c->stats.demod_sync_good = a;
 	c->stats.decoder_crc_good = b;
 	*out = c->stats;
@@ -851,8 +859,8 @@ extern "C" int vdl2gpu_get_channel_counters(vdl2gpu_ctx *c, uint64_t *out, uint3
 	for(uint32_t ch = 0; ch < n_channels; ch++) {
 		uint64_t *o = out + (size_t)ch * VDL2_NUM_COUNTERS;
 		for(int k = 0; k < VDL2_NUM_COUNTERS; k++) o[k] = k3[(size_t)k * c->n_chp + ch];
-		o[VDL2_CNT_SYNC_GOOD] = sync[slot_of(ch, c->lanes)];          /* K2's own counters live in its state planes, by slot */
-		o[VDL2_CNT_HDR_CRC_GOOD] = hdr[slot_of(ch, c->lanes)];
+		o[VDL2_CNT_SYNC_GOOD] = sync[slot_of(ch, c->lanes, c->full_warps)];          /* K2's own counters live in its state planes, by slot */
+		o[VDL2_CNT_HDR_CRC_GOOD] = hdr[slot_of(ch, c->lanes, c->full_warps)];
 	}
 	return VDL2GPU_OK;
 }
@@ -887,7 +895,7 @@ extern "C" int vdl2gpu_read_dec(vdl2gpu_ctx *c, float *out, size_t cap_floats, u
 		CU(cudaMemcpy(tmp.data(), c->d_dec2[(c->chunk_seq + 1) & 1u], tmp.size() * sizeof(float2), cudaMemcpyDeviceToHost));
 		for(uint32_t m = 0; m < c->last_n_dec; m++)
 			for(uint32_t ch = 0; ch < c->n_ch; ch++) {
-				const float2 v = tmp[(size_t)m * c->n_chp + slot_of(ch, c->lanes)];
+				const float2 v = tmp[(size_t)m * c->n_chp + slot_of(ch, c->lanes, c->full_warps)];
 				out[((size_t)m * c->n_ch + ch) * 2] = v.x; out[((size_t)m * c->n_ch + ch) * 2 + 1] = v.y;
 			}
 	}
@@ -1015,7 +1023,7 @@ extern "C" int vdl2gpu_launch_phase_mag(const float *dec, uint32_t n_elems, floa
 	vdl2_k2_params p2;
 	memset(&p2, 0, sizeof(p2));
 	/* one row of n_elems "channels": K2a is element-wise, the row structure does not matter */
-	p2.dec = reinterpret_cast<const float2 *>(dec); p2.n_dec = 1; p2.n_ch = n_elems; p2.n_chp = n_elems; p2.lanes = 32;
+	p2.dec = reinterpret_cast<const float2 *>(dec); p2.n_dec = 1; p2.n_ch = n_elems; p2.n_chp = n_elems; p2.lanes = 32; p2.full_warps = 0xFFFFFFFFu;
 	p2.phase = phase_out - (size_t)VDL2_SYNC_BUFLEN * n_elems;       /* the launcher skips the 160 history rows */
 	p2.mag = mag_out; p2.k2a_mode = exact_libm ? 0u : 1u;
 	KL(vdl2_launch_k2a(&p2, (cudaStream_t)stream));
@@ -1078,12 +1086,12 @@ extern "C" uint32_t vdl2gpu_stage_row_stride(uint32_t n_channels) { return (n_ch
 
 /* initial per-channel state: vdl2_channel_init + demod_reset (src/demod.c:205-220,379-392), process_samples locals
  * (src/demod.c:289-298); shared by the batch context and the stage stubs */
-static void initial_state(const vdl2gpu_config &cfg, const uint32_t *freqs, uint32_t n_ch, uint32_t n_chp, uint32_t lanes,
+static void initial_state(const vdl2gpu_config &cfg, const uint32_t *freqs, uint32_t n_ch, uint32_t n_chp, uint32_t lanes, uint32_t full_warps,
 		std::vector<uint32_t> &k1, std::vector<uint32_t> &k2) {
 	k1.assign((size_t)K1_NFIELDS * n_chp, 0u); k2.assign((size_t)K2_NFIELDS * n_chp, 0u);
 	auto fbits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
 	for(uint32_t chan = 0; chan < n_ch; chan++) {
-		const uint32_t ch = slot_of(chan, lanes);          /* index into the per-channel planes */
+		const uint32_t ch = slot_of(chan, lanes, full_warps);          /* index into the per-channel planes */
 		/* a channel on the centre frequency skips the mixer in the reference (src/demod.c:312); with a zero
 		 * phase step the table gives cos = 1, sin = 0 and the products are exact, so no branch is needed */
 		k1[(size_t)K1_DPHI * n_chp + ch] = (cfg.centerfreq != freqs[chan]) ? dphi_for(cfg.centerfreq, freqs[chan], cfg.sample_rate) : 0u;
@@ -1127,7 +1135,7 @@ extern "C" int vdl2gpu_stage_create(const vdl2gpu_config *cfg, uint32_t max_dec,
 	st->d_ready = reinterpret_cast<uint32_t *>(b + L.ready); st->d_ctl = reinterpret_cast<vdl2_queue_ctl *>(b + L.ctl);
 	st->d_events = b + L.events;
 	std::vector<uint32_t> k1, k2;
-	initial_state(st->cfg, st->freqs.data(), st->n_ch, st->n_chp, 32u, k1, k2);
+	initial_state(st->cfg, st->freqs.data(), st->n_ch, st->n_chp, 32u, 0xFFFFFFFFu, k1, k2);
 	std::vector<int32_t> fl(st->n_slots);
 	for(uint32_t i = 0; i < st->n_slots; i++) fl[i] = (int32_t)i;
 	vdl2_queue_ctl ctl;
@@ -1162,7 +1170,7 @@ extern "C" int vdl2gpu_launch_mix_iir_decimate(vdl2gpu_stage *st, const float *s
 	vdl2_k1_params p1;
 	memset(&p1, 0, sizeof(p1));
 	p1.samples = reinterpret_cast<const float2 *>(samples); p1.n_pairs = n_pairs; p1.oversample = os; p1.cnt0 = st->decim_cnt;
-	p1.n_ch = st->n_ch; p1.n_chp = st->n_chp; p1.lanes = 32; p1.dec = reinterpret_cast<float2 *>(dec_out); p1.state = st->d_k1;
+	p1.n_ch = st->n_ch; p1.n_chp = st->n_chp; p1.lanes = 32; p1.full_warps = 0xFFFFFFFFu; p1.dec = reinterpret_cast<float2 *>(dec_out); p1.state = st->d_k1;
 	p1.lut = reinterpret_cast<const float4 *>(st->d_tab->lut);
 	p1.a0 = st->tab.t.A[0]; p1.a1 = st->tab.t.A[1]; p1.a2 = st->tab.t.A[2]; p1.b1 = st->tab.t.B[1]; p1.b2 = st->tab.t.B[2];
 	p1.one = 1.0f; p1.neg_one = -1.0f; p1.two = 2.0f;
@@ -1181,7 +1189,7 @@ extern "C" int vdl2gpu_launch_sync_slice(vdl2gpu_stage *st, const float *dec, ui
 	vdl2_k2_params p2;
 	memset(&p2, 0, sizeof(p2));
 	p2.dec = reinterpret_cast<const float2 *>(dec); p2.phase = st->d_phase; p2.mag = st->d_mag; p2.hist_tmp = st->d_hist_tmp;
-	p2.n_dec = n_dec; p2.n_ch = st->n_ch; p2.n_chp = st->n_chp; p2.lanes = 32; p2.dec_base = st->total_dec;
+	p2.n_dec = n_dec; p2.n_ch = st->n_ch; p2.n_chp = st->n_chp; p2.lanes = 32; p2.full_warps = 0xFFFFFFFFu; p2.dec_base = st->total_dec;
 	p2.state = st->d_k2; p2.ring = st->d_ring; p2.tables = st->d_tab; p2.max_ppm = st->cfg.max_ppm; p2.s27 = st->tab.s27;
 	p2.pool = st->d_pool; p2.free_list = st->d_free; p2.ready = st->d_ready; p2.ctl = st->d_ctl;
 	p2.events = st->d_events; p2.event_cap = st->event_cap; p2.trace = (st->cfg.flags & VDL2GPU_FLAG_TRACE) ? 1u : 0u;

@@ -123,10 +123,11 @@ __device__ __forceinline__ void k1_store_state(const vdl2_k1_params &p, uint32_t
 
 /* slot (index into every per-channel array) -> public channel number and activity: a warp holds `lanes` channels in its
  * first `lanes` lanes */
-__device__ __forceinline__ bool vdl2_slot_channel(uint32_t slot, uint32_t lanes, uint32_t n_ch, uint32_t &chan) {
-	const uint32_t lane = slot & 31u;
-	chan = (slot >> 5) * lanes + lane;
-	return lane < lanes && chan < n_ch;
+__device__ __forceinline__ bool vdl2_slot_channel(uint32_t slot, uint32_t lanes, uint32_t full_warps, uint32_t n_ch, uint32_t &chan) {
+	const uint32_t lane = slot & 31u, w = slot >> 5;
+	const uint32_t mine = w < full_warps ? lanes : lanes - 1u;                 /* channels of this warp */
+	chan = (w < full_warps ? w * lanes : full_warps * lanes + (w - full_warps) * (lanes - 1u)) + lane;
+	return lane < mine && chan < n_ch;
 }
 
 /* independent-streams mode: all channels of a block belong to stream (first channel / ch_per_stream); a block never
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_scalar(vdl2_k1_para
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ch = blockIdx.x * BLOCK + tid;
 	uint32_t chan;
-	const bool active = vdl2_slot_channel(ch, p.lanes, p.n_ch, chan);
+	const bool active = vdl2_slot_channel(ch, p.lanes, p.full_warps, p.n_ch, chan);
 	const uint32_t n_pairs = p.ca ? p.ca->n_pairs : p.n_pairs, cnt0 = p.ca ? p.ca->cnt0 : p.cnt0;
 	const float2 *samples = k1_stream_of(p, blockIdx.x * BLOCK);
 	for(uint32_t i = tid; i < 257; i += BLOCK) s_lut[i] = p.lut[i];
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	const int trace_k = tid == 0 ? vdl2_trace_begin(p.trace_blocks, 1) : -1;
 	const uint32_t ch = blockIdx.x * BLOCK + tid;
 	uint32_t chan;
-	const bool active = vdl2_slot_channel(ch, p.lanes, p.n_ch, chan);
+	const bool active = vdl2_slot_channel(ch, p.lanes, p.full_warps, p.n_ch, chan);
 	const uint32_t n_pairs = p.ca ? p.ca->n_pairs : p.n_pairs, cnt0 = p.ca ? p.ca->cnt0 : p.cnt0;
 	const float2 *samples = k1_stream_of(p, blockIdx.x * BLOCK);
 	for(uint32_t i = tid; i < 257 * NLUT; i += BLOCK) s_lut[i] = p.lut[i / NLUT];
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(K1L_BLOCK) k1_mix_iir_decimate_lanes(vdl2_k1_p
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ch = blockIdx.x * K1L_BLOCK + tid;
 	uint32_t chan;
-	const bool active = vdl2_slot_channel(ch, p.lanes, p.n_ch, chan);
+	const bool active = vdl2_slot_channel(ch, p.lanes, p.full_warps, p.n_ch, chan);
 	const uint32_t n_pairs = p.ca ? p.ca->n_pairs : p.n_pairs, cnt0 = p.ca ? p.ca->cnt0 : p.cnt0;
 	const size_t stride = p.stream_stride;                 /* float2 elements between consecutive samples */
 	const float2 *samples = p.samples + (size_t)blockIdx.x * K1L_BLOCK;      /* this block's 128 columns */
@@ -561,7 +562,8 @@ __global__ void __launch_bounds__(256) k2a_phase_mag(const float2 *__restrict__ 
 	}
 	const uint32_t n_elems = ca ? ca->n_dec * n_chp : n_elems_p;
 	uint32_t i = blockIdx.x * 256u + threadIdx.x;
-	if(i >= n_elems || (i & 31u) >= lanes) return;            /* n_chp is a multiple of 32: i & 31 is the lane of the slot */
+	if(i >= n_elems || (i & 31u) >= lanes) return;            /* n_chp is a multiple of 32: i & 31 is the lane of the slot (a warp
+	                                                            * with lanes - 1 channels computes one idle element: harmless) */
 	const float2 d = dec[i];
 	float ph, mg;
 	if(FAST) {
@@ -632,7 +634,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	if(MODE) for(uint32_t i = tid; i < VDL2_UNWRAP_STATES * 6; i += BLOCK) s_unwrap[i] = p.tables->unwrap_lut[i];
 	__syncthreads();
 	uint32_t chan;                                    /* public channel number (events, burst records); ch = slot */
-	if(!vdl2_slot_channel(ch, p.lanes, p.n_ch, chan)) return;
+	if(!vdl2_slot_channel(ch, p.lanes, p.full_warps, p.n_ch, chan)) return;
 	const uint32_t s = p.n_chp;
 	uint32_t *st = p.state;
 	vdl2_chan v;

@@ -36,8 +36,10 @@ typedef struct {
 	uint32_t oversample;
 	uint32_t cnt0;               /* decimation counter on entry (src/demod.c:289,322), same for all channels */
 	uint32_t n_ch, n_chp;        /* channels; per-channel array stride = channel SLOTS (n_chp >= n_ch, multiple of 32) */
-	uint32_t lanes;              /* channels per warp (1..32): channel c sits in slot (c / lanes) * 32 + c % lanes, so that the
-	                              * warps of the channel kernels can be spread over every SM sub-partition (see vdl2_host.cu) */
+	uint32_t lanes;              /* channels per warp (1..32) for the first `full_warps` warps, lanes - 1 for the others: the
+	                              * channels are dealt out evenly so that the warps of the channel kernels cover every SM
+	                              * sub-partition and all live equally long (see create_impl in vdl2_host.cu) */
+	uint32_t full_warps;
 	float2 *dec;                 /* [n_dec][n_chp] */
 	uint32_t *state;             /* [K1_NFIELDS][n_chp] */
 	const float4 *lut;           /* 257 x {cos, sin, dcos*2^-16, dsin*2^-16} */
@@ -57,7 +59,7 @@ typedef struct {
 	float *hist_tmp;             /* [160][n_chp] scratch for the history shift of short chunks */
 	uint32_t n_dec;
 	uint32_t n_ch, n_chp;
-	uint32_t lanes;              /* channels per warp, as in vdl2_k1_params */
+	uint32_t lanes, full_warps;  /* channel slot mapping, as in vdl2_k1_params */
 	uint64_t dec_base;           /* absolute index of dec[0] */
 	uint32_t *state;             /* [K2_NFIELDS][n_chp] */
 	float *ring;                 /* [160][n_chp] */
