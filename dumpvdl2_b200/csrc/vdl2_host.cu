@@ -84,6 +84,7 @@ struct vdl2gpu_ctx {
 	uint32_t raw_bytes = 0;                             /* size of each slot's raw staging buffers (allocated on the first host submit) */
 	int k1_variant = 2, k2_variant = 5, k2a_mode = 1;   /* A/B knobs (VDL2GPU_K1_VARIANT, VDL2GPU_K2_VARIANT, VDL2GPU_K2A), read at create */
 	bool use_graphs = true;
+	bool k2a_exclusive = true;                          /* K1 of chunk c+1 waits for K2a of chunk c (VDL2GPU_K2A_EXCLUSIVE=0: let them overlap) */
 	uint64_t overflows_reported = 0;
 	host_tables tab;
 	vdl2_tables *d_tab = nullptr;
@@ -226,6 +227,7 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 		if((e = getenv("VDL2GPU_K2A"))) c->k2a_mode = atoi(e);
 		if((e = getenv("VDL2GPU_NO_GRAPH")) && atoi(e)) c->use_graphs = false;
 		if((e = getenv("VDL2GPU_BLOCK_TRACE")) && atoi(e)) c->block_trace_cap = 1u << 16;
+		if((e = getenv("VDL2GPU_K2A_EXCLUSIVE"))) c->k2a_exclusive = atoi(e) != 0;
 	}
 	if(cfg->flags & (VDL2GPU_FLAG_NO_GRAPH | VDL2GPU_FLAG_TRACE)) c->use_graphs = false;
 	c->freqs.assign(cfg->freqs, cfg->freqs + cfg->n_channels);
@@ -620,7 +622,7 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	if(c->chunk_seq >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_back_done[db], 0));   /* K2 of chunk c-2 has read this buffer */
 	/* K1 (one warp per SM sub-partition, latency-bound) pairs well with the equally latency-bound walker K2 and K3 of
 	 * the previous chunk, but not with K2a, a full-occupancy issue-bound pass: let K2a of chunk c-1 finish first */
-	if(c->chunk_seq >= 1 && c->s_back != c->stream) CU(cudaStreamWaitEvent(c->stream, c->ev_k2a_done, 0));
+	if(c->k2a_exclusive && c->chunk_seq >= 1 && c->s_back != c->stream) CU(cudaStreamWaitEvent(c->stream, c->ev_k2a_done, 0));
 	if(graph) {
 		s.h_args->raw = d_raw; s.h_args->dec_base = s.dec_base; s.h_args->n_pairs = n_pairs; s.h_args->cnt0 = c->decim_cnt;
 		s.h_args->n_dec = s.n_dec; s.h_args->pad = 0;
