@@ -96,6 +96,7 @@ struct vdl2gpu_mg {
 	cudaStream_t s_comm = nullptr, s_half[2] = { nullptr, nullptr };
 	cudaEvent_t ev_staged[2] = { nullptr, nullptr }, ev_gathered = nullptr;
 	uint32_t seq[2] = { 0, 0 };                  /* how many times each half has been filled */
+	uint32_t submitted[2] = { 0, 0 };            /* the filling of each half that vdl2gpu_mg_submit last consumed */
 	uint32_t next_half = 0;
 	bool imported = false;
 	mg_nccl_comm comm = nullptr;
@@ -226,6 +227,11 @@ extern "C" int vdl2gpu_mg_stage(vdl2gpu_mg *m, const void *const *src, const uin
 	/* this rank's own K0 kernels of the previous use: the context's "input consumed" event (recorded per chunk) */
 	int rc = vdl2gpu_wait_input_consumed(m->ctx, m->s_comm);
 	if(rc) return rc;
+	if(m->mode == VDL2GPU_MG_COPY_ENGINE && m->rank != 0 && prev != 0 && m->submitted[h] != prev) {
+		/* the previous filling of this half was staged but never submitted here: acknowledge it anyway, rank 0 waits for
+		 * every rank's acknowledgement before it overwrites the half */
+		MG_DRV(g_write32((CUstream)m->s_half[h], (CUdeviceptr)(m->root_flags + 2 + 2 * m->rank + h), prev, CU_STREAM_WRITE_VALUE_DEFAULT));
+	}
 	if(m->rank == 0) {
 		if(n_src == 0 || !src || !src_bytes) return VDL2GPU_EINVAL;
 		uint32_t off = 0;
@@ -278,6 +284,7 @@ extern "C" int vdl2gpu_mg_submit(vdl2gpu_mg *m, int h, uint32_t n_chunks, uint32
 		int rc = vdl2gpu_submit_device(m->ctx, m->recv[h] + (size_t)k * chunk_bytes, chunk_bytes, s);
 		if(rc) return rc;
 	}
+	m->submitted[h] = m->seq[h];
 	if(m->mode == VDL2GPU_MG_COPY_ENGINE && m->rank != 0) {
 		/* tell rank 0 that this half has been read (after the last chunk's K0) */
 		int rc = vdl2gpu_wait_input_consumed(m->ctx, s);

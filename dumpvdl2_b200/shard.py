@@ -56,9 +56,10 @@ class MultiGpuIngest:
     """ctypes face of vdl2gpu_mg_* (include/vdl2gpu.h): the double-buffered fan-out of every step's chunks from rank 0.
     torch.distributed only carries the set-up blobs (NCCL unique id / CUDA IPC handles) between the processes.
 
-    mode: "nccl", "ce" (copy engines + stream memory operations, no kernel), or "auto" (ce if every rank can set it up)."""
+    mode: "nccl" (default), "ce" (copy engines + stream memory operations, no kernel), or "auto" (ce if every rank can set
+    it up, else nccl)."""
 
-    def __init__(self, channels, rank, world, stage_bytes, mode="auto", share_from=None):
+    def __init__(self, channels, rank, world, stage_bytes, mode="nccl", share_from=None):
         import ctypes as C
         import torch.distributed as dist
         from . import api
