@@ -314,7 +314,7 @@ class Vdl2Channels:
         _check(self.L, self.L.vdl2gpu_enable_timing(self.h, 1 if on else 0), "vdl2gpu_enable_timing")
 
     def timeline(self, cap=4096):
-        """rows of [chunk, front start, K0|K1, K1 end, back start, K2a|K2, K2|K3, K3 end] (ms) for the timed chunks"""
+        """rows of [chunk, front start, K1 end, K2a start, K2a end, K2 start, K2|K3, K3 end] (ms) for the timed chunks"""
         a = np.zeros((cap, 8), np.float32)
         n = _check(self.L, self.L.vdl2gpu_get_timeline(self.h, a.ctypes.data, cap), "vdl2gpu_get_timeline")
         return a[:n]

@@ -50,14 +50,14 @@ struct chunk_slot {
 	uint8_t *h_raw = nullptr, *d_raw = nullptr;
 	uint8_t *h_out = nullptr, *d_out = nullptr;
 	cudaEvent_t done = nullptr;
-	cudaEvent_t tk[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   /* front: 0,1,2  back: 3,6,4,5 */
+	cudaEvent_t tk[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   /* front: 0,1,2  mid: 3,6  back: 7,4,5 */
 	bool busy = false, timed = false;
 	uint64_t seq = 0;
 	/* per-chunk arguments (pinned host copy, device copy made by the first node of the front graph) and the three
 	 * CUDA graphs of this slot per decimated-sample buffer: front {args copy, K0, K1}, K2a, back {K2, history, K3, finish} */
 	vdl2_chunk_args *h_args = nullptr, *d_args = nullptr;
-	cudaGraphExec_t g_front[2] = { nullptr, nullptr }, g_k2a[2] = { nullptr, nullptr }, g_back[2] = { nullptr, nullptr };
-	uint32_t graph_pairs[2] = { 0, 0 };
+	cudaGraphExec_t g_front[6] = { nullptr }, g_k2a[6] = { nullptr }, g_back[6] = { nullptr };    /* index = chunk number mod 6 (dec buffer, plane) */
+	uint32_t graph_pairs[6] = { 0 };
 	uint64_t first_pair = 0, dec_base = 0;
 	uint32_t n_pairs = 0, n_dec = 0;
 	struct timeval arrival = { 0, 0 };
@@ -72,8 +72,11 @@ struct vdl2gpu_ctx {
 	 * 12.1 -> 8.7 ms per chunk on B200.  This only works because every kernel of the chain requests the SAME
 	 * shared-memory carve-out (vdl2_kernels.cu): with per-kernel defaults the SMs drain to re-partition L1/shared
 	 * memory and the overlap is a 1.7x slow-down.  VDL2GPU_FLAG_NO_OVERLAP puts everything on one stream. */
-	cudaStream_t stream = nullptr, s_back = nullptr;
-	cudaEvent_t ev_k1_done[2] = { nullptr, nullptr }, ev_back_done[2] = { nullptr, nullptr }, ev_k2a_done = nullptr;
+	cudaStream_t stream = nullptr, s_mid = nullptr, s_back = nullptr;
+	/* three stages, three chunks in flight: K0+K1 of chunk c+2 (front), K2a of chunk c+1 (mid), K2+K3 of chunk c (back).
+	 * dec is triple-buffered (written by K1, read by K2a and K2), the phase / magnitude planes alternate (written by K2a,
+	 * read by K2; K2a of chunk c takes its 160 history rows from the other plane, i.e. from chunk c-1). */
+	cudaEvent_t ev_k1_done[3] = { nullptr, nullptr, nullptr }, ev_back_done[3] = { nullptr, nullptr, nullptr }, ev_k2a_done[2] = { nullptr, nullptr };
 	uint64_t chunk_seq = 0;
 	cudaEvent_t ev_input_ready = nullptr, ev_input_consumed = nullptr;
 	uint32_t n_ch = 0, n_chp = 0, max_pairs = 0, max_dec = 0, n_slots = 0, out_cap = 0, event_cap = 0;
@@ -89,8 +92,8 @@ struct vdl2gpu_ctx {
 	host_tables tab;
 	vdl2_tables *d_tab = nullptr;
 	float2 *d_samples = nullptr;
-	float2 *d_dec2[2] = { nullptr, nullptr };
-	float *d_phase = nullptr, *d_mag = nullptr, *d_hist_tmp = nullptr;
+	float2 *d_dec3[3] = { nullptr, nullptr, nullptr };
+	float *d_phase2[2] = { nullptr, nullptr }, *d_mag2[2] = { nullptr, nullptr };
 	uint32_t *d_k1 = nullptr, *d_k2 = nullptr, *d_counters = nullptr, *d_ready = nullptr;
 	float *d_ring = nullptr;
 	vdl2_burst_slot *d_pool = nullptr;
@@ -158,6 +161,7 @@ static int free_ctx(vdl2gpu_ctx *c) {
 	if(!c) return VDL2GPU_OK;
 	cudaSetDevice(c->device);
 	if(c->stream) cudaStreamSynchronize(c->stream);
+	if(c->s_mid) cudaStreamSynchronize(c->s_mid);
 	if(c->s_back) cudaStreamSynchronize(c->s_back);
 	for(auto &s : c->chunks) {
 		if(s.h_raw) cudaFreeHost(s.h_raw);
@@ -165,7 +169,7 @@ static int free_ctx(vdl2gpu_ctx *c) {
 		if(s.h_out) cudaFreeHost(s.h_out);
 		if(s.done) cudaEventDestroy(s.done);
 		for(auto &e : s.tk) if(e) cudaEventDestroy(e);
-		for(int i = 0; i < 2; i++) {
+		for(int i = 0; i < 6; i++) {
 			if(s.g_front[i]) cudaGraphExecDestroy(s.g_front[i]);
 			if(s.g_k2a[i]) cudaGraphExecDestroy(s.g_k2a[i]);
 			if(s.g_back[i]) cudaGraphExecDestroy(s.g_back[i]);
@@ -173,15 +177,19 @@ static int free_ctx(vdl2gpu_ctx *c) {
 		if(s.h_args) cudaFreeHost(s.h_args);
 		if(s.d_args) cudaFree(s.d_args);
 	}
-	cudaFree(c->d_tab); cudaFree(c->d_samples); cudaFree(c->d_dec2[0]); cudaFree(c->d_dec2[1]); cudaFree(c->d_phase); cudaFree(c->d_mag); cudaFree(c->d_hist_tmp); cudaFree(c->d_k1); cudaFree(c->d_k2);
+	cudaFree(c->d_tab); cudaFree(c->d_samples);
+	for(int i = 0; i < 3; i++) cudaFree(c->d_dec3[i]);
+	for(int i = 0; i < 2; i++) { cudaFree(c->d_phase2[i]); cudaFree(c->d_mag2[i]); }
+	cudaFree(c->d_k1); cudaFree(c->d_k2);
 	cudaFree(c->d_counters); cudaFree(c->d_ready); cudaFree(c->d_ring); cudaFree(c->d_pool); cudaFree(c->d_free);
 	cudaFree(c->d_ctl); cudaFree(c->d_events); cudaFree(c->d_block_trace);
 	if(c->ev_input_ready) cudaEventDestroy(c->ev_input_ready);
 	if(c->ev_input_consumed) cudaEventDestroy(c->ev_input_consumed);
 	if(c->ev_drain) cudaEventDestroy(c->ev_drain);
 	if(c->ev_t0) cudaEventDestroy(c->ev_t0);
-	if(c->ev_k2a_done) cudaEventDestroy(c->ev_k2a_done);
-	for(int i = 0; i < 2; i++) { if(c->ev_k1_done[i]) cudaEventDestroy(c->ev_k1_done[i]); if(c->ev_back_done[i]) cudaEventDestroy(c->ev_back_done[i]); }
+	for(int i = 0; i < 2; i++) if(c->ev_k2a_done[i]) cudaEventDestroy(c->ev_k2a_done[i]);
+	for(int i = 0; i < 3; i++) { if(c->ev_k1_done[i]) cudaEventDestroy(c->ev_k1_done[i]); if(c->ev_back_done[i]) cudaEventDestroy(c->ev_back_done[i]); }
+	if(c->s_mid && c->s_mid != c->stream) cudaStreamDestroy(c->s_mid);
 	if(c->s_back && c->s_back != c->stream) cudaStreamDestroy(c->s_back);
 	if(c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -274,10 +282,10 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 
 	/* equal (default) priorities: raising either stage's priority slowed the pair down (tools/probe_overlap.py) */
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-	if(cfg->flags & VDL2GPU_FLAG_NO_OVERLAP) c->s_back = c->stream;
-	else CU(cudaStreamCreateWithFlags(&c->s_back, cudaStreamNonBlocking));
-	CU(cudaEventCreateWithFlags(&c->ev_k2a_done, cudaEventDisableTiming));
-	for(int i = 0; i < 2; i++) {
+	if(cfg->flags & VDL2GPU_FLAG_NO_OVERLAP) { c->s_back = c->stream; c->s_mid = c->stream; }
+	else { CU(cudaStreamCreateWithFlags(&c->s_back, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&c->s_mid, cudaStreamNonBlocking)); }
+	for(int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&c->ev_k2a_done[i], cudaEventDisableTiming));
+	for(int i = 0; i < 3; i++) {
 		CU(cudaEventCreateWithFlags(&c->ev_k1_done[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&c->ev_back_done[i], cudaEventDisableTiming));
 	}
@@ -294,14 +302,15 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	CU(cudaMemcpy(c->d_tab, &c->tab.t, sizeof(vdl2_tables), cudaMemcpyHostToDevice));
 	if(c->lane_streams) CU(cudaMalloc(&c->d_samples, (size_t)c->max_pairs * c->n_chp * sizeof(float2)));
 	else CU(cudaMalloc(&c->d_samples, (size_t)c->n_streams * c->max_pairs * sizeof(float2)));
-	for(int i = 0; i < 2; i++) {
-		CU(cudaMalloc(&c->d_dec2[i], (size_t)c->max_dec * c->n_chp * sizeof(float2)));
-		CU(cudaMemset(c->d_dec2[i], 0, (size_t)c->max_dec * c->n_chp * sizeof(float2)));
+	for(int i = 0; i < 3; i++) {
+		CU(cudaMalloc(&c->d_dec3[i], (size_t)c->max_dec * c->n_chp * sizeof(float2)));
+		CU(cudaMemset(c->d_dec3[i], 0, (size_t)c->max_dec * c->n_chp * sizeof(float2)));
 	}
-	CU(cudaMalloc(&c->d_phase, (size_t)(c->max_dec + VDL2_SYNC_BUFLEN) * c->n_chp * sizeof(float)));
-	CU(cudaMemset(c->d_phase, 0, (size_t)(c->max_dec + VDL2_SYNC_BUFLEN) * c->n_chp * sizeof(float)));
-	CU(cudaMalloc(&c->d_mag, (size_t)c->max_dec * c->n_chp * sizeof(float)));
-	CU(cudaMalloc(&c->d_hist_tmp, (size_t)VDL2_SYNC_BUFLEN * c->n_chp * sizeof(float)));
+	for(int i = 0; i < 2; i++) {
+		CU(cudaMalloc(&c->d_phase2[i], (size_t)(c->max_dec + VDL2_SYNC_BUFLEN) * c->n_chp * sizeof(float)));
+		CU(cudaMemset(c->d_phase2[i], 0, (size_t)(c->max_dec + VDL2_SYNC_BUFLEN) * c->n_chp * sizeof(float)));
+		CU(cudaMalloc(&c->d_mag2[i], (size_t)c->max_dec * c->n_chp * sizeof(float)));
+	}
 	CU(cudaMalloc(&c->d_k1, (size_t)K1_NFIELDS * c->n_chp * 4));
 	CU(cudaMalloc(&c->d_k2, (size_t)K2_NFIELDS * c->n_chp * 4));
 	CU(cudaMalloc(&c->d_counters, (size_t)VDL2_NUM_COUNTERS * c->n_chp * 4));
@@ -431,13 +440,13 @@ static void parse_region(const uint8_t *region, uint32_t out_cap, double rate, s
 
 static void harvest(vdl2gpu_ctx *c, chunk_slot &s) {
 	if(s.timed) {
-		static const int from[5] = { 0, 1, 3, 6, 4 }, to[5] = { 1, 2, 6, 4, 5 };   /* K0, K1 on the front stream; K2a, K2, K3 on the back stream */
+		static const int from[5] = { 0, 1, 3, 7, 4 }, to[5] = { 1, 2, 6, 4, 5 };   /* K0, K1 front stream; K2a middle stream; K2, K3 back stream */
 		for(int k = 0; k < 5; k++) {
 			float ms = 0.f;
 			if(cudaEventElapsedTime(&ms, s.tk[from[k]], s.tk[to[k]]) == cudaSuccess) { c->k_ms[k] += ms; c->k_launches[k]++; }
 		}
 		if(c->ev_t0 && c->timeline.size() < 8u * 4096u) {
-			static const int order[7] = { 0, 1, 2, 3, 6, 4, 5 };   /* front start, K0|K1, K1 end, back start, K2a|K2, K2|K3, K3 end */
+			static const int order[7] = { 0, 2, 3, 6, 7, 4, 5 };   /* front start, K1 end, K2a start, K2a end, K2 start, K2|K3, K3 end */
 			c->timeline.push_back((float)s.seq);
 			for(int k = 0; k < 7; k++) {
 				float ms = -1.f;
@@ -508,11 +517,12 @@ static int acquire_slot(vdl2gpu_ctx *c, chunk_slot **out) {
 	return VDL2GPU_OK;
 }
 
-/* parameter blocks of one chunk.  With `ca` the per-chunk values come from the device copy of the chunk arguments
- * (graph replay); the sizes given here then only size the grids. */
-static void fill_params(vdl2gpu_ctx *c, chunk_slot &s, int db, uint32_t n_pairs, uint32_t cnt0, uint32_t n_dec, uint64_t dec_base,
-		const vdl2_chunk_args *ca, vdl2_k1_params &p1, vdl2_k2_params &p2, vdl2_k3_params &p3) {
-	float2 *d_dec = c->d_dec2[db];
+/* parameter blocks of one chunk (number `seq`).  With `ca` the per-chunk values come from the device copy of the chunk
+ * arguments (graph replay); the sizes given here then only size the grids. */
+static void fill_params(vdl2gpu_ctx *c, chunk_slot &s, uint64_t seq, uint32_t n_pairs, uint32_t cnt0, uint32_t n_dec, uint32_t prev_n_dec,
+		uint64_t dec_base, const vdl2_chunk_args *ca, vdl2_k1_params &p1, vdl2_k2a_params &pa, vdl2_k2_params &p2, vdl2_k3_params &p3) {
+	float2 *d_dec = c->d_dec3[seq % 3u];
+	const int pb = (int)(seq & 1u);
 	p1.samples = c->d_samples; p1.n_pairs = n_pairs; p1.oversample = c->cfg.oversample; p1.cnt0 = cnt0;
 	p1.n_ch = c->n_ch; p1.n_chp = c->n_chp; p1.lanes = c->lanes; p1.full_warps = c->full_warps; p1.dec = d_dec; p1.state = c->d_k1;
 	p1.lut = reinterpret_cast<const float4 *>(c->d_tab->lut);
@@ -520,7 +530,11 @@ static void fill_params(vdl2gpu_ctx *c, chunk_slot &s, int db, uint32_t n_pairs,
 	p1.one = 1.0f; p1.neg_one = -1.0f; p1.two = 2.0f;
 	p1.trace_blocks = c->d_block_trace; p2.trace_blocks = c->d_block_trace;
 	p1.ch_per_stream = c->ch_per_stream; p1.stream_stride = c->lane_streams ? c->n_chp : c->max_pairs; p1.ca = ca;
-	p2.dec = d_dec; p2.phase = c->d_phase; p2.mag = c->d_mag; p2.hist_tmp = c->d_hist_tmp; p2.n_dec = n_dec; p2.n_ch = c->n_ch; p2.n_chp = c->n_chp; p2.lanes = c->lanes; p2.full_warps = c->full_warps; p2.dec_base = dec_base;
+	pa.dec = d_dec; pa.phase = c->d_phase2[pb]; pa.mag = c->d_mag2[pb]; pa.phase_prev = c->d_phase2[pb ^ 1];
+	pa.n_dec = n_dec; pa.prev_n_dec = prev_n_dec; pa.n_ch = c->n_ch; pa.n_chp = c->n_chp; pa.lanes = c->lanes; pa.full_warps = c->full_warps;
+	pa.mode = (uint32_t)c->k2a_mode; pa.ca = ca;
+	p2.dec = d_dec; p2.phase = c->d_phase2[pb]; p2.mag = c->d_mag2[pb]; p2.hist_tmp = nullptr; p2.n_dec = n_dec; p2.n_ch = c->n_ch; p2.n_chp = c->n_chp;
+	p2.lanes = c->lanes; p2.full_warps = c->full_warps; p2.dec_base = dec_base;
 	p2.state = c->d_k2; p2.ring = c->d_ring; p2.tables = c->d_tab; p2.max_ppm = c->cfg.max_ppm; p2.s27 = c->tab.s27;
 	p2.pool = c->d_pool; p2.free_list = c->d_free; p2.ready = c->d_ready; p2.ctl = c->d_ctl;
 	p2.events = c->d_events; p2.event_cap = c->event_cap; p2.trace = (c->cfg.flags & VDL2GPU_FLAG_TRACE) ? 1u : 0u;
@@ -529,12 +543,12 @@ static void fill_params(vdl2gpu_ctx *c, chunk_slot &s, int db, uint32_t n_pairs,
 	p3.out = s.d_out; p3.out_cap = c->out_cap; p3.n_chp = c->n_chp; p3.counters = c->d_counters;
 }
 
-#define K3_GRID (148u * 16u)      /* 16 resident blocks per SM (11.4 KB shared memory each): ~1.5 bursts per block per chunk at the bench traffic */
+#define K3_GRID (148u * 16u)      /* 16 resident blocks per SM: ~1.5 bursts per block per chunk at the bench traffic */
 
-/* One CUDA graph per stage, slot and decimated-sample buffer, captured once for the chunk shape (n_pairs) and replayed:
- * a chunk then costs three graph launches and a handful of event calls instead of eight kernel launches.  Everything
- * that differs between two chunks of the same shape (input pointer, decimation phase, sample counts, absolute sample
- * index) travels in the chunk-argument block the front graph copies to the device first. */
+/* One CUDA graph per stage, captured once per (slot, chunk number mod 6 = dec buffer and plane) for the chunk shape
+ * (n_pairs) and replayed: a chunk then costs three graph launches and a handful of event calls instead of seven kernel
+ * launches.  Everything that differs between two chunks of the same shape (input pointer, decimation phase, sample
+ * counts, absolute sample index) travels in the chunk-argument block the front graph copies to the device first. */
 static int capture_one(cudaStream_t st, cudaGraphExec_t *out, int (*body)(void *), void *arg) {
 	cudaGraph_t g = nullptr;
 	CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
@@ -547,14 +561,17 @@ static int capture_one(cudaStream_t st, cudaGraphExec_t *out, int (*body)(void *
 	return VDL2GPU_OK;
 }
 
-struct capture_env { vdl2gpu_ctx *c; chunk_slot *s; int db; uint32_t n_pairs; uint32_t k0_fmt; };
+struct capture_env { vdl2gpu_ctx *c; chunk_slot *s; uint64_t seq; uint32_t n_pairs; uint32_t k0_fmt; };
+#define CAPTURE_PARAMS \
+	capture_env *e = static_cast<capture_env *>(a); \
+	vdl2gpu_ctx *c = e->c; \
+	vdl2_k1_params p1; vdl2_k2a_params pa; vdl2_k2_params p2; vdl2_k3_params p3; \
+	const uint32_t os = c->cfg.oversample; \
+	fill_params(c, *e->s, e->seq, e->n_pairs, 0, (os - 1 + e->n_pairs) / os, 0, 0, e->s->d_args, p1, pa, p2, p3)
 
 static int body_front(void *a) {
-	capture_env *e = static_cast<capture_env *>(a);
-	vdl2gpu_ctx *c = e->c;
-	vdl2_k1_params p1; vdl2_k2_params p2; vdl2_k3_params p3;
-	const uint32_t os = c->cfg.oversample;
-	fill_params(c, *e->s, e->db, e->n_pairs, 0, (os - 1 + e->n_pairs) / os, 0, e->s->d_args, p1, p2, p3);
+	CAPTURE_PARAMS;
+	(void)pa; (void)p2; (void)p3;
 	CU(cudaMemcpyAsync(e->s->d_args, e->s->h_args, sizeof(vdl2_chunk_args), cudaMemcpyHostToDevice, c->stream));
 	const uint32_t bpp = c->cfg.sample_fmt == VDL2GPU_FMT_S16_LE ? 4u : 2u;
 	if(c->lane_streams) KL(vdl2_launch_k0_lanes(nullptr, e->n_pairs, e->k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->n_streams,
@@ -565,36 +582,30 @@ static int body_front(void *a) {
 	return 0;
 }
 static int body_k2a(void *a) {
-	capture_env *e = static_cast<capture_env *>(a);
-	vdl2gpu_ctx *c = e->c;
-	vdl2_k1_params p1; vdl2_k2_params p2; vdl2_k3_params p3;
-	const uint32_t os = c->cfg.oversample;
-	fill_params(c, *e->s, e->db, e->n_pairs, 0, (os - 1 + e->n_pairs) / os, 0, e->s->d_args, p1, p2, p3);
-	KL(vdl2_launch_k2a(&p2, c->s_back));
+	CAPTURE_PARAMS;
+	(void)p1; (void)p2; (void)p3;
+	KL(vdl2_launch_k2a_warps(&pa, c->s_mid));
 	return 0;
 }
 static int body_back(void *a) {
-	capture_env *e = static_cast<capture_env *>(a);
-	vdl2gpu_ctx *c = e->c;
-	vdl2_k1_params p1; vdl2_k2_params p2; vdl2_k3_params p3;
-	const uint32_t os = c->cfg.oversample;
-	fill_params(c, *e->s, e->db, e->n_pairs, 0, (os - 1 + e->n_pairs) / os, 0, e->s->d_args, p1, p2, p3);
+	CAPTURE_PARAMS;
+	(void)p1; (void)pa;
 	KL(vdl2_launch_k2(&p2, c->s_back));
-	KL(vdl2_launch_copy_hist(&p2, c->s_back));
 	KL(vdl2_launch_k3(&p3, K3_GRID, c->s_back));
 	return 0;
 }
 
-static int ensure_graphs(vdl2gpu_ctx *c, chunk_slot &s, int db, uint32_t n_pairs, uint32_t k0_fmt) {
-	if(s.g_front[db] && s.graph_pairs[db] == n_pairs) return VDL2GPU_OK;
-	if(s.g_front[db]) { cudaGraphExecDestroy(s.g_front[db]); s.g_front[db] = nullptr; }
-	if(s.g_k2a[db]) { cudaGraphExecDestroy(s.g_k2a[db]); s.g_k2a[db] = nullptr; }
-	if(s.g_back[db]) { cudaGraphExecDestroy(s.g_back[db]); s.g_back[db] = nullptr; }
-	capture_env e = { c, &s, db, n_pairs, k0_fmt };
-	int rc = capture_one(c->stream, &s.g_front[db], body_front, &e);
-	if(rc == 0) rc = capture_one(c->s_back, &s.g_k2a[db], body_k2a, &e);
-	if(rc == 0) rc = capture_one(c->s_back, &s.g_back[db], body_back, &e);
-	if(rc == 0) s.graph_pairs[db] = n_pairs;
+static int ensure_graphs(vdl2gpu_ctx *c, chunk_slot &s, uint64_t seq, uint32_t n_pairs, uint32_t k0_fmt) {
+	const int k = (int)(seq % 6u);
+	if(s.g_front[k] && s.graph_pairs[k] == n_pairs) return VDL2GPU_OK;
+	if(s.g_front[k]) { cudaGraphExecDestroy(s.g_front[k]); s.g_front[k] = nullptr; }
+	if(s.g_k2a[k]) { cudaGraphExecDestroy(s.g_k2a[k]); s.g_k2a[k] = nullptr; }
+	if(s.g_back[k]) { cudaGraphExecDestroy(s.g_back[k]); s.g_back[k] = nullptr; }
+	capture_env e = { c, &s, seq, n_pairs, k0_fmt };
+	int rc = capture_one(c->stream, &s.g_front[k], body_front, &e);
+	if(rc == 0) rc = capture_one(c->s_mid, &s.g_k2a[k], body_k2a, &e);
+	if(rc == 0) rc = capture_one(c->s_back, &s.g_back[k], body_back, &e);
+	if(rc == 0) s.graph_pairs[k] = n_pairs;
 	return rc;
 }
 
@@ -608,63 +619,59 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	s.n_dec = (c->decim_cnt + n_pairs) / os;
 	gettimeofday(&s.arrival, NULL);
 	s.timed = c->timing;
-	const int db = (int)(c->chunk_seq & 1u);                 /* decimated-sample buffer of this chunk */
+	const uint64_t seq = c->chunk_seq;
+	const int db = (int)(seq % 3u), pb = (int)(seq & 1u), gk = (int)(seq % 6u);
 	const uint32_t bpp = c->cfg.sample_fmt == VDL2GPU_FMT_S16_LE ? 4u : 2u;
-	/* graph replay needs the history copy to be the single-kernel form for every chunk of this shape (n_dec >= 160) */
-	s.seq = c->chunk_seq;
-	bool graph = c->use_graphs && !planar && c->s_back != c->stream && n_pairs / os >= VDL2_SYNC_BUFLEN;
+	const bool overlap = c->s_back != c->stream;
+	s.seq = seq;
+	bool graph = c->use_graphs && !planar && overlap;
 	if(graph && c->graph_nominal == 0) c->graph_nominal = n_pairs;
 	graph = graph && n_pairs == c->graph_nominal;            /* odd-sized chunks (the tail of a file) take the direct path */
-	if(graph && ensure_graphs(c, s, db, n_pairs, k0_fmt) != VDL2GPU_OK) { c->use_graphs = false; graph = false; }
-	vdl2_k1_params p1; vdl2_k2_params p2; vdl2_k3_params p3;
-	fill_params(c, s, db, n_pairs, c->decim_cnt, s.n_dec, s.dec_base, nullptr, p1, p2, p3);
-	/* ---- front stage: K0, K1 ---- */
-	if(c->chunk_seq >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_back_done[db], 0));   /* K2 of chunk c-2 has read this buffer */
-	/* K1 (one warp per SM sub-partition, latency-bound) pairs well with the equally latency-bound walker K2 and K3 of
-	 * the previous chunk, but not with K2a, a full-occupancy issue-bound pass: let K2a of chunk c-1 finish first */
-	if(c->k2a_exclusive && c->chunk_seq >= 1 && c->s_back != c->stream) CU(cudaStreamWaitEvent(c->stream, c->ev_k2a_done, 0));
+	if(graph && ensure_graphs(c, s, seq, n_pairs, k0_fmt) != VDL2GPU_OK) { c->use_graphs = false; graph = false; }
+	vdl2_k1_params p1; vdl2_k2a_params pa; vdl2_k2_params p2; vdl2_k3_params p3;
+	fill_params(c, s, seq, n_pairs, c->decim_cnt, s.n_dec, c->last_n_dec, s.dec_base, nullptr, p1, pa, p2, p3);
 	if(graph) {
 		s.h_args->raw = d_raw; s.h_args->dec_base = s.dec_base; s.h_args->n_pairs = n_pairs; s.h_args->cnt0 = c->decim_cnt;
-		s.h_args->n_dec = s.n_dec; s.h_args->pad = 0;
-		/* timed chunks: stage boundaries only (K0 counts into K1, K3 into K2) */
-		if(s.timed) { CU(cudaEventRecord(s.tk[0], c->stream)); CU(cudaEventRecord(s.tk[1], c->stream)); }
-		CU(cudaGraphLaunch(s.g_front[db], c->stream));
-		if(s.timed) CU(cudaEventRecord(s.tk[2], c->stream));
-		CU(cudaEventRecord(c->ev_input_consumed, c->stream));
-		CU(cudaEventRecord(c->ev_k1_done[db], c->stream));
-		CU(cudaStreamWaitEvent(c->s_back, c->ev_k1_done[db], 0));
-		if(s.timed) CU(cudaEventRecord(s.tk[3], c->s_back));
-		CU(cudaGraphLaunch(s.g_k2a[db], c->s_back));
-		CU(cudaEventRecord(c->ev_k2a_done, c->s_back));
-		if(s.timed) CU(cudaEventRecord(s.tk[6], c->s_back));
-		CU(cudaGraphLaunch(s.g_back[db], c->s_back));
-		CU(cudaEventRecord(c->ev_back_done[db], c->s_back));
-		if(s.timed) { CU(cudaEventRecord(s.tk[4], c->s_back)); CU(cudaEventRecord(s.tk[5], c->s_back)); }
-		c->stats.graph_launches += 3;
+		s.h_args->n_dec = s.n_dec; s.h_args->prev_n_dec = c->last_n_dec;
+	}
+	/* ---- front stage: K0, K1 -> dec[db] (free once K2 of chunk c-3 is done) ---- */
+	if(seq >= 3) CU(cudaStreamWaitEvent(c->stream, c->ev_back_done[db], 0));
+	if(s.timed) { CU(cudaEventRecord(s.tk[0], c->stream)); if(graph) CU(cudaEventRecord(s.tk[1], c->stream)); }
+	if(graph) {
+		CU(cudaGraphLaunch(s.g_front[gk], c->stream));
 	} else {
-		if(s.timed) CU(cudaEventRecord(s.tk[0], c->stream));
 		if(c->lane_streams) KL(vdl2_launch_k0_lanes(d_raw, n_pairs, k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->n_streams,
 				n_pairs * bpp, c->n_chp, nullptr, c->stream));
 		else KL(vdl2_launch_k0(d_raw, n_pairs, k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->n_streams,
 				n_pairs * bpp, c->max_pairs, nullptr, c->stream));
-		CU(cudaEventRecord(c->ev_input_consumed, c->stream));
 		if(s.timed) CU(cudaEventRecord(s.tk[1], c->stream));
 		KL(vdl2_launch_k1(&p1, (c->cfg.flags & VDL2GPU_FLAG_K1_SCALAR) ? 1 : 0, c->k1_variant, c->stream));
-		if(s.timed) CU(cudaEventRecord(s.tk[2], c->stream));
-		CU(cudaEventRecord(c->ev_k1_done[db], c->stream));
-		/* ---- back stage: K2a, K2, K3 ---- */
-		CU(cudaStreamWaitEvent(c->s_back, c->ev_k1_done[db], 0));
-		if(s.timed) CU(cudaEventRecord(s.tk[3], c->s_back));
-		KL(vdl2_launch_k2a(&p2, c->s_back));
-		CU(cudaEventRecord(c->ev_k2a_done, c->s_back));
-		if(s.timed) CU(cudaEventRecord(s.tk[6], c->s_back));
+	}
+	if(s.timed) CU(cudaEventRecord(s.tk[2], c->stream));
+	CU(cudaEventRecord(c->ev_input_consumed, c->stream));
+	CU(cudaEventRecord(c->ev_k1_done[db], c->stream));
+	/* ---- middle stage: K2a -> plane[pb] (free once K2 of chunk c-2 is done), history from plane[pb ^ 1] (chunk c-1, same stream) ---- */
+	CU(cudaStreamWaitEvent(c->s_mid, c->ev_k1_done[db], 0));
+	if(seq >= 2 && overlap) CU(cudaStreamWaitEvent(c->s_mid, c->ev_back_done[(seq - 2) % 3u], 0));
+	if(s.timed) CU(cudaEventRecord(s.tk[3], c->s_mid));
+	if(graph) CU(cudaGraphLaunch(s.g_k2a[gk], c->s_mid));
+	else KL(vdl2_launch_k2a_warps(&pa, c->s_mid));
+	if(s.timed) CU(cudaEventRecord(s.tk[6], c->s_mid));
+	CU(cudaEventRecord(c->ev_k2a_done[pb], c->s_mid));
+	/* ---- back stage: K2, K3 ---- */
+	CU(cudaStreamWaitEvent(c->s_back, c->ev_k2a_done[pb], 0));
+	if(s.timed) CU(cudaEventRecord(s.tk[7], c->s_back));
+	if(graph) {
+		CU(cudaGraphLaunch(s.g_back[gk], c->s_back));
+		if(s.timed) CU(cudaEventRecord(s.tk[4], c->s_back));
+		c->stats.graph_launches += 3;
+	} else {
 		KL(vdl2_launch_k2(&p2, c->s_back));
-		KL(vdl2_launch_copy_hist(&p2, c->s_back));
-		CU(cudaEventRecord(c->ev_back_done[db], c->s_back));
 		if(s.timed) CU(cudaEventRecord(s.tk[4], c->s_back));
 		KL(vdl2_launch_k3(&p3, K3_GRID, c->s_back));
-		if(s.timed) CU(cudaEventRecord(s.tk[5], c->s_back));
 	}
+	if(s.timed) CU(cudaEventRecord(s.tk[5], c->s_back));
+	CU(cudaEventRecord(c->ev_back_done[db], c->s_back));
 	CU(cudaEventRecord(s.done, c->s_back));
 	c->chunk_seq++;
 	s.busy = true;
@@ -677,7 +684,7 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	c->stats.chunks_submitted++;
 	c->stats.iq_samples += n_pairs;
 	c->stats.dec_samples += s.n_dec;
-	c->stats.kernel_launches += (n_pairs ? 2 : 0) + (s.n_dec ? (s.n_dec >= VDL2_SYNC_BUFLEN ? 3 : 4) : 0) + 2;
+	c->stats.kernel_launches += (n_pairs ? 2 : 0) + 1 + (s.n_dec ? 1 : 0) + 2;
 	return VDL2GPU_OK;
 }
 
@@ -890,11 +897,11 @@ extern "C" int vdl2gpu_read_dec(vdl2gpu_ctx *c, float *out, size_t cap_floats, u
 	if((size_t)c->last_n_dec * c->n_ch * 2 > cap_floats) return VDL2GPU_ETOOBIG;
 	if(c->last_n_dec == 0) return VDL2GPU_OK;
 	if(c->lanes == 32) {
-		CU(cudaMemcpy2D(out, (size_t)c->n_ch * sizeof(float2), c->d_dec2[(c->chunk_seq + 1) & 1u], (size_t)c->n_chp * sizeof(float2),
+		CU(cudaMemcpy2D(out, (size_t)c->n_ch * sizeof(float2), c->d_dec3[(c->chunk_seq + 2) % 3u], (size_t)c->n_chp * sizeof(float2),
 				(size_t)c->n_ch * sizeof(float2), c->last_n_dec, cudaMemcpyDeviceToHost));
 	} else {
 		std::vector<float2> tmp((size_t)c->last_n_dec * c->n_chp);
-		CU(cudaMemcpy(tmp.data(), c->d_dec2[(c->chunk_seq + 1) & 1u], tmp.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+		CU(cudaMemcpy(tmp.data(), c->d_dec3[(c->chunk_seq + 2) % 3u], tmp.size() * sizeof(float2), cudaMemcpyDeviceToHost));
 		for(uint32_t m = 0; m < c->last_n_dec; m++)
 			for(uint32_t ch = 0; ch < c->n_ch; ch++) {
 				const float2 v = tmp[(size_t)m * c->n_chp + slot_of(ch, c->lanes, c->full_warps)];

@@ -580,6 +580,59 @@ __global__ void __launch_bounds__(256) k2a_phase_mag(const float2 *__restrict__ 
 	mag[i] = mg;
 }
 
+/* K2a, resident form used by the streaming pipeline: one 128-thread block per SM-sized group of slots, laid out like K1's and
+ * K2's blocks (warp w owns slots 32 w .. 32 w + 31), so that the three kernels of three consecutive chunks sit side by
+ * side on every SM: K1 of chunk c+2, K2a of chunk c+1, K2 of chunk c.  Each thread walks its channel's decimated samples
+ * four at a time (four independent evaluations in flight).  Before that it copies the previous plane's last 160 phase rows
+ * into this plane's history rows (the planes alternate between chunks; with n_dec < 160 the source range still lies inside
+ * the previous plane, history rows included, so short chunks need no special case). */
+template<bool FAST>
+__global__ void __launch_bounds__(128) k2a_phase_mag_warps(vdl2_k2a_params p) {
+	__shared__ double s_atan[VDL2_ATAN_TABLE_DOUBLES];
+	if(FAST) {
+		if(threadIdx.x < VDL2_ATAN_TABLE_DOUBLES) s_atan[threadIdx.x] = c_atan_tab[threadIdx.x];
+		__syncthreads();
+	}
+	const uint32_t slot = blockIdx.x * 128u + threadIdx.x;
+	uint32_t chan;
+	if(!vdl2_slot_channel(slot, p.lanes, p.full_warps, p.n_ch, chan)) return;
+	const uint32_t n_dec = p.ca ? p.ca->n_dec : p.n_dec, prev_n_dec = p.ca ? p.ca->prev_n_dec : p.prev_n_dec;
+	const size_t s = p.n_chp;
+	{
+		const float *src = p.phase_prev + (size_t)prev_n_dec * s + slot;
+		float *dst = p.phase + slot;
+#pragma unroll 8
+		for(uint32_t i = 0; i < VDL2_SYNC_BUFLEN; i++) dst[(size_t)i * s] = src[(size_t)i * s];
+	}
+	const float2 *dec = p.dec + slot;
+	float *ph = p.phase + (size_t)VDL2_SYNC_BUFLEN * s + slot, *mg = p.mag + slot;
+	uint32_t t = 0;
+	for(; t + 4 <= n_dec; t += 4) {
+		float2 d[4];
+		float a[4], m[4];
+		int sp[4], sm[4];
+#pragma unroll
+		for(int k = 0; k < 4; k++) d[k] = dec[(size_t)(t + k) * s];
+#pragma unroll
+		for(int k = 0; k < 4; k++) {
+			if(FAST) { a[k] = vdl2_phase_fast(d[k].x, d[k].y, s_atan, &sp[k]); m[k] = vdl2_mag_fast(d[k].x, d[k].y, &sm[k]); }
+			else { sp[k] = 1; sm[k] = 1; a[k] = 0.f; m[k] = 0.f; }
+		}
+#pragma unroll
+		for(int k = 0; k < 4; k++) {
+			if(sp[k]) a[k] = vdl2_phase_of(d[k].x, d[k].y);
+			if(sm[k]) m[k] = vdl2_mag_of(d[k].x, d[k].y);
+			ph[(size_t)(t + k) * s] = a[k];
+			mg[(size_t)(t + k) * s] = m[k];
+		}
+	}
+	for(; t < n_dec; t++) {
+		const float2 d = dec[(size_t)t * s];
+		ph[(size_t)t * s] = vdl2_phase_of(d.x, d.y);
+		mg[(size_t)t * s] = vdl2_mag_of(d.x, d.y);
+	}
+}
+
 /* carry the last 160 phase rows over to the front of the plane for the next chunk: rows [n_dec, n_dec+160) -> [0, 160) */
 __global__ void __launch_bounds__(256) k_copy_rows(const float *__restrict__ src, float *__restrict__ dst, uint32_t n) {
 	uint32_t i = blockIdx.x * 256u + threadIdx.x;
@@ -1016,6 +1069,8 @@ extern "C" int vdl2_kernels_init_device(int device) {
 		cudaFuncSetAttribute(k1_mix_iir_decimate_lanes<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1L_SMEM_BYTES);
 		cudaFuncSetAttribute(k1_mix_iir_decimate_lanes<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1L_SMEM_BYTES);
 		vdl2_set_carveout(k2a_phase_mag<true>, pct);
+		vdl2_set_carveout(k2a_phase_mag_warps<true>, pct);
+		vdl2_set_carveout(k2a_phase_mag_warps<false>, pct);
 		vdl2_set_carveout(k2a_phase_mag<false>, pct);
 #define K2_SETUP(BLK, BLOCKED, MODE) do { vdl2_set_carveout(k2_sync_slice<BLK, BLOCKED, MODE>, pct); \
 		cudaFuncSetAttribute(k2_sync_slice<BLK, BLOCKED, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_BYTES(BLK, MODE)); } while(0)
@@ -1092,6 +1147,14 @@ extern "C" int vdl2_launch_k2a(const vdl2_k2_params *p, cudaStream_t st) {
 	const uint32_t hist = VDL2_SYNC_BUFLEN * p->n_chp;
 	if(p->k2a_mode) k2a_phase_mag<true><<<(n_elems + 255u) / 256u, 256, 0, st>>>(p->dec, p->phase + hist, p->mag, n_elems, p->n_chp, p->lanes ? p->lanes : 32u, p->ca);
 	else k2a_phase_mag<false><<<(n_elems + 255u) / 256u, 256, 0, st>>>(p->dec, p->phase + hist, p->mag, n_elems, p->n_chp, p->lanes ? p->lanes : 32u, p->ca);
+	return (int)cudaGetLastError();
+}
+
+extern "C" int vdl2_launch_k2a_warps(const vdl2_k2a_params *p, cudaStream_t st) {
+	if(p->n_ch == 0) return 0;
+	const uint32_t blocks = (p->n_chp + 127u) / 128u;
+	if(p->mode) k2a_phase_mag_warps<true><<<blocks, 128, 0, st>>>(*p);
+	else k2a_phase_mag_warps<false><<<blocks, 128, 0, st>>>(*p);
 	return (int)cudaGetLastError();
 }
 

@@ -14,7 +14,7 @@ typedef struct {
 	uint32_t n_pairs;            /* complex samples per stream in this chunk */
 	uint32_t cnt0;               /* decimation counter on entry */
 	uint32_t n_dec;              /* decimated samples this chunk produces */
-	uint32_t pad;
+	uint32_t prev_n_dec;         /* ... and the previous chunk produced (its last 160 phase rows are this chunk's history) */
 } vdl2_chunk_args;
 
 /* optional per-block scheduling trace (VDL2GPU_BLOCK_TRACE=1): every block of K1 and K2 appends one record */
@@ -79,6 +79,19 @@ typedef struct {
 	vdl2_block_trace *trace_blocks;
 } vdl2_k2_params;
 
+/* K2a in its resident form (k2a_phase_mag_warps): warp w computes phase and magnitude of slots [32 w, 32 w + 32) for every
+ * decimated sample of the chunk and first carries the last 160 phase rows of the previous chunk's plane over */
+typedef struct {
+	const float2 *dec;           /* [n_dec][n_chp] */
+	float *phase;                /* this chunk's plane [160 + n_dec][n_chp] */
+	float *mag;                  /* [n_dec][n_chp] */
+	const float *phase_prev;     /* the previous chunk's plane (the other of the two) */
+	uint32_t n_dec, prev_n_dec;
+	uint32_t n_ch, n_chp, lanes, full_warps;
+	uint32_t mode;               /* 0 libdevice atan2 / IEEE sqrt for every sample, 1 the Ziv-guarded short forms */
+	const vdl2_chunk_args *ca;
+} vdl2_k2a_params;
+
 typedef struct {
 	vdl2_burst_slot *pool;
 	int32_t *free_list;
@@ -105,6 +118,7 @@ int vdl2_launch_k0_lanes(const void *raw, uint32_t n_pairs, uint32_t fmt, const 
 int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, int variant, cudaStream_t st);
 int vdl2_launch_copy_hist(const vdl2_k2_params *p, cudaStream_t st);
 int vdl2_launch_k2a(const vdl2_k2_params *p, cudaStream_t st);
+int vdl2_launch_k2a_warps(const vdl2_k2a_params *p, cudaStream_t st);
 int vdl2_launch_k2(const vdl2_k2_params *p, cudaStream_t st);
 int vdl2_launch_k3(const vdl2_k3_params *p, uint32_t grid, cudaStream_t st);
 int vdl2_launch_k4(const uint8_t *frames, const uint32_t *offsets, const uint32_t *lens, uint32_t n, uint16_t *out, cudaStream_t st);

@@ -220,8 +220,8 @@ int vdl2gpu_read_events(vdl2gpu_ctx *ctx, vdl2gpu_event *out, uint32_t cap);
 int vdl2gpu_enable_timing(vdl2gpu_ctx *ctx, int on);
 int vdl2gpu_get_kernel_ms(vdl2gpu_ctx *ctx, double ms[5], uint64_t launches[5]);
 /* stage boundaries of the timed chunks harvested so far, 8 floats per chunk: chunk number, then ms since
- * vdl2gpu_enable_timing(ctx, 1) of: front start, K0|K1, K1 end, back start, K2a|K2, K2|K3, K3 end (with graph replay
- * only the stage boundaries are known: K0 counts into K1 and K3 into K2).  Returns the number of rows copied. */
+ * vdl2gpu_enable_timing(ctx, 1) of: front (K0+K1) start, K1 end, K2a start, K2a end, K2 start, K2|K3, K3 end (with graph
+ * replay K3 counts into K2).  Returns the number of rows copied. */
 int vdl2gpu_get_timeline(vdl2gpu_ctx *ctx, float *out, uint32_t cap_rows);
 /* diagnostic (context created with VDL2GPU_BLOCK_TRACE=1 in the environment): where and when every block of K1 / K2 ran,
  * 6 x uint64 per record {kernel (1 K1, 2 K2), block, SM id, 0, start ns, end ns}.  Synchronises. */
