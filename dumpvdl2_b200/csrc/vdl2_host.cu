@@ -87,6 +87,7 @@ struct vdl2gpu_ctx {
 	uint32_t raw_bytes = 0;                             /* size of each slot's raw staging buffers (allocated on the first host submit) */
 	int k1_variant = 2, k2_variant = 5, k2a_mode = 1;   /* A/B knobs (VDL2GPU_K1_VARIANT, VDL2GPU_K2_VARIANT, VDL2GPU_K2A), read at create */
 	bool use_graphs = true;
+	uint32_t k2a_split = 3;                             /* resident K2a blocks per SM (VDL2GPU_K2A_SPLIT) */
 	bool k2a_exclusive = true;                          /* K1 of chunk c+1 waits for K2a of chunk c (VDL2GPU_K2A_EXCLUSIVE=0: let them overlap) */
 	uint64_t overflows_reported = 0;
 	host_tables tab;
@@ -236,6 +237,7 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 		if((e = getenv("VDL2GPU_NO_GRAPH")) && atoi(e)) c->use_graphs = false;
 		if((e = getenv("VDL2GPU_BLOCK_TRACE")) && atoi(e)) c->block_trace_cap = 1u << 16;
 		if((e = getenv("VDL2GPU_K2A_EXCLUSIVE"))) c->k2a_exclusive = atoi(e) != 0;
+		if((e = getenv("VDL2GPU_K2A_SPLIT")) && atoi(e) >= 1 && atoi(e) <= 16) c->k2a_split = (uint32_t)atoi(e);
 	}
 	if(cfg->flags & (VDL2GPU_FLAG_NO_GRAPH | VDL2GPU_FLAG_TRACE)) c->use_graphs = false;
 	c->freqs.assign(cfg->freqs, cfg->freqs + cfg->n_channels);
@@ -532,7 +534,7 @@ static void fill_params(vdl2gpu_ctx *c, chunk_slot &s, uint64_t seq, uint32_t n_
 	p1.ch_per_stream = c->ch_per_stream; p1.stream_stride = c->lane_streams ? c->n_chp : c->max_pairs; p1.ca = ca;
 	pa.dec = d_dec; pa.phase = c->d_phase2[pb]; pa.mag = c->d_mag2[pb]; pa.phase_prev = c->d_phase2[pb ^ 1];
 	pa.n_dec = n_dec; pa.prev_n_dec = prev_n_dec; pa.n_ch = c->n_ch; pa.n_chp = c->n_chp; pa.lanes = c->lanes; pa.full_warps = c->full_warps;
-	pa.mode = (uint32_t)c->k2a_mode; pa.ca = ca;
+	pa.mode = (uint32_t)c->k2a_mode; pa.split = c->k2a_split; pa.ca = ca;
 	p2.dec = d_dec; p2.phase = c->d_phase2[pb]; p2.mag = c->d_mag2[pb]; p2.hist_tmp = nullptr; p2.n_dec = n_dec; p2.n_ch = c->n_ch; p2.n_chp = c->n_chp;
 	p2.lanes = c->lanes; p2.full_warps = c->full_warps; p2.dec_base = dec_base;
 	p2.state = c->d_k2; p2.ring = c->d_ring; p2.tables = c->d_tab; p2.max_ppm = c->cfg.max_ppm; p2.s27 = c->tab.s27;

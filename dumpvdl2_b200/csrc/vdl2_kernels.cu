@@ -587,18 +587,22 @@ __global__ void __launch_bounds__(256) k2a_phase_mag(const float2 *__restrict__ 
  * into this plane's history rows (the planes alternate between chunks; with n_dec < 160 the source range still lies inside
  * the previous plane, history rows included, so short chunks need no special case). */
 template<bool FAST>
-__global__ void __launch_bounds__(128) k2a_phase_mag_warps(vdl2_k2a_params p) {
+__global__ void __launch_bounds__(128, 9) k2a_phase_mag_warps(vdl2_k2a_params p) {      /* <= 56 registers: three blocks fit beside K1 and K2 */
 	__shared__ double s_atan[VDL2_ATAN_TABLE_DOUBLES];
 	if(FAST) {
 		if(threadIdx.x < VDL2_ATAN_TABLE_DOUBLES) s_atan[threadIdx.x] = c_atan_tab[threadIdx.x];
 		__syncthreads();
 	}
-	const uint32_t slot = blockIdx.x * 128u + threadIdx.x;
+	const uint32_t nblk = (p.n_chp + 127u) / 128u, slice = blockIdx.x / nblk;
+	const uint32_t slot = (blockIdx.x % nblk) * 128u + threadIdx.x;
 	uint32_t chan;
 	if(!vdl2_slot_channel(slot, p.lanes, p.full_warps, p.n_ch, chan)) return;
-	const uint32_t n_dec = p.ca ? p.ca->n_dec : p.n_dec, prev_n_dec = p.ca ? p.ca->prev_n_dec : p.prev_n_dec;
+	const uint32_t n_all = p.ca ? p.ca->n_dec : p.n_dec, prev_n_dec = p.ca ? p.ca->prev_n_dec : p.prev_n_dec;
+	/* this block's time slice [t, n_dec) of the chunk, boundaries on multiples of 4 samples */
+	const uint32_t per = ((n_all + p.split - 1u) / p.split + 3u) & ~3u;
+	const uint32_t n_dec = min(n_all, (slice + 1u) * per);
 	const size_t s = p.n_chp;
-	{
+	if(slice == 0) {
 		const float *src = p.phase_prev + (size_t)prev_n_dec * s + slot;
 		float *dst = p.phase + slot;
 #pragma unroll 8
@@ -606,7 +610,7 @@ __global__ void __launch_bounds__(128) k2a_phase_mag_warps(vdl2_k2a_params p) {
 	}
 	const float2 *dec = p.dec + slot;
 	float *ph = p.phase + (size_t)VDL2_SYNC_BUFLEN * s + slot, *mg = p.mag + slot;
-	uint32_t t = 0;
+	uint32_t t = min(n_all, slice * per);
 	for(; t + 4 <= n_dec; t += 4) {
 		float2 d[4];
 		float a[4], m[4];
@@ -1152,7 +1156,7 @@ extern "C" int vdl2_launch_k2a(const vdl2_k2_params *p, cudaStream_t st) {
 
 extern "C" int vdl2_launch_k2a_warps(const vdl2_k2a_params *p, cudaStream_t st) {
 	if(p->n_ch == 0) return 0;
-	const uint32_t blocks = (p->n_chp + 127u) / 128u;
+	const uint32_t blocks = ((p->n_chp + 127u) / 128u) * (p->split ? p->split : 1u);
 	if(p->mode) k2a_phase_mag_warps<true><<<blocks, 128, 0, st>>>(*p);
 	else k2a_phase_mag_warps<false><<<blocks, 128, 0, st>>>(*p);
 	return (int)cudaGetLastError();

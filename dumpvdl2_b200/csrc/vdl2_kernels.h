@@ -89,6 +89,7 @@ typedef struct {
 	uint32_t n_dec, prev_n_dec;
 	uint32_t n_ch, n_chp, lanes, full_warps;
 	uint32_t mode;               /* 0 libdevice atan2 / IEEE sqrt for every sample, 1 the Ziv-guarded short forms */
+	uint32_t split;              /* time slices per chunk: the grid is `split` x (one block per 128 slots) */
 	const vdl2_chunk_args *ca;
 } vdl2_k2a_params;
 
