@@ -87,7 +87,9 @@ struct vdl2gpu_ctx {
 	uint32_t raw_bytes = 0;                             /* size of each slot's raw staging buffers (allocated on the first host submit) */
 	int k1_variant = 2, k2_variant = 5, k2a_mode = 1;   /* A/B knobs (VDL2GPU_K1_VARIANT, VDL2GPU_K2_VARIANT, VDL2GPU_K2A), read at create */
 	bool use_graphs = true;
-	uint32_t k2a_split = 3;                             /* resident K2a blocks per SM (VDL2GPU_K2A_SPLIT) */
+	uint32_t k2a_split = 64;                            /* time slices of the K2a grid (VDL2GPU_K2A_SPLIT) */
+	int stages = 2;                                     /* 2: K2a runs alone between K1 of chunk c and K1 of chunk c+1 (default, see run_chain);
+	                                                     * 3: K2a of chunk c+1 beside K1 of chunk c+2 and K2 of chunk c (VDL2GPU_STAGES=3) */
 	bool k2a_exclusive = true;                          /* K1 of chunk c+1 waits for K2a of chunk c (VDL2GPU_K2A_EXCLUSIVE=0: let them overlap) */
 	uint64_t overflows_reported = 0;
 	host_tables tab;
@@ -190,7 +192,7 @@ static int free_ctx(vdl2gpu_ctx *c) {
 	if(c->ev_t0) cudaEventDestroy(c->ev_t0);
 	for(int i = 0; i < 2; i++) if(c->ev_k2a_done[i]) cudaEventDestroy(c->ev_k2a_done[i]);
 	for(int i = 0; i < 3; i++) { if(c->ev_k1_done[i]) cudaEventDestroy(c->ev_k1_done[i]); if(c->ev_back_done[i]) cudaEventDestroy(c->ev_back_done[i]); }
-	if(c->s_mid && c->s_mid != c->stream) cudaStreamDestroy(c->s_mid);
+	if(c->s_mid && c->s_mid != c->stream && c->s_mid != c->s_back) cudaStreamDestroy(c->s_mid);
 	if(c->s_back && c->s_back != c->stream) cudaStreamDestroy(c->s_back);
 	if(c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -237,7 +239,8 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 		if((e = getenv("VDL2GPU_NO_GRAPH")) && atoi(e)) c->use_graphs = false;
 		if((e = getenv("VDL2GPU_BLOCK_TRACE")) && atoi(e)) c->block_trace_cap = 1u << 16;
 		if((e = getenv("VDL2GPU_K2A_EXCLUSIVE"))) c->k2a_exclusive = atoi(e) != 0;
-		if((e = getenv("VDL2GPU_K2A_SPLIT")) && atoi(e) >= 1 && atoi(e) <= 16) c->k2a_split = (uint32_t)atoi(e);
+		if((e = getenv("VDL2GPU_STAGES")) && atoi(e) == 3) { c->stages = 3; c->k2a_split = 3; }
+		if((e = getenv("VDL2GPU_K2A_SPLIT")) && atoi(e) >= 1 && atoi(e) <= 256) c->k2a_split = (uint32_t)atoi(e);
 	}
 	if(cfg->flags & (VDL2GPU_FLAG_NO_GRAPH | VDL2GPU_FLAG_TRACE)) c->use_graphs = false;
 	c->freqs.assign(cfg->freqs, cfg->freqs + cfg->n_channels);
@@ -285,7 +288,11 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	/* equal (default) priorities: raising either stage's priority slowed the pair down (tools/probe_overlap.py) */
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	if(cfg->flags & VDL2GPU_FLAG_NO_OVERLAP) { c->s_back = c->stream; c->s_mid = c->stream; }
-	else { CU(cudaStreamCreateWithFlags(&c->s_back, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&c->s_mid, cudaStreamNonBlocking)); }
+	else {
+		CU(cudaStreamCreateWithFlags(&c->s_back, cudaStreamNonBlocking));
+		if(c->stages == 3) CU(cudaStreamCreateWithFlags(&c->s_mid, cudaStreamNonBlocking));
+		else c->s_mid = c->s_back;
+	}
 	for(int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&c->ev_k2a_done[i], cudaEventDisableTiming));
 	for(int i = 0; i < 3; i++) {
 		CU(cudaEventCreateWithFlags(&c->ev_k1_done[i], cudaEventDisableTiming));
@@ -638,6 +645,11 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 	}
 	/* ---- front stage: K0, K1 -> dec[db] (free once K2 of chunk c-3 is done) ---- */
 	if(seq >= 3) CU(cudaStreamWaitEvent(c->stream, c->ev_back_done[db], 0));
+	/* Two-stage schedule (default): K1 of this chunk starts when K2a of the previous chunk has finished.  K2a is a short
+	 * full-occupancy pass; when it ends the GPU is empty, and K2 of chunk c-1 and K1 of chunk c are then launched into that
+	 * empty machine together, one block per SM each - the only arrangement in which the block scheduler was found to keep
+	 * the two long kernels side by side on every SM, launch after launch (see the slot mapping in create_impl). */
+	if(c->stages == 2 && seq >= 1 && overlap) CU(cudaStreamWaitEvent(c->stream, c->ev_k2a_done[pb ^ 1], 0));
 	if(s.timed) { CU(cudaEventRecord(s.tk[0], c->stream)); if(graph) CU(cudaEventRecord(s.tk[1], c->stream)); }
 	if(graph) {
 		CU(cudaGraphLaunch(s.g_front[gk], c->stream));

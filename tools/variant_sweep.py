@@ -95,8 +95,8 @@ def main():
                 ("k2_staged_1warp", dict(VDL2GPU_K2_VARIANT=261), 0), ("k2_plane_1warp", dict(VDL2GPU_K2_VARIANT=258), 0),
                 ("all_1warp", dict(VDL2GPU_K2_VARIANT=261, VDL2GPU_K1_VARIANT=8), 0),
                 ("k2a_overlap", dict(VDL2GPU_K2A_EXCLUSIVE=0), 0), ("k2a_overlap_libm", dict(VDL2GPU_K2A_EXCLUSIVE=0, VDL2GPU_K2A=0), 0),
-                ("split1", dict(VDL2GPU_K2A_SPLIT=1), 0), ("split2", dict(VDL2GPU_K2A_SPLIT=2), 0), ("split3", dict(VDL2GPU_K2A_SPLIT=3), 0),
-                ("split4", dict(VDL2GPU_K2A_SPLIT=4), 0),
+                ("split8", dict(VDL2GPU_K2A_SPLIT=8), 0), ("split16", dict(VDL2GPU_K2A_SPLIT=16), 0), ("split32", dict(VDL2GPU_K2A_SPLIT=32), 0),
+                ("split64", dict(VDL2GPU_K2A_SPLIT=64), 0), ("stages3", dict(VDL2GPU_STAGES=3), 0),
                 ("default_again", {}, 0), ("no_graph_again", {}, vd.FLAG_NO_GRAPH)]
     extra = os.environ.get("VDL2GPU_SWEEP_EXTRA")          # "name:KEY=V,KEY=V;name2:..."
     if extra:
