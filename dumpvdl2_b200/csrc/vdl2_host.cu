@@ -257,7 +257,7 @@ static int create_impl(const vdl2gpu_config *cfg, vdl2gpu_ctx *c) {
 	 * sub-partitions, they are dealt out evenly over ALL of them: every warp holds floor or ceil of n_ch / (4 x SMs)
 	 * channels instead of 32 (27 or 28 at 16384 channels on 148 SMs), each of the two kernels launches exactly one block
 	 * per SM, every block lives for the whole kernel, and every SM looks the same to the scheduler. */
-	if(cfg->n_streams <= 1) {
+	if(cfg->n_streams <= 1 || cfg->n_streams == cfg->n_channels) {
 		const uint32_t warps_all = 4u * (uint32_t)c->n_sms;
 		if(c->n_ch > 16u * warps_all && c->n_ch <= 32u * warps_all) {
 			const char *e = getenv("VDL2GPU_BALANCE");
@@ -584,7 +584,7 @@ static int body_front(void *a) {
 	CU(cudaMemcpyAsync(e->s->d_args, e->s->h_args, sizeof(vdl2_chunk_args), cudaMemcpyHostToDevice, c->stream));
 	const uint32_t bpp = c->cfg.sample_fmt == VDL2GPU_FMT_S16_LE ? 4u : 2u;
 	if(c->lane_streams) KL(vdl2_launch_k0_lanes(nullptr, e->n_pairs, e->k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->n_streams,
-			e->n_pairs * bpp, c->n_chp, e->s->d_args, c->stream));
+			e->n_pairs * bpp, c->n_chp, c->lanes, c->full_warps, e->s->d_args, c->stream));
 	else KL(vdl2_launch_k0(nullptr, e->n_pairs, e->k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->n_streams,
 			e->n_pairs * bpp, c->max_pairs, e->s->d_args, c->stream));
 	KL(vdl2_launch_k1(&p1, (c->cfg.flags & VDL2GPU_FLAG_K1_SCALAR) ? 1 : 0, c->k1_variant, c->stream));
@@ -655,7 +655,7 @@ static int run_chain(vdl2gpu_ctx *c, chunk_slot &s, const void *d_raw, uint32_t 
 		CU(cudaGraphLaunch(s.g_front[gk], c->stream));
 	} else {
 		if(c->lane_streams) KL(vdl2_launch_k0_lanes(d_raw, n_pairs, k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->n_streams,
-				n_pairs * bpp, c->n_chp, nullptr, c->stream));
+				n_pairs * bpp, c->n_chp, c->lanes, c->full_warps, nullptr, c->stream));
 		else KL(vdl2_launch_k0(d_raw, n_pairs, k0_fmt, c->d_tab->levels, reinterpret_cast<float *>(c->d_samples), c->n_streams,
 				n_pairs * bpp, c->max_pairs, nullptr, c->stream));
 		if(s.timed) CU(cudaEventRecord(s.tk[1], c->stream));

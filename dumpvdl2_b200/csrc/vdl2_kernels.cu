@@ -34,6 +34,15 @@ __device__ __forceinline__ int vdl2_trace_begin(vdl2_block_trace *t, uint32_t ke
 }
 __device__ __forceinline__ void vdl2_trace_end(vdl2_block_trace *t, int k) { if(k >= 0) t->rec[k].t_end = vdl2_globaltimer(); }
 
+/* slot (index into every per-channel array) -> public channel number and activity: a warp holds `lanes` channels in its
+ * first `lanes` lanes */
+__device__ __forceinline__ bool vdl2_slot_channel(uint32_t slot, uint32_t lanes, uint32_t full_warps, uint32_t n_ch, uint32_t &chan) {
+	const uint32_t lane = slot & 31u, w = slot >> 5;
+	const uint32_t mine = w < full_warps ? lanes : lanes - 1u;                 /* channels of this warp */
+	chan = (w < full_warps ? w * lanes : full_warps * lanes + (w - full_warps) * (lanes - 1u)) + lane;
+	return lane < mine && chan < n_ch;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * K0: sample conversion.  Output: float2 {re, im} per complex sample (src/demod.c:339-365).
  * ---------------------------------------------------------------------------------------------- */
@@ -70,14 +79,16 @@ __global__ void __launch_bounds__(256) k0_convert(const uint8_t *__restrict__ ra
  * shared memory: reads run along the samples of a stream, writes along the streams of a sample. */
 __global__ void __launch_bounds__(1024) k0_convert_lanes(const uint8_t *__restrict__ raw0, uint32_t n_pairs_p, uint32_t fmt,
 		const float *__restrict__ levels, float2 *__restrict__ out, uint32_t n_streams, uint32_t raw_stride, uint32_t out_stride,
-		const vdl2_chunk_args *__restrict__ ca) {
+		uint32_t lanes, uint32_t full_warps, const vdl2_chunk_args *__restrict__ ca) {
 	__shared__ float2 tile[32][33];
 	const uint32_t n_pairs = ca ? ca->n_pairs : n_pairs_p;
 	const uint8_t *raw = ca ? static_cast<const uint8_t *>(ca->raw) : raw0;
 	const uint32_t tx = threadIdx.x, ty = threadIdx.y;
-	const uint32_t s_in = blockIdx.y * 32u + ty, i_in = blockIdx.x * 32u + tx;
+	const uint32_t i_in = blockIdx.x * 32u + tx;
+	uint32_t s_in;                                    /* stream = channel that lives in column (slot) blockIdx.y * 32 + ty */
+	const bool have = vdl2_slot_channel(blockIdx.y * 32u + ty, lanes, full_warps, n_streams, s_in);
 	float re = 0.f, im = 0.f;
-	if(s_in < n_streams && i_in < n_pairs) {
+	if(have && i_in < n_pairs) {
 		const uint8_t *r = raw + (size_t)s_in * raw_stride;
 		if(fmt == 0) {
 			uchar2 v = reinterpret_cast<const uchar2 *>(r)[i_in];
@@ -119,15 +130,6 @@ __device__ __forceinline__ void k1_store_state(const vdl2_k1_params &p, uint32_t
 	st[K1_YR1 * s + ch] = __float_as_uint(yr1); st[K1_YR2 * s + ch] = __float_as_uint(yr2);
 	st[K1_YI1 * s + ch] = __float_as_uint(yi1); st[K1_YI2 * s + ch] = __float_as_uint(yi2);
 	st[K1_PHI * s + ch] = phi & 0xFFFFFFu;
-}
-
-/* slot (index into every per-channel array) -> public channel number and activity: a warp holds `lanes` channels in its
- * first `lanes` lanes */
-__device__ __forceinline__ bool vdl2_slot_channel(uint32_t slot, uint32_t lanes, uint32_t full_warps, uint32_t n_ch, uint32_t &chan) {
-	const uint32_t lane = slot & 31u, w = slot >> 5;
-	const uint32_t mine = w < full_warps ? lanes : lanes - 1u;                 /* channels of this warp */
-	chan = (w < full_warps ? w * lanes : full_warps * lanes + (w - full_warps) * (lanes - 1u)) + lane;
-	return lane < mine && chan < n_ch;
 }
 
 /* independent-streams mode: all channels of a block belong to stream (first channel / ch_per_stream); a block never
@@ -408,11 +410,11 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
  * buffer: src/demod.c:302-310).  samples = float2[n_pairs][stride] time-major across streams (k0_convert_lanes), so a
  * block of 128 channels reads 1 KB of contiguous bytes per sample: the algorithmic 8 B per channel-sample are real HBM
  * traffic here.  Rows are fetched by TMA bulk copies (one 1 KB cp.async.bulk per sample row) into a double-buffered
- * shared-memory tile of 40 rows per buffer; with one block per SM ~80 KB per SM (12 MB over the GPU) are in flight,
+ * shared-memory tile of 80 rows per buffer; with one block per SM ~160 KB per SM (24 MB over the GPU) are in flight,
  * above the bandwidth-delay product of HBM.  Arithmetic and NCO table layout as in the packed kernel.
  * ---------------------------------------------------------------------------------------------- */
 #define K1L_BLOCK 128
-#define K1L_TILE_ROWS 40
+#define K1L_TILE_ROWS 80
 #define K1L_SMEM_BYTES (257 * 8 * 16 + 2 * K1L_TILE_ROWS * K1L_BLOCK * 8 + 16)
 
 template<int OS, bool SYM>
@@ -463,18 +465,23 @@ __global__ void __launch_bounds__(K1L_BLOCK) k1_mix_iir_decimate_lanes(vdl2_k1_p
 	const uint32_t n_tiles = (n_groups + TG - 1) / TG;
 	/* bytes of one row that exist in the sample plane for this block (a full 1 KB except in a ragged last block) */
 	const uint32_t row_bytes = (uint32_t)min((size_t)K1L_BLOCK, stride - (size_t)blockIdx.x * K1L_BLOCK) * 8u;
-	/* thread 0 arms the barrier with the tile's byte count, then threads 0..rows-1 request one row each */
-	auto request_tile = [&](uint32_t t, uint32_t buf) {
+	/* thread 0 arms the barrier with the tile's byte count (`arm`, before a block barrier), then threads 0..rows-1 request
+	 * one row each (`request`, after it) */
+	auto arm = [&](uint32_t t, uint32_t buf) {
 		const uint32_t rows = min((uint32_t)TG, n_groups - t * TG) * OS;
 		if(tid == 0)
 			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&s_bar[buf])), "r"(rows * row_bytes) : "memory");
-		__syncthreads();
+	};
+	auto request = [&](uint32_t t, uint32_t buf) {
+		const uint32_t rows = min((uint32_t)TG, n_groups - t * TG) * OS;
 		const float2 *src = samples + (size_t)(head + (size_t)t * TG * OS) * stride;
 		for(uint32_t r = tid; r < rows; r += K1L_BLOCK)
 			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 					:: "r"(smem_u32(&s_tiles[((size_t)buf * TG * OS + r) * K1L_BLOCK])), "l"(src + (size_t)r * stride), "r"(row_bytes), "r"(smem_u32(&s_bar[buf])) : "memory");
 	};
-	for(uint32_t t = 0; t < 2 && t < n_tiles; t++) request_tile(t, t);
+	for(uint32_t t = 0; t < 2 && t < n_tiles; t++) arm(t, t);
+	__syncthreads();
+	for(uint32_t t = 0; t < 2 && t < n_tiles; t++) request(t, t);
 	for(uint32_t g0 = 0, tile = 0; g0 < n_groups; g0 += TG, tile++) {
 		const uint32_t ng = min((uint32_t)TG, n_groups - g0);
 		const float2 *s_tile = s_tiles + (size_t)(tile & 1u) * TG * OS * K1L_BLOCK + tid;
@@ -522,8 +529,9 @@ __global__ void __launch_bounds__(K1L_BLOCK) k1_mix_iir_decimate_lanes(vdl2_k1_p
 		}
 		m += ng;
 		pos += ng * OS;
-		__syncthreads();                                           /* every warp is done with this buffer */
-		if(tile + 2 < n_tiles) request_tile(tile + 2, tile & 1u);
+		if(tile + 2 < n_tiles) arm(tile + 2, tile & 1u);           /* arming does not touch the tile's data */
+		__syncthreads();                                           /* every warp is done with this buffer, the barrier is armed */
+		if(tile + 2 < n_tiles) request(tile + 2, tile & 1u);
 	}
 	if(active) {
 		for(; pos < n_pairs; pos++) {
@@ -1099,10 +1107,10 @@ extern "C" int vdl2_launch_k0(const void *raw, uint32_t n_pairs, uint32_t fmt, c
 }
 
 extern "C" int vdl2_launch_k0_lanes(const void *raw, uint32_t n_pairs, uint32_t fmt, const float *levels, float *out2, uint32_t n_streams,
-		uint32_t raw_stride, uint32_t out_stride, const vdl2_chunk_args *ca, cudaStream_t st) {
+		uint32_t raw_stride, uint32_t out_stride, uint32_t lanes, uint32_t full_warps, const vdl2_chunk_args *ca, cudaStream_t st) {
 	if(n_pairs == 0 || n_streams == 0) return 0;
 	k0_convert_lanes<<<dim3((n_pairs + 31) / 32, (out_stride + 31) / 32), dim3(32, 32), 0, st>>>(static_cast<const uint8_t *>(raw), n_pairs, fmt,
-			levels, reinterpret_cast<float2 *>(out2), n_streams, raw_stride, out_stride, ca);
+			levels, reinterpret_cast<float2 *>(out2), n_streams, raw_stride, out_stride, lanes, full_warps, ca);
 	return (int)cudaGetLastError();
 }
 

@@ -301,3 +301,46 @@ def test_one_stream_per_channel_mode(n_streams):
     st = g.stats()
     assert st["pool_overflows"] == 0 and st["out_overflows"] == 0
     g.close()
+
+
+def test_one_stream_per_channel_with_the_balanced_slot_mapping():
+    """9600 streams x 1 channel: more than half a machine's worth, so the channels are dealt out over all 592 warps (17 or
+    16 per warp) and K0 has to place stream c in column slot(c).  The streams are built on the device (stream s = the base
+    stream started 7919 s samples later) and fed through submit_device; a sample of channels is checked against the oracle."""
+    import torch
+    from dumpvdl2_b200 import synth
+    fs, center, pairs = 2100000, cases.CENTER, 65536
+    S, n_chunks = 9600, 3
+    base, offs, _ = synth.traffic_stream(fs, 0.3, 8, 12.0, 24.0, -20.0, 0x56444C51, "u8")
+    L = base.size // 2
+    b2 = torch.from_numpy(base[:2 * L].reshape(L, 2)).cuda()
+    ar = torch.arange(n_chunks * pairs, device="cuda", dtype=torch.int64)
+    raw = torch.empty(n_chunks, S, pairs, 2, dtype=torch.uint8, device="cuda")
+    for s0 in range(0, S, 128):
+        sh = (torch.arange(s0, min(s0 + 128, S), device="cuda", dtype=torch.int64) * 7919) % L
+        idx = (ar[None, :] + sh[:, None]) % L                      # [streams][time]
+        blk = b2[idx]                                              # [streams][time][2]
+        for c in range(n_chunks):
+            raw[c, s0:s0 + idx.shape[0]] = blk[:, c * pairs:(c + 1) * pairs]
+    freqs = [center + int(offs[s % len(offs)]) for s in range(S)]
+    g = vd.Vdl2Channels(fs, 20, vd.FMT_U8, center, freqs, max_chunk_bytes=2 * pairs, n_streams=S)
+    st = torch.cuda.current_stream()
+    for c in range(n_chunks):
+        g.submit_device(raw[c].data_ptr(), 2 * pairs, st.cuda_stream)
+    got = {}
+    for f in g.flush():
+        got.setdefault(f.channel, []).append(f)
+    cnt = g.channel_counters()
+    g.close()
+    checked = 0
+    for s in (0, 1, 16, 17, 31, 32, 4799, 4800, 9215, 9216, 9599):
+        iq = np.roll(base[:2 * L], -2 * ((7919 * s) % L))[:2 * n_chunks * pairs]
+        o = po.Oracle(fs, 20, po.FMT_U8, center, [freqs[s]])
+        o.process_chunked(iq, 2 * pairs)
+        mine = got.get(s, [])
+        for f in mine:
+            f.channel = 0
+        util.assert_frames_equal(mine, o.frames(), f"stream {s}")
+        assert np.array_equal(cnt[s:s + 1], o.counters())
+        checked += len(mine)
+    assert checked > 5
