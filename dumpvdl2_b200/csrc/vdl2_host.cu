@@ -539,7 +539,9 @@ static void fill_params(vdl2gpu_ctx *c, chunk_slot &s, uint64_t seq, uint32_t n_
 	p1.one = 1.0f; p1.neg_one = -1.0f; p1.two = 2.0f;
 	p1.trace_blocks = c->d_block_trace; p2.trace_blocks = c->d_block_trace;
 	p1.ch_per_stream = c->ch_per_stream; p1.stream_stride = c->lane_streams ? c->n_chp : c->max_pairs; p1.ca = ca;
-	pa.dec = d_dec; pa.phase = c->d_phase2[pb]; pa.mag = c->d_mag2[pb]; pa.phase_prev = c->d_phase2[pb ^ 1];
+	/* the default walk (variant 5) computes the four magnitudes a block needs from the staged samples: no magnitude plane */
+	const bool need_mag = (c->k2_variant & 0xFF) >= 0 && (c->k2_variant & 0xFF) <= 4;
+	pa.dec = d_dec; pa.phase = c->d_phase2[pb]; pa.mag = need_mag ? c->d_mag2[pb] : nullptr; pa.phase_prev = c->d_phase2[pb ^ 1];
 	pa.n_dec = n_dec; pa.prev_n_dec = prev_n_dec; pa.n_ch = c->n_ch; pa.n_chp = c->n_chp; pa.lanes = c->lanes; pa.full_warps = c->full_warps;
 	pa.mode = (uint32_t)c->k2a_mode; pa.split = c->k2a_split; pa.ca = ca;
 	p2.dec = d_dec; p2.phase = c->d_phase2[pb]; p2.mag = c->d_mag2[pb]; p2.hist_tmp = nullptr; p2.n_dec = n_dec; p2.n_ch = c->n_ch; p2.n_chp = c->n_chp;

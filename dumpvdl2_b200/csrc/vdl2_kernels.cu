@@ -627,21 +627,24 @@ __global__ void __launch_bounds__(128, 9) k2a_phase_mag_warps(vdl2_k2a_params p)
 		for(int k = 0; k < 4; k++) d[k] = dec[(size_t)(t + k) * s];
 #pragma unroll
 		for(int k = 0; k < 4; k++) {
-			if(FAST) { a[k] = vdl2_phase_fast(d[k].x, d[k].y, s_atan, &sp[k]); m[k] = vdl2_mag_fast(d[k].x, d[k].y, &sm[k]); }
-			else { sp[k] = 1; sm[k] = 1; a[k] = 0.f; m[k] = 0.f; }
+			sm[k] = 1; m[k] = 0.f;
+			if(FAST) { a[k] = vdl2_phase_fast(d[k].x, d[k].y, s_atan, &sp[k]); if(p.mag != nullptr) m[k] = vdl2_mag_fast(d[k].x, d[k].y, &sm[k]); }
+			else { sp[k] = 1; a[k] = 0.f; }
 		}
 #pragma unroll
 		for(int k = 0; k < 4; k++) {
 			if(sp[k]) a[k] = vdl2_phase_of(d[k].x, d[k].y);
-			if(sm[k]) m[k] = vdl2_mag_of(d[k].x, d[k].y);
 			ph[(size_t)(t + k) * s] = a[k];
-			mg[(size_t)(t + k) * s] = m[k];
+			if(p.mag != nullptr) {
+				if(sm[k]) m[k] = vdl2_mag_of(d[k].x, d[k].y);
+				mg[(size_t)(t + k) * s] = m[k];
+			}
 		}
 	}
 	for(; t < n_dec; t++) {
 		const float2 d = dec[(size_t)t * s];
 		ph[(size_t)t * s] = vdl2_phase_of(d.x, d.y);
-		mg[(size_t)t * s] = vdl2_mag_of(d.x, d.y);
+		if(p.mag != nullptr) mg[(size_t)t * s] = vdl2_mag_of(d.x, d.y);
 	}
 }
 
@@ -675,8 +678,8 @@ __device__ __forceinline__ void k2_cp_async_wait_all() { asm volatile("cp.async.
  * block inputs loaded one block ahead into registers; 3 phase ring, block inputs staged one block ahead in shared
  * memory by cp.async (VDL2GPU_K2_VARIANT=4); 4 phase ring, ALL block inputs (phase, magnitude, decimated samples)
  * staged one block ahead by cp.async (VDL2GPU_K2_VARIANT=5) */
-/* staging floats per thread: mode 4 two buffers of (12 phase + 12 magnitude + 12 float2 samples), mode 3 two buffers of 16 */
-#define K2_STAGE_FLOATS(MODE) ((MODE) == 4 ? 2 * (2 * VDL2_WALK_BLOCK + 2 * VDL2_WALK_BLOCK) : (MODE) == 3 ? 2 * 16 : 0)
+/* staging floats per thread: mode 4 two buffers of (12 phase + 12 float2 samples), mode 3 two buffers of 16 */
+#define K2_STAGE_FLOATS(MODE) ((MODE) == 4 ? 2 * (VDL2_WALK_BLOCK + 2 * VDL2_WALK_BLOCK) : (MODE) == 3 ? 2 * 16 : 0)
 #define K2_SMEM_BYTES(BLOCK, MODE) ((VDL2_SYNC_BUFLEN + K2_STAGE_FLOATS(MODE)) * (BLOCK) * 4 + 36 * 4 + VDL2_UNWRAP_STATES * 6 * 4)
 
 template<int BLOCK, bool BLOCKED, int MODE>
@@ -737,17 +740,16 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	uint32_t m = 0;
 	if(BLOCKED) {
 		if(MODE == 4) {
-			/* Everything a block of 12 samples can need - its 12 phases, 12 magnitudes and 12 decimated samples - is staged one
-			 * block ahead in shared memory by cp.async (36 LDGSTS per lane and block): neither the searching path nor the
+			/* Everything a block of 12 samples can need - its 12 phases and 12 decimated samples (the magnitudes are computed
+			 * from those) - is staged one block ahead in shared memory by cp.async (24 LDGSTS per lane and block): neither the searching path nor the
 			 * symbol slicing of a channel that is inside a burst ever waits for global memory, whatever mix of states the 32
 			 * channels of the warp are in. */
-			float (*s_st)[2 * VDL2_WALK_BLOCK][BLOCK] = reinterpret_cast<float (*)[2 * VDL2_WALK_BLOCK][BLOCK]>(s_stage_area);   /* [2]: rows 0..11 phase, 12..23 magnitude */
-			float2 (*s_sd)[VDL2_WALK_BLOCK][BLOCK] = reinterpret_cast<float2 (*)[VDL2_WALK_BLOCK][BLOCK]>(s_stage_area + 2 * 2 * VDL2_WALK_BLOCK * BLOCK);
+			float (*s_st)[VDL2_WALK_BLOCK][BLOCK] = reinterpret_cast<float (*)[VDL2_WALK_BLOCK][BLOCK]>(s_stage_area);   /* [2][12]: phases */
+			float2 (*s_sd)[VDL2_WALK_BLOCK][BLOCK] = reinterpret_cast<float2 (*)[VDL2_WALK_BLOCK][BLOCK]>(s_stage_area + 2 * VDL2_WALK_BLOCK * BLOCK);
 			auto stage = [&](uint32_t buf, size_t o) {
 #pragma unroll
 				for(int t = 0; t < VDL2_WALK_BLOCK; t++) {
 					k2_cp_async4(&s_st[buf][t][tid], phs + o + (size_t)t * s);
-					k2_cp_async4(&s_st[buf][VDL2_WALK_BLOCK + t][tid], mgs + o + (size_t)t * s);
 					k2_cp_async8(&s_sd[buf][t][tid], dec + o + (size_t)t * s);
 				}
 				k2_cp_async_commit();
@@ -762,11 +764,18 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 				const int first = vdl2_walk_first(v);
 #pragma unroll
 				for(int t = 0; t < VDL2_WALK_BLOCK; t++) pf.pw[t] = s_st[b][t][tid];
+				/* the four magnitudes the block's sync attempts use (src/demod.c:238) straight from the staged samples: the
+				 * Ziv-guarded square root, IEEE square root when it asks for it; no magnitude plane is read in this mode */
 #pragma unroll
-				for(int j = 0; j < 4; j++) pf.mg[j] = s_st[b][VDL2_WALK_BLOCK + first + VDL2_SYNC_SKIP * j][tid];
+				for(int j = 0; j < 4; j++) {
+					const float2 dj = s_sd[b][first + VDL2_SYNC_SKIP * j][tid];
+					int slow;
+					pf.mg[j] = vdl2_mag_fast(dj.x, dj.y, &slow);
+					if(slow) pf.mg[j] = vdl2_mag_of(dj.x, dj.y);
+				}
 				pf.first = first; pf.valid = 1;
 				vdl2_walk_block_ring<true>(v, ring, BLOCK, env, chan, dec_base + m, &s_sd[b][0][tid], &s_st[b][0][tid],
-						&s_st[b][VDL2_WALK_BLOCK][tid], BLOCK, pf, false);
+						nullptr, BLOCK, pf, false);
 			}
 			k2_cp_async_wait_all();
 		} else if(MODE == 3) {
@@ -834,7 +843,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 	for(; m < n_dec; m++) {
 		const size_t o = (size_t)m * s;
 		const float2 d = __ldg(&dec[o]);
-		vdl2_demod_step_pm(v, ring, BLOCK, env, chan, dec_base + m, d.x, d.y, __ldg(&phs[o]), __ldg(&mgs[o]), false, 0.f, 0.f);
+		vdl2_demod_step_pm(v, ring, BLOCK, env, chan, dec_base + m, d.x, d.y, __ldg(&phs[o]), MODE == 4 ? vdl2_mag_of(d.x, d.y) : __ldg(&mgs[o]), false, 0.f, 0.f);
 	}
 
 #pragma unroll 4

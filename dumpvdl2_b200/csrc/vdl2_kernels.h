@@ -84,7 +84,7 @@ typedef struct {
 typedef struct {
 	const float2 *dec;           /* [n_dec][n_chp] */
 	float *phase;                /* this chunk's plane [160 + n_dec][n_chp] */
-	float *mag;                  /* [n_dec][n_chp] */
+	float *mag;                  /* [n_dec][n_chp], or NULL: the walk (variant 5) takes the magnitudes from the samples itself */
 	const float *phase_prev;     /* the previous chunk's plane (the other of the two) */
 	uint32_t n_dec, prev_n_dec;
 	uint32_t n_ch, n_chp, lanes, full_warps;

