@@ -620,8 +620,19 @@ VDL2_HD void vdl2_walk_tail(vdl2_chan &v, float *ring, int rs, const vdl2_k2_env
 		} else {
 			const float2 d = VDL2_LD(STAGED, dec + (ptrdiff_t)t * (ptrdiff_t)stride);
 			const float phi = VDL2_LD(STAGED, phase + (ptrdiff_t)t * (ptrdiff_t)stride);
-			const float mgt = VDL2_LD(STAGED, mag + (ptrdiff_t)t * (ptrdiff_t)stride);
-			vdl2_demod_step_pm(v, ring, rs, env, chan_idx, idx0 + (uint64_t)t, d.x, d.y, phi, mgt, false, 0.f, 0.f);
+			if(mag) {
+				const float mgt = VDL2_LD(STAGED, mag + (ptrdiff_t)t * (ptrdiff_t)stride);
+				vdl2_demod_step_pm(v, ring, rs, env, chan_idx, idx0 + (uint64_t)t, d.x, d.y, phi, mgt, false, 0.f, 0.f);
+			} else {
+				/* no magnitude plane: vdl2_demod_step_pm with the magnitude taken from the sample, and only on the
+				 * samples that consume it (every SYNC_SKIP-th while searching) */
+				if(vdl2_dec_state(v) == VDL2_DEC_IDLE) vdl2_demod_reset(v);
+				vdl2_init_write(v, ring, rs, phi);
+				if(++v.sclk >= VDL2_SYNC_SKIP) {
+					v.sclk = 0;
+					vdl2_init_eval(v, ring, rs, env, chan_idx, idx0 + (uint64_t)t, vdl2_mag_of(d.x, d.y), false, 0.f, 0.f);
+				}
+			}
 			t++;
 		}
 	}
@@ -644,7 +655,11 @@ VDL2_HD void vdl2_walk_block_ring(vdl2_chan &v, float *ring, int rs, const vdl2_
 	}
 	if(!have_mg && fast) {
 #pragma unroll
-		for(int j = 0; j < 4; j++) mg[j] = VDL2_LD(STAGED, mag + (ptrdiff_t)(first + VDL2_SYNC_SKIP * j) * (ptrdiff_t)stride);
+		for(int j = 0; j < 4; j++) {
+			const ptrdiff_t o = (ptrdiff_t)(first + VDL2_SYNC_SKIP * j) * (ptrdiff_t)stride;
+			if(mag) mg[j] = VDL2_LD(STAGED, mag + o);
+			else { const float2 d = VDL2_LD(STAGED, dec + o); mg[j] = vdl2_mag_of(d.x, d.y); }
+		}
 	}
 	/* request the next block's inputs now; they arrive while this block is evaluated */
 	if(has_next) {

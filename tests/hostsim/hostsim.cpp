@@ -157,6 +157,21 @@ int hostsim_k2k3(const float *dec /*[n_dec][n_ch][2]*/, uint32_t n_dec, uint32_t
 					vdl2_walk_block_ring(chans[ch], &rings[(size_t)ch * VDL2_SYNC_BUFLEN], 1, env, ch, base + m,
 							reinterpret_cast<const float2 *>(dec2 + o), &phase[o + (size_t)VDL2_SYNC_BUFLEN * n_ch], &mag[o], n_ch, pf, false);
 				}
+			} else if(use_pre == 5) {         /* the kernel's default walk (MODE 4): no magnitude plane, the four attempt magnitudes from the samples */
+				const float *phs = &phase[((size_t)base + VDL2_SYNC_BUFLEN) * n_ch + ch];
+				for(; m + VDL2_WALK_BLOCK <= n; m += VDL2_WALK_BLOCK) {
+					const size_t o = (size_t)(base + m) * n_ch + ch;
+					vdl2_walk_pref pf;
+					const int first = vdl2_walk_first(chans[ch]);
+					for(int t = 0; t < VDL2_WALK_BLOCK; t++) pf.pw[t] = phs[(size_t)(m + t) * n_ch];
+					for(int j = 0; j < 4; j++) {
+						const float *d = &dec[(o + (size_t)(first + VDL2_SYNC_SKIP * j) * n_ch) * 2];
+						pf.mg[j] = vdl2_mag_of(d[0], d[1]);
+					}
+					pf.first = first; pf.valid = 1;
+					vdl2_walk_block_ring(chans[ch], &rings[(size_t)ch * VDL2_SYNC_BUFLEN], 1, env, ch, base + m,
+							reinterpret_cast<const float2 *>(dec2 + o), &phase[o + (size_t)VDL2_SYNC_BUFLEN * n_ch], nullptr, n_ch, pf, false);
+				}
 			} else if(use_pre == 3) {         /* the kernel's ring walk, inputs requested one block ahead */
 				vdl2_walk_pref pf;
 				memset(&pf, 0, sizeof(pf));

@@ -16,7 +16,7 @@ def _samples(case):
     return po.levels_u8()[b]
 
 
-@pytest.mark.parametrize("use_pre", [4, 3, 2, 1, 0], ids=["ring_staged", "ring", "blocked_lut", "blocked", "per_sample"])
+@pytest.mark.parametrize("use_pre", [5, 4, 3, 2, 1, 0], ids=["ring_nomag", "ring_staged", "ring", "blocked_lut", "blocked", "per_sample"])
 @pytest.mark.parametrize("name", ["cfg2", "mixed_s16", "fec", "noisy", "wav", "hdlc_edge", "mirics_os13", "maxlen", "stress"])
 def test_device_functions_on_host_match_oracle(name, use_pre):
     c = (cases.ALL_GOLDEN.get(name) or getattr(cases, "case_" + name))()
@@ -51,7 +51,7 @@ def test_max_ppm_veto_in_blocked_walk():
     must fall back to the per-sample path there."""
     c = dict(cases.case_mixed_s16()); c["max_ppm"] = 1.0
     o = util.run_oracle(c, trace=True, dec_tap=True)
-    for mode in (1, 2, 3, 4):
+    for mode in (1, 2, 3, 4, 5):
         _check_veto(c, o, mode)
 
 
