@@ -13,7 +13,8 @@
  *
  * Error budget (relative to the final result r; the guard used is 2^-44, 16x the bound):
  *   t = num/den      num, den exact in double (|c| <= 1 has 4 significant bits, the floats 24);
- *                    two Newton steps on a >= 2^-18 reciprocal seed: |dt/t| <= 2^-51
+ *                    one Newton step on a >= 2^-18 reciprocal seed leaves |1 - den r| <= 2^-36, and the correction
+ *                    t += r (num - den t) squares that: |dt/t| <= 2^-51 (rounding of the last fma dominates)
  *   atan(t)          |t| <= 1/16 (+2^-20 slack from the approximate selection of k); the series is cut after
  *                    t^11/11: truncation <= t^12/13 <= 2^-51.7 relative to t; evaluation error <= 2^-51
  *   A_k + atan(t)    table entry rounded to nearest: 2^-54 absolute (values < 1), sum 2^-53 relative
@@ -112,8 +113,7 @@ VDL2_FM_HD float vdl2_phase_fast(float re, float im, const double *tab, int *slo
 #else
 	double r = vdl2_fm_rcp_seed(den);
 #endif
-	r = vdl2_fm_fma(r, vdl2_fm_fma(-den, r, 1.0), r);
-	r = vdl2_fm_fma(r, vdl2_fm_fma(-den, r, 1.0), r);
+	r = vdl2_fm_fma(r, vdl2_fm_fma(-den, r, 1.0), r);      /* one Newton step: |1 - den r| <= 2^-36 */
 	double t = num * r;
 	t = vdl2_fm_fma(vdl2_fm_fma(-den, t, num), r, t);       /* one correction: t within an ulp of num/den */
 	const double s = t * t;
@@ -144,9 +144,167 @@ VDL2_FM_HD float vdl2_phase_fast(float re, float im, const double *tab, int *slo
 #endif
 }
 
+/* The same evaluation as straight-line code (no early exit): the range test only feeds the *slow flag, so the whole
+ * routine can be scheduled into the middle of another instruction stream (K1 interleaves it with the filter
+ * recurrence of the next decimation group).  Out-of-range inputs run through the arithmetic harmlessly (the result
+ * is discarded by the caller when *slow is set; the table index is clamped).  An exact zero sample, which the
+ * early-exit version hands to the slow path, is answered here: atan2(+-0, +0) = +-0, atan2(+-0, -0) = +-pi. */
+VDL2_FM_HD float vdl2_phase_fast_nb(float re, float im, const double *tab, int *slow) {
+	const float ax = fabsf(re), ay = fabsf(im);
+	const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+	const bool in_range = ax <= 1.0e30f && ay <= 1.0e30f && mx >= 1.0e-30f && (mn >= mx * 1.0e-6f || mn == 0.0f);
+	const bool zero = ax == 0.0f && ay == 0.0f;
+#if defined(__CUDA_ARCH__)
+	const float q = __fdividef(mn, mx);
+	uint32_t k = __float_as_uint(__fmaf_rn(q, 8.0f, 12582912.0f)) & 15u;
+#else
+	const float q = mn / mx;
+	float kf = q * 8.0f + 12582912.0f;
+	uint32_t kb; memcpy(&kb, &kf, 4);
+	uint32_t k = kb & 15u;
+#endif
+	k = k > 8u ? 8u : k;
+	const double A = tab[2 * k], c = tab[2 * k + 1];
+	const double dmx = (double)mx, dmn = (double)mn;
+	const double num = vdl2_fm_fma(-c, dmx, dmn);
+	const double den = vdl2_fm_fma(c, dmn, dmx);
+#ifdef VDL2_FM_RCP_SEED_OVERRIDE
+	double r = VDL2_FM_RCP_SEED_OVERRIDE(den);
+#else
+	double r = vdl2_fm_rcp_seed(den);
+#endif
+	r = vdl2_fm_fma(r, vdl2_fm_fma(-den, r, 1.0), r);
+	double t = num * r;
+	t = vdl2_fm_fma(vdl2_fm_fma(-den, t, num), r, t);
+	const double s = t * t;
+	double p = VDL2_FM_K(0, VDL2_FM_C0);
+	p = vdl2_fm_fma(p, s, VDL2_FM_K(1, VDL2_FM_C1));
+	p = vdl2_fm_fma(p, s, VDL2_FM_K(2, VDL2_FM_C2));
+	p = vdl2_fm_fma(p, s, VDL2_FM_K(3, VDL2_FM_C3));
+	p = vdl2_fm_fma(p, s, VDL2_FM_K(4, VDL2_FM_C4));
+	double a = A + vdl2_fm_fma(t * s, p, t);
+	const double a1 = (VDL2_FM_K(5, VDL2_PIO2_HI) - a) + VDL2_FM_K(6, VDL2_PIO2_LO);
+	a = ay > ax ? a1 : a;
+	const double a2 = (VDL2_FM_K(7, VDL2_PI_HI) - a) + VDL2_FM_K(8, VDL2_PI_LO);
+	a = re < 0.0f ? a2 : a;
+	uint64_t bits;
+#if defined(__CUDA_ARCH__)
+	bits = (uint64_t)__double_as_longlong(a);
+#else
+	memcpy(&bits, &a, 8);
+#endif
+	const uint32_t drop = (uint32_t)bits & 0x1FFFFFFFu;
+	const uint32_t dist = drop > 0x10000000u ? drop - 0x10000000u : 0x10000000u - drop;
+	*slow = (!zero && (!in_range || (dist < 512u && a != 0.0))) ? 1 : 0;
+	float f = (float)a;
+	uint32_t re_bits, im_bits, f_bits;
+#if defined(__CUDA_ARCH__)
+	re_bits = __float_as_uint(re); im_bits = __float_as_uint(im); f_bits = __float_as_uint(f);
+#else
+	memcpy(&re_bits, &re, 4); memcpy(&im_bits, &im, 4); memcpy(&f_bits, &f, 4);
+#endif
+	if(zero) f_bits = (re_bits & 0x80000000u) ? 0x40490FDBu /* fl32(pi) */ : 0u;
+	f_bits = (f_bits & 0x7FFFFFFFu) | (im_bits & 0x80000000u);
+#if defined(__CUDA_ARCH__)
+	return __uint_as_float(f_bits);
+#else
+	memcpy(&f, &f_bits, 4);
+	return f;
+#endif
+}
+
+/* vdl2_phase_fast_nb cut into 14 short stages plus a finish, the same operations in the same order.  K1 issues one
+ * stage every other input sample of a decimation group, so consecutive links of the dependent FP64 chain are ~75 cycles
+ * apart in its instruction stream and never stall its single warp per SM sub-partition. */
+struct vdl2_phase_pipe {
+	float re, im, ax, ay, mx, mn;
+	double A, c, dmx, dmn, num, den, r, e, t, s, p, ts, a;
+	float f;
+	int slow;
+};
+#define VDL2_PHASE_PIPE_STAGES 17
+VDL2_FM_HD void vdl2_phase_pipe_stage(vdl2_phase_pipe &q, int st, const double *tab) {
+	switch(st) {
+	case 0: {
+		q.ax = fabsf(q.re); q.ay = fabsf(q.im);
+		q.mx = fmaxf(q.ax, q.ay); q.mn = fminf(q.ax, q.ay);
+#if defined(__CUDA_ARCH__)
+		const float qq = __fdividef(q.mn, q.mx);
+		uint32_t k = __float_as_uint(__fmaf_rn(qq, 8.0f, 12582912.0f)) & 15u;
+#else
+		const float qq = q.mn / q.mx;
+		float kf = qq * 8.0f + 12582912.0f;
+		uint32_t kb; memcpy(&kb, &kf, 4);
+		uint32_t k = kb & 15u;
+#endif
+		k = k > 8u ? 8u : k;
+		q.A = tab[2 * k]; q.c = tab[2 * k + 1];
+		q.dmx = (double)q.mx; q.dmn = (double)q.mn;
+	} break;
+	case 1:
+		q.num = vdl2_fm_fma(-q.c, q.dmx, q.dmn);
+		q.den = vdl2_fm_fma(q.c, q.dmn, q.dmx);
+#ifdef VDL2_FM_RCP_SEED_OVERRIDE
+		q.r = VDL2_FM_RCP_SEED_OVERRIDE(q.den);
+#else
+		q.r = vdl2_fm_rcp_seed(q.den);
+#endif
+		break;
+	case 2: q.e = vdl2_fm_fma(-q.den, q.r, 1.0); break;
+	case 3: q.r = vdl2_fm_fma(q.r, q.e, q.r); break;
+	case 4: q.t = q.num * q.r; break;
+	case 5: q.e = vdl2_fm_fma(-q.den, q.t, q.num); break;
+	case 6: q.t = vdl2_fm_fma(q.e, q.r, q.t); break;
+	case 7: q.s = q.t * q.t; break;
+	case 8: q.p = vdl2_fm_fma(VDL2_FM_K(0, VDL2_FM_C0), q.s, VDL2_FM_K(1, VDL2_FM_C1)); q.ts = q.t * q.s; break;
+	case 9: q.p = vdl2_fm_fma(q.p, q.s, VDL2_FM_K(2, VDL2_FM_C2)); break;
+	case 10: q.p = vdl2_fm_fma(q.p, q.s, VDL2_FM_K(3, VDL2_FM_C3)); break;
+	case 11: q.p = vdl2_fm_fma(q.p, q.s, VDL2_FM_K(4, VDL2_FM_C4)); break;
+	case 12: q.a = vdl2_fm_fma(q.ts, q.p, q.t); break;
+	case 13: q.a = q.A + q.a; break;
+	case 14: {                                                  /* first quadrant -> first octant pair */
+		const double a1 = (VDL2_FM_K(5, VDL2_PIO2_HI) - q.a) + VDL2_FM_K(6, VDL2_PIO2_LO);
+		q.a = q.ay > q.ax ? a1 : q.a;
+	} break;
+	case 15: {
+		const double a2 = (VDL2_FM_K(7, VDL2_PI_HI) - q.a) + VDL2_FM_K(8, VDL2_PI_LO);
+		q.a = q.re < 0.0f ? a2 : q.a;
+	} break;
+	case 16: {
+		const bool in_range = q.ax <= 1.0e30f && q.ay <= 1.0e30f && q.mx >= 1.0e-30f && (q.mn >= q.mx * 1.0e-6f || q.mn == 0.0f);
+		const bool zero = q.ax == 0.0f && q.ay == 0.0f;
+		const double a = q.a;
+		uint64_t bits;
+#if defined(__CUDA_ARCH__)
+		bits = (uint64_t)__double_as_longlong(a);
+#else
+		memcpy(&bits, &a, 8);
+#endif
+		const uint32_t drop = (uint32_t)bits & 0x1FFFFFFFu;
+		const uint32_t dist = drop > 0x10000000u ? drop - 0x10000000u : 0x10000000u - drop;
+		q.slow = (!zero && (!in_range || (dist < 512u && a != 0.0))) ? 1 : 0;
+		float f = (float)a;
+		uint32_t re_bits, im_bits, f_bits;
+#if defined(__CUDA_ARCH__)
+		re_bits = __float_as_uint(q.re); im_bits = __float_as_uint(q.im); f_bits = __float_as_uint(f);
+#else
+		memcpy(&re_bits, &q.re, 4); memcpy(&im_bits, &q.im, 4); memcpy(&f_bits, &f, 4);
+#endif
+		if(zero) f_bits = (re_bits & 0x80000000u) ? 0x40490FDBu : 0u;
+		f_bits = (f_bits & 0x7FFFFFFFu) | (im_bits & 0x80000000u);
+#if defined(__CUDA_ARCH__)
+		q.f = __uint_as_float(f_bits);
+#else
+		memcpy(&q.f, &f_bits, 4);
+#endif
+	} break;
+	default: break;
+	}
+}
+
 /* hypotf(re, im) as glibc evaluates it for finite arguments, (float)sqrt((double)re*re + (double)im*im) (src/demod.c:238):
- * the sum is formed exactly as there (both squares are exact in double, one rounding), the square root by two Newton
- * steps on the hardware seed (error < 2 ulp of the double) and the same rounding-boundary test as above decides
+ * the sum is formed exactly as there (both squares are exact in double, one rounding), the square root by one coupled Newton
+ * step on the hardware seed plus a residual correction (error < 2 ulp of the double) and the same rounding-boundary test as above decides
  * whether the narrowed float can be trusted; otherwise *slow is set and the caller takes the IEEE square root. */
 VDL2_FM_HD double vdl2_fm_rsqrt_seed(double d) {
 #if defined(__CUDA_ARCH__)
@@ -170,11 +328,9 @@ VDL2_FM_HD float vdl2_mag_fast(float re, float im, int *slow) {
 	const double y = vdl2_fm_rsqrt_seed(s);
 #endif
 	double g = s * y, h = 0.5 * y;
-	double e = vdl2_fm_fma(-g, h, 0.5);
+	double e = vdl2_fm_fma(-g, h, 0.5);                        /* one coupled Newton step: relative error <= ~2^-35 ... */
 	g = vdl2_fm_fma(g, e, g); h = vdl2_fm_fma(h, e, h);
-	e = vdl2_fm_fma(-g, h, 0.5);
-	g = vdl2_fm_fma(g, e, g); h = vdl2_fm_fma(h, e, h);
-	g = vdl2_fm_fma(vdl2_fm_fma(-g, g, s), h, g);              /* residual correction: g within an ulp of sqrt(s) */
+	g = vdl2_fm_fma(vdl2_fm_fma(-g, g, s), h, g);              /* ... squared by the residual correction: g within an ulp of sqrt(s) */
 	uint64_t bits;
 #if defined(__CUDA_ARCH__)
 	bits = (uint64_t)__double_as_longlong(g);

@@ -266,10 +266,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
  * pipe (measured: 6.6 ms instead of 5.1 ms per launch once the channels of a warp sit on different frequencies).
  * BLOCK = 32 keeps one warp per block and a single table copy; the launcher uses it when a 128-channel block would
  * straddle two streams in independent-streams mode. */
-template<int OS, int BLOCK, int BATCH, bool SYM>
+/* break-point table of vdl2_phase_fast: constant memory, copied to shared memory by the kernels that use it */
+__constant__ double c_atan_tab[VDL2_ATAN_TABLE_DOUBLES] = VDL2_ATAN_TABLE_INIT;
+
+/* PH (fused phase pass): the thread also produces the phase of every decimated sample it writes.  In the tile loop the
+ * atan2 of group g-1's output is evaluated during group g, cut into the 17 branch-free stages of vdl2_phase_pipe_stage
+ * (~20 FP64 operations and their conversions) that are issued one per input sample of the unrolled body: the dependent
+ * FP64 chain is thereby spread over the group's FP32 filter recurrence instead of being appended to it (the FP64 pipe is
+ * otherwise idle in this kernel and one warp per SM sub-partition leaves about half of the issue slots empty).  The Ziv
+ * fall-back (about one sample in a million) and the store come at the end of the body. */
+__device__ __forceinline__ float k1_phase_exact(float re, float im, const double *tab) {
+	int slow;
+	float f = vdl2_phase_fast_nb(re, im, tab, &slow);
+	if(slow) f = vdl2_phase_of(re, im);
+	return f;
+}
+
+template<int OS, int BLOCK, int BATCH, bool SYM, bool PH = false>
 __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_params p) {
 	constexpr int TG = K1P_TILE_GROUPS(OS);
 	constexpr int NLUT = BLOCK >= 128 ? 8 : 1;                    /* table copies */
+	static_assert(!PH || (BATCH != 0 && BLOCK >= VDL2_ATAN_TABLE_DOUBLES && OS + BATCH >= VDL2_PHASE_PIPE_STAGES + 2), "fused phase pass: pipelined kernel only");
+	__shared__ double s_atan[PH ? VDL2_ATAN_TABLE_DOUBLES : 1];
 	__shared__ float4 s_lut[257 * NLUT];
 	__shared__ __align__(128) float2 s_tiles[2][TG * OS + 2];
 	__shared__ __align__(8) uint64_t s_bar[2];
@@ -283,6 +301,17 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	for(uint32_t i = tid; i < 257 * NLUT; i += BLOCK) s_lut[i] = p.lut[i / NLUT];
 	const float4 *lut = s_lut + (NLUT > 1 ? (tid & (NLUT - 1)) : 0);       /* this lane's copy; entry i at lut[i * NLUT] */
 	if(tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+	if(PH && tid < VDL2_ATAN_TABLE_DOUBLES) s_atan[tid] = c_atan_tab[tid];
+	float *phase = nullptr;                                   /* this slot's column, row 0 = first sample of the chunk */
+	if(PH && active) {
+		/* history prefix: the last 160 phase rows of the previous chunk (src/demod.c:105-198 looks 150 samples back) */
+		const uint32_t prev_n_dec = p.ca ? p.ca->prev_n_dec : p.prev_n_dec;
+		const float *src = p.phase_prev + (size_t)prev_n_dec * p.n_chp + ch;
+		float *dst = p.phase + ch;
+#pragma unroll 8
+		for(uint32_t i = 0; i < VDL2_SYNC_BUFLEN; i++) dst[(size_t)i * p.n_chp] = src[(size_t)i * p.n_chp];
+		phase = p.phase + (size_t)VDL2_SYNC_BUFLEN * p.n_chp + ch;
+	}
 	float xr1 = 0, xr2 = 0, xi1 = 0, xi2 = 0, yr1 = 0, yr2 = 0, yi1 = 0, yi2 = 0;
 	uint32_t phi = 0, dphi = 0;
 	if(active) k1_load_state(p, ch, xr1, xr2, xi1, xi2, yr1, yr2, yi1, yi2, phi, dphi);
@@ -305,7 +334,12 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	if(active) {
 		for(; pos < head; pos++) {
 			u64 y0 = k1_packed_step(samples[pos], lut[((phi >> 16) & 0xFFu) * NLUT], phi, dphi, x1, x2, y1, y2, c);
-			if(++cnt == OS) { cnt = 0; p.dec[(size_t)m * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0)); m++; }
+			if(++cnt == OS) {
+				cnt = 0;
+				p.dec[(size_t)m * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0));
+				if(PH) phase[(size_t)m * p.n_chp] = k1_phase_exact(f2_lo(y0), f2_hi(y0), s_atan);
+				m++;
+			}
 		}
 	}
 	/* same bookkeeping for every lane, active or not */
@@ -332,6 +366,8 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	__syncthreads();
 	/* the tile loop, compiled twice: with the tile known to start on element 0 the compiler fetches two samples per
 	 * LDS.128; the misaligned case (odd decimation phase on entry) reads from element 1 with 64-bit loads */
+	u64 yprev = f2_pack(1.0f, 0.0f);                              /* output of the previous group, its phase still owed */
+	bool owed = false;
 	auto tile_loop = [&](auto MIS) {
 	for(uint32_t g0 = 0, tile = 0; g0 < n_groups; g0 += TG, tile++) {
 		const uint32_t ng = min((uint32_t)TG, n_groups - g0);
@@ -341,6 +377,8 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 			for(uint32_t g = 0; g < ng; g++) {
 				const float2 *sp = &s_tile[g * OS];
 				u64 y0 = 0;
+				vdl2_phase_pipe pq;
+				if(PH) { pq.re = f2_lo(yprev); pq.im = f2_hi(yprev); }
 				if(BATCH == 0) {
 #pragma unroll
 					for(int k = 0; k < OS; k++)
@@ -356,6 +394,12 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 #pragma unroll
 					for(int k = -LA; k < OS; k++) {
 						const int kl = k + LA, km = k + MA;
+						if(PH) {
+							/* phase of the previous group's output, one link of the FP64 chain per input sample: stage 0
+							 * (break-point look-up, conversions) gets three sample slots, the others one each */
+							const int slot = k + LA, st = slot == 0 ? 0 : slot - 2;
+							if((slot == 0 || slot >= 3) && st < VDL2_PHASE_PIPE_STAGES) vdl2_phase_pipe_stage(pq, st, s_atan);
+						}
 						if(kl < OS) {
 							const uint32_t ph = phi + (uint32_t)kl * dphi;
 							E[kl] = lut[((ph >> 16) & 0xFFu) * NLUT];
@@ -385,6 +429,15 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 					phi += (uint32_t)OS * dphi;
 				}
 				p.dec[(size_t)(m + g) * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0));
+				if(PH) {
+					if(owed) {
+						float ph_prev = pq.f;
+						if(pq.slow) ph_prev = vdl2_phase_of(f2_lo(yprev), f2_hi(yprev));
+						phase[(size_t)(m + g - 1u) * p.n_chp] = ph_prev;
+					}
+					yprev = y0;
+					owed = true;
+				}
 			}
 		}
 		m += ng;
@@ -394,11 +447,17 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	}
 	};
 	if(mis) tile_loop(std::integral_constant<int, 1>{}); else tile_loop(std::integral_constant<int, 0>{});
+	if(PH && active && owed) phase[(size_t)(m - 1u) * p.n_chp] = k1_phase_exact(f2_lo(yprev), f2_hi(yprev), s_atan);
 	/* tail: fewer than OS samples left */
 	if(active) {
 		for(; pos < n_pairs; pos++) {
 			u64 y0 = k1_packed_step(samples[pos], lut[((phi >> 16) & 0xFFu) * NLUT], phi, dphi, x1, x2, y1, y2, c);
-			if(++cnt == OS) { cnt = 0; p.dec[(size_t)m * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0)); m++; }
+			if(++cnt == OS) {
+				cnt = 0;
+				p.dec[(size_t)m * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0));
+				if(PH) phase[(size_t)m * p.n_chp] = k1_phase_exact(f2_lo(y0), f2_hi(y0), s_atan);
+				m++;
+			}
 		}
 		k1_store_state(p, ch, f2_lo(x1), f2_lo(x2), f2_hi(x1), f2_hi(x2), f2_lo(y1), f2_lo(y2), f2_hi(y1), f2_hi(y2), phi);
 	}
@@ -557,7 +616,6 @@ __global__ void __launch_bounds__(K1L_BLOCK) k1_mix_iir_decimate_lanes(vdl2_k1_p
  * (exact sum of squares, Newton square root); only when one of them reports that its double lies within 2^-44 of a
  * float rounding boundary, or for zero / non-finite / extreme inputs (about one sample in 3e5), the libdevice
  * routine / the IEEE square root decide, as they do for every sample when FAST is off. */
-__constant__ double c_atan_tab[VDL2_ATAN_TABLE_DOUBLES] = VDL2_ATAN_TABLE_INIT;
 
 template<bool FAST>
 __global__ void __launch_bounds__(256) k2a_phase_mag(const float2 *__restrict__ dec, float *__restrict__ phase,
@@ -1078,6 +1136,12 @@ extern "C" int vdl2_kernels_init_device(int device) {
 		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK1, 10, false>, pct);
 		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK1, 10, true>, pct);
 		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK1, 10, false>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, true, true>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<20, K1_BLOCK, 10, false, true>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK, 10, true, true>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<10, K1_BLOCK, 10, false, true>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<13, K1_BLOCK, 10, true, true>, pct);
+		vdl2_set_carveout(k1_mix_iir_decimate_packed<13, K1_BLOCK, 10, false, true>, pct);
 		vdl2_set_carveout(k1_mix_iir_decimate_scalar<K1_BLOCK1>, pct);
 		vdl2_set_carveout(k0_convert, pct);
 		vdl2_set_carveout(k0_convert_lanes, pct);
@@ -1126,9 +1190,20 @@ extern "C" int vdl2_launch_k0_lanes(const void *raw, uint32_t n_pairs, uint32_t 
 template<int OS, int BLOCK>
 static void k1_launch_packed(const vdl2_k1_params *p, int variant, bool sym, cudaStream_t st) {
 	const uint32_t blocks = (p->n_chp + BLOCK - 1) / BLOCK;
+	if(BLOCK == K1_BLOCK && variant != 0 && p->phase != nullptr) {            /* fused phase pass */
+		if(sym) k1_mix_iir_decimate_packed<OS, K1_BLOCK, 10, true, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		else k1_mix_iir_decimate_packed<OS, K1_BLOCK, 10, false, true><<<blocks, K1_BLOCK, 0, st>>>(*p);
+		return;
+	}
 	if(variant == 0 && BLOCK == K1_BLOCK) k1_mix_iir_decimate_packed<OS, K1_BLOCK, 0, false><<<blocks, BLOCK, 0, st>>>(*p);
 	else if(sym) k1_mix_iir_decimate_packed<OS, BLOCK, 10, true><<<blocks, BLOCK, 0, st>>>(*p);
 	else k1_mix_iir_decimate_packed<OS, BLOCK, 10, false><<<blocks, BLOCK, 0, st>>>(*p);
+}
+
+extern "C" int vdl2_k1_fuses_phase(uint32_t oversample, uint32_t ch_per_stream, int force_scalar, int variant) {
+	if(force_scalar || variant == 0 || variant == 8 || ch_per_stream == 1) return 0;
+	if(ch_per_stream != 0 && ch_per_stream % K1_BLOCK != 0) return 0;
+	return oversample == 20 || oversample == 10 || oversample == 13;
 }
 
 /* variant: 0 un-pipelined packed kernel, 4 no symmetric-tap specialisation, 8 one warp per block (single NCO table copy),

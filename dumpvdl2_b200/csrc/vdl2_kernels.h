@@ -50,6 +50,12 @@ typedef struct {
 	uint32_t stream_stride;      /* float2 elements between consecutive streams in `samples` (ch_per_stream == 1: per sample row) */
 	const vdl2_chunk_args *ca;   /* NULL, or device pointer overriding n_pairs / cnt0 */
 	vdl2_block_trace *trace_blocks;
+	/* fused phase pass (vdl2_k1_fuses_phase): K1 also writes fl32(atan2(im, re)) of every decimated sample to
+	 * phase[(160 + m) * n_chp + slot] and first copies the 160 history rows from phase_prev[(prev_n_dec + i) * n_chp + slot];
+	 * NULL = decimated samples only (a K2a launch produces the phase plane) */
+	float *phase;
+	const float *phase_prev;
+	uint32_t prev_n_dec;         /* overridden by ca->prev_n_dec */
 } vdl2_k1_params;
 
 typedef struct {
@@ -117,6 +123,9 @@ int vdl2_launch_k0(const void *raw, uint32_t n_pairs, uint32_t fmt, const float 
 int vdl2_launch_k0_lanes(const void *raw, uint32_t n_pairs, uint32_t fmt, const float *levels, float *out2, uint32_t n_streams,
 		uint32_t raw_stride, uint32_t out_stride, uint32_t lanes, uint32_t full_warps, const vdl2_chunk_args *ca, cudaStream_t st);
 int vdl2_launch_k1(const vdl2_k1_params *p, int force_scalar, int variant, cudaStream_t st);
+/* whether vdl2_launch_k1 with these arguments runs a kernel that honours p->phase (the pipelined packed kernel with
+ * 128-channel blocks); everything else leaves the phase plane to K2a */
+int vdl2_k1_fuses_phase(uint32_t oversample, uint32_t ch_per_stream, int force_scalar, int variant);
 int vdl2_launch_copy_hist(const vdl2_k2_params *p, cudaStream_t st);
 int vdl2_launch_k2a(const vdl2_k2_params *p, cudaStream_t st);
 int vdl2_launch_k2a_warps(const vdl2_k2a_params *p, cudaStream_t st);

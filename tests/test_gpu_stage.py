@@ -212,7 +212,7 @@ def test_cuda_graph_replay_equals_direct_launches():
     assert len(f_graph) > 20
 
 
-@pytest.mark.parametrize("env", [dict(VDL2GPU_K2A=0), dict(VDL2GPU_K2_VARIANT=1), dict(VDL2GPU_K2_VARIANT=3),
+@pytest.mark.parametrize("env", [dict(VDL2GPU_K2A=0), dict(VDL2GPU_FUSE_PHASE=1), dict(VDL2GPU_K2_VARIANT=1), dict(VDL2GPU_K2_VARIANT=3),
                                  dict(VDL2GPU_K2_VARIANT=4), dict(VDL2GPU_K2_VARIANT=5), dict(VDL2GPU_K2_VARIANT=0), dict(VDL2GPU_K1_VARIANT=0),
                                  dict(VDL2GPU_K1_VARIANT=8),
                                  dict(VDL2GPU_K1_VARIANT=4)])
