@@ -598,9 +598,9 @@ def main():
                         chunk_pairs=CHUNK_PAIRS, chunks_per_step=CPS, channel_order=args.channel_order,
                         parallelism=(f"channel-shard x{world} (k mod N), {mg.mode_name} fan-out of the IQ chunks" if world > 1 else "single GPU"),
                         l2=f"inputs larger than L2: the per-chunk working set (decimated buffer {n_mine * (CHUNK_PAIRS // OVERSAMPLE) * 8 / 1e6:.0f} MB "
-                           f"written by K1, read by K2a/K2, + phase/magnitude planes) exceeds the 126 MB L2 and is rewritten every chunk",
+                           f"written by K1, read by K2a/K2, + phase plane) exceeds the 126 MB L2 and is rewritten every chunk",
                         k1_impl="scalar" if args.k1_scalar else "pipelined f32x2",
-                        pipeline="two streams: K0/K1 of chunk c+1 beside K2a/K2/K3 of chunk c; three CUDA graph replays per chunk"),
+                        pipeline="two streams in lock step: K2a of chunk c alone (phase pass, full occupancy), then K0/K1 of chunk c+1 beside K2/K3 of chunk c, one block per SM each; three CUDA graph replays per chunk"),
             channels_at_realtime=value / 2.1,
             frames_per_step=A1["frames"] / K,
             step_ms=stat(A1["per_step"]), host_us_per_submit=A1["host_us_per_submit"],

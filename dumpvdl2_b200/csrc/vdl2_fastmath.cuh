@@ -213,95 +213,6 @@ VDL2_FM_HD float vdl2_phase_fast_nb(float re, float im, const double *tab, int *
 #endif
 }
 
-/* vdl2_phase_fast_nb cut into 14 short stages plus a finish, the same operations in the same order.  K1 issues one
- * stage every other input sample of a decimation group, so consecutive links of the dependent FP64 chain are ~75 cycles
- * apart in its instruction stream and never stall its single warp per SM sub-partition. */
-struct vdl2_phase_pipe {
-	float re, im, ax, ay, mx, mn;
-	double A, c, dmx, dmn, num, den, r, e, t, s, p, ts, a;
-	float f;
-	int slow;
-};
-#define VDL2_PHASE_PIPE_STAGES 17
-VDL2_FM_HD void vdl2_phase_pipe_stage(vdl2_phase_pipe &q, int st, const double *tab) {
-	switch(st) {
-	case 0: {
-		q.ax = fabsf(q.re); q.ay = fabsf(q.im);
-		q.mx = fmaxf(q.ax, q.ay); q.mn = fminf(q.ax, q.ay);
-#if defined(__CUDA_ARCH__)
-		const float qq = __fdividef(q.mn, q.mx);
-		uint32_t k = __float_as_uint(__fmaf_rn(qq, 8.0f, 12582912.0f)) & 15u;
-#else
-		const float qq = q.mn / q.mx;
-		float kf = qq * 8.0f + 12582912.0f;
-		uint32_t kb; memcpy(&kb, &kf, 4);
-		uint32_t k = kb & 15u;
-#endif
-		k = k > 8u ? 8u : k;
-		q.A = tab[2 * k]; q.c = tab[2 * k + 1];
-		q.dmx = (double)q.mx; q.dmn = (double)q.mn;
-	} break;
-	case 1:
-		q.num = vdl2_fm_fma(-q.c, q.dmx, q.dmn);
-		q.den = vdl2_fm_fma(q.c, q.dmn, q.dmx);
-#ifdef VDL2_FM_RCP_SEED_OVERRIDE
-		q.r = VDL2_FM_RCP_SEED_OVERRIDE(q.den);
-#else
-		q.r = vdl2_fm_rcp_seed(q.den);
-#endif
-		break;
-	case 2: q.e = vdl2_fm_fma(-q.den, q.r, 1.0); break;
-	case 3: q.r = vdl2_fm_fma(q.r, q.e, q.r); break;
-	case 4: q.t = q.num * q.r; break;
-	case 5: q.e = vdl2_fm_fma(-q.den, q.t, q.num); break;
-	case 6: q.t = vdl2_fm_fma(q.e, q.r, q.t); break;
-	case 7: q.s = q.t * q.t; break;
-	case 8: q.p = vdl2_fm_fma(VDL2_FM_K(0, VDL2_FM_C0), q.s, VDL2_FM_K(1, VDL2_FM_C1)); q.ts = q.t * q.s; break;
-	case 9: q.p = vdl2_fm_fma(q.p, q.s, VDL2_FM_K(2, VDL2_FM_C2)); break;
-	case 10: q.p = vdl2_fm_fma(q.p, q.s, VDL2_FM_K(3, VDL2_FM_C3)); break;
-	case 11: q.p = vdl2_fm_fma(q.p, q.s, VDL2_FM_K(4, VDL2_FM_C4)); break;
-	case 12: q.a = vdl2_fm_fma(q.ts, q.p, q.t); break;
-	case 13: q.a = q.A + q.a; break;
-	case 14: {                                                  /* first quadrant -> first octant pair */
-		const double a1 = (VDL2_FM_K(5, VDL2_PIO2_HI) - q.a) + VDL2_FM_K(6, VDL2_PIO2_LO);
-		q.a = q.ay > q.ax ? a1 : q.a;
-	} break;
-	case 15: {
-		const double a2 = (VDL2_FM_K(7, VDL2_PI_HI) - q.a) + VDL2_FM_K(8, VDL2_PI_LO);
-		q.a = q.re < 0.0f ? a2 : q.a;
-	} break;
-	case 16: {
-		const bool in_range = q.ax <= 1.0e30f && q.ay <= 1.0e30f && q.mx >= 1.0e-30f && (q.mn >= q.mx * 1.0e-6f || q.mn == 0.0f);
-		const bool zero = q.ax == 0.0f && q.ay == 0.0f;
-		const double a = q.a;
-		uint64_t bits;
-#if defined(__CUDA_ARCH__)
-		bits = (uint64_t)__double_as_longlong(a);
-#else
-		memcpy(&bits, &a, 8);
-#endif
-		const uint32_t drop = (uint32_t)bits & 0x1FFFFFFFu;
-		const uint32_t dist = drop > 0x10000000u ? drop - 0x10000000u : 0x10000000u - drop;
-		q.slow = (!zero && (!in_range || (dist < 512u && a != 0.0))) ? 1 : 0;
-		float f = (float)a;
-		uint32_t re_bits, im_bits, f_bits;
-#if defined(__CUDA_ARCH__)
-		re_bits = __float_as_uint(q.re); im_bits = __float_as_uint(q.im); f_bits = __float_as_uint(f);
-#else
-		memcpy(&re_bits, &q.re, 4); memcpy(&im_bits, &q.im, 4); memcpy(&f_bits, &f, 4);
-#endif
-		if(zero) f_bits = (re_bits & 0x80000000u) ? 0x40490FDBu : 0u;
-		f_bits = (f_bits & 0x7FFFFFFFu) | (im_bits & 0x80000000u);
-#if defined(__CUDA_ARCH__)
-		q.f = __uint_as_float(f_bits);
-#else
-		memcpy(&q.f, &f_bits, 4);
-#endif
-	} break;
-	default: break;
-	}
-}
-
 /* hypotf(re, im) as glibc evaluates it for finite arguments, (float)sqrt((double)re*re + (double)im*im) (src/demod.c:238):
  * the sum is formed exactly as there (both squares are exact in double, one rounding), the square root by one coupled Newton
  * step on the hardware seed plus a residual correction (error < 2 ulp of the double) and the same rounding-boundary test as above decides

@@ -269,12 +269,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 /* break-point table of vdl2_phase_fast: constant memory, copied to shared memory by the kernels that use it */
 __constant__ double c_atan_tab[VDL2_ATAN_TABLE_DOUBLES] = VDL2_ATAN_TABLE_INIT;
 
-/* PH (fused phase pass): the thread also produces the phase of every decimated sample it writes.  In the tile loop the
- * atan2 of group g-1's output is evaluated during group g, cut into the 17 branch-free stages of vdl2_phase_pipe_stage
- * (~20 FP64 operations and their conversions) that are issued one per input sample of the unrolled body: the dependent
- * FP64 chain is thereby spread over the group's FP32 filter recurrence instead of being appended to it (the FP64 pipe is
- * otherwise idle in this kernel and one warp per SM sub-partition leaves about half of the issue slots empty).  The Ziv
- * fall-back (about one sample in a million) and the store come at the end of the body. */
+/* PH (fused phase pass, opt-in: VDL2GPU_FUSE_PHASE=1): the thread also produces the phase of every decimated sample it
+ * writes.  In the tile loop the atan2 of group g-1's output is written out as straight-line code at the top of group g's
+ * unrolled body (vdl2_phase_fast_nb: ~20 FP64 operations and their conversions, no branch) so that it can be scheduled
+ * into the group's FP32 filter recurrence; the Ziv fall-back (about one sample in a million) and the store come at the
+ * end of the body.  Measured: 6.4 instead of 5.0 ms per launch, more than the separate K2a pass costs. */
 __device__ __forceinline__ float k1_phase_exact(float re, float im, const double *tab) {
 	int slow;
 	float f = vdl2_phase_fast_nb(re, im, tab, &slow);
@@ -286,7 +285,7 @@ template<int OS, int BLOCK, int BATCH, bool SYM, bool PH = false>
 __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_params p) {
 	constexpr int TG = K1P_TILE_GROUPS(OS);
 	constexpr int NLUT = BLOCK >= 128 ? 8 : 1;                    /* table copies */
-	static_assert(!PH || (BATCH != 0 && BLOCK >= VDL2_ATAN_TABLE_DOUBLES && OS + BATCH >= VDL2_PHASE_PIPE_STAGES + 2), "fused phase pass: pipelined kernel only");
+	static_assert(!PH || (BATCH != 0 && BLOCK >= VDL2_ATAN_TABLE_DOUBLES), "fused phase pass: pipelined kernel only");
 	__shared__ double s_atan[PH ? VDL2_ATAN_TABLE_DOUBLES : 1];
 	__shared__ float4 s_lut[257 * NLUT];
 	__shared__ __align__(128) float2 s_tiles[2][TG * OS + 2];
@@ -377,8 +376,9 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 			for(uint32_t g = 0; g < ng; g++) {
 				const float2 *sp = &s_tile[g * OS];
 				u64 y0 = 0;
-				vdl2_phase_pipe pq;
-				if(PH) { pq.re = f2_lo(yprev); pq.im = f2_hi(yprev); }
+				float ph_prev = 0.0f;
+				int ph_slow = 0;
+				if(PH) ph_prev = vdl2_phase_fast_nb(f2_lo(yprev), f2_hi(yprev), s_atan, &ph_slow);
 				if(BATCH == 0) {
 #pragma unroll
 					for(int k = 0; k < OS; k++)
@@ -394,12 +394,6 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 #pragma unroll
 					for(int k = -LA; k < OS; k++) {
 						const int kl = k + LA, km = k + MA;
-						if(PH) {
-							/* phase of the previous group's output, one link of the FP64 chain per input sample: stage 0
-							 * (break-point look-up, conversions) gets three sample slots, the others one each */
-							const int slot = k + LA, st = slot == 0 ? 0 : slot - 2;
-							if((slot == 0 || slot >= 3) && st < VDL2_PHASE_PIPE_STAGES) vdl2_phase_pipe_stage(pq, st, s_atan);
-						}
 						if(kl < OS) {
 							const uint32_t ph = phi + (uint32_t)kl * dphi;
 							E[kl] = lut[((ph >> 16) & 0xFFu) * NLUT];
@@ -431,8 +425,7 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 				p.dec[(size_t)(m + g) * p.n_chp + ch] = make_float2(f2_lo(y0), f2_hi(y0));
 				if(PH) {
 					if(owed) {
-						float ph_prev = pq.f;
-						if(pq.slow) ph_prev = vdl2_phase_of(f2_lo(yprev), f2_hi(yprev));
+						if(ph_slow) ph_prev = vdl2_phase_of(f2_lo(yprev), f2_hi(yprev));
 						phase[(size_t)(m + g - 1u) * p.n_chp] = ph_prev;
 					}
 					yprev = y0;

@@ -71,14 +71,6 @@ static void worker(int id, uint64_t n) {
 			int s2 = 0;
 			const float g2 = vdl2_phase_fast_nb(re, im, TAB, &s2);
 			uint32_t a2, b2; memcpy(&a2, &g2, 4); memcpy(&b2, &got, 4);
-			{                                          // ... and so must the staged form K1 interleaves with its filter
-				vdl2_phase_pipe q; q.re = re; q.im = im;
-				for(int st = 0; st < VDL2_PHASE_PIPE_STAGES; st++) vdl2_phase_pipe_stage(q, st, TAB);
-				const int s3 = q.slow;
-				const float g3 = q.f;
-				uint32_t a3; memcpy(&a3, &g3, 4);
-				if(s3 != s2 || (!s2 && a3 != a2)) { if(n_bad++ < 20) printf("PIPE MISMATCH re=%a im=%a pipe=%a(%d) nb=%a(%d)\n", re, im, g3, s3, g2, s2); }
-			}
 			if(re == 0.0f && im == 0.0f) { memcpy(&b2, &want, 4); if(s2 || a2 != b2) { if(n_bad++ < 20) printf("NB ZERO MISMATCH re=%a im=%a nb=%a(%d) want=%a\n", re, im, g2, s2, want); } }
 			else if(s2 != slow || (!slow && a2 != b2)) { if(n_bad++ < 20) printf("NB MISMATCH re=%a im=%a nb=%a(%d) fast=%a(%d)\n", re, im, g2, s2, got, slow); }
 		}
