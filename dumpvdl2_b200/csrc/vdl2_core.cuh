@@ -694,13 +694,19 @@ VDL2_HD void vdl2_walk_block_ring(vdl2_chan &v, float *ring, int rs, const vdl2_
 		else if(first == 2) ph[3][14] = pw[1];
 		vdl2_metric_core_n<4, true>(ph, env.pr_phase, env.lr_X, env.lr_denom, env.unwrap_lut, p0, sl);
 		const int sclk_entry = v.sclk;
+		/* The twelve ring slots of the block follow from the entry position (vdl2_init_write advances by one with a
+		 * wrap at 160): slot of sample t = wrap(entry + 1 + t), each computed on its own instead of as a chain of
+		 * twelve dependent updates; the saturating run counter is advanced once, by the number of samples written. */
+		const int rp_entry = v.ring_pos + 1;
+#define VDL2_RING_SLOT(t) ((rp_entry + (t)) >= VDL2_SYNC_BUFLEN ? (rp_entry + (t)) - VDL2_SYNC_BUFLEN : (rp_entry + (t)))
 		bool go = true;
 #pragma unroll
 		for(int g = 0; g < 4; g++) {
 			if(go) {
 #pragma unroll
 				for(int u = 0; u < VDL2_SYNC_SKIP; u++)
-					if(u <= first) vdl2_init_write(v, ring, rs, pw[VDL2_SYNC_SKIP * g + u]);
+					if(u <= first) ring[VDL2_RING_SLOT(VDL2_SYNC_SKIP * g + u) * rs] = pw[VDL2_SYNC_SKIP * g + u];
+				v.ring_pos = VDL2_RING_SLOT(VDL2_SYNC_SKIP * g + first);
 				v.sclk = 0;
 				vdl2_init_eval(v, ring, rs, env, chan_idx, idx0 + (uint64_t)(VDL2_SYNC_SKIP * g + first), mg[g], true, p0[g], sl[g]);
 				if((v.state & VDL2_ST_LOCKED) || v.sclk != 0) {
@@ -709,12 +715,18 @@ VDL2_HD void vdl2_walk_block_ring(vdl2_chan &v, float *ring, int rs, const vdl2_
 				} else {
 #pragma unroll
 					for(int u = 0; u < VDL2_SYNC_SKIP; u++)
-						if(u > first) vdl2_init_write(v, ring, rs, pw[VDL2_SYNC_SKIP * g + u]);
+						if(u > first) ring[VDL2_RING_SLOT(VDL2_SYNC_SKIP * g + u) * rs] = pw[VDL2_SYNC_SKIP * g + u];
+					v.ring_pos = VDL2_RING_SLOT(VDL2_SYNC_SKIP * g + VDL2_SYNC_SKIP - 1);
 					v.sclk = sclk_entry;
 				}
 			}
 		}
+#undef VDL2_RING_SLOT
 		if(go) resume = VDL2_WALK_BLOCK;
+		{
+			const uint32_t run = v.pure_run + (uint32_t)resume;       /* `resume` samples were written above */
+			v.pure_run = run < VDL2_PURE_SATURATED ? run : VDL2_PURE_SATURATED;
+		}
 	}
 	vdl2_walk_tail<STAGED>(v, ring, rs, env, chan_idx, idx0, dec, phase, mag, stride, resume);
 }

@@ -254,4 +254,33 @@ VDL2_FM_HD float vdl2_mag_fast(float re, float im, int *slow) {
 	return (float)g;
 }
 
+/* vdl2_mag_fast as straight-line code: the range test only feeds *slow, so several evaluations can be interleaved by the
+ * instruction scheduler (the K2 walk computes the four magnitudes of a block together). */
+VDL2_FM_HD float vdl2_mag_fast_nb(float re, float im, int *slow) {
+	const float ax = fabsf(re), ay = fabsf(im);
+	const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+	const bool in_range = ax <= 1.0e18f && ay <= 1.0e18f && mx >= 1.0e-18f;
+	const double dmx = (double)mx, dmn = (double)mn;
+	const double s = vdl2_fm_fma(dmx, dmx, dmn * dmn);
+#ifdef VDL2_FM_RSQRT_SEED_OVERRIDE
+	const double y = VDL2_FM_RSQRT_SEED_OVERRIDE(s);
+#else
+	const double y = vdl2_fm_rsqrt_seed(s);
+#endif
+	double g = s * y, h = 0.5 * y;
+	double e = vdl2_fm_fma(-g, h, 0.5);
+	g = vdl2_fm_fma(g, e, g); h = vdl2_fm_fma(h, e, h);
+	g = vdl2_fm_fma(vdl2_fm_fma(-g, g, s), h, g);
+	uint64_t bits;
+#if defined(__CUDA_ARCH__)
+	bits = (uint64_t)__double_as_longlong(g);
+#else
+	memcpy(&bits, &g, 8);
+#endif
+	const uint32_t drop = (uint32_t)bits & 0x1FFFFFFFu;
+	const uint32_t dist = drop > 0x10000000u ? drop - 0x10000000u : 0x10000000u - drop;
+	*slow = (!in_range || dist < 512u) ? 1 : 0;
+	return (float)g;
+}
+
 #endif

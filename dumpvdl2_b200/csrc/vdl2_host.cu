@@ -80,6 +80,7 @@ struct vdl2gpu_ctx {
 	uint64_t chunk_seq = 0;
 	cudaEvent_t ev_input_ready = nullptr, ev_input_consumed = nullptr;
 	uint32_t n_ch = 0, n_chp = 0, max_pairs = 0, max_dec = 0, n_slots = 0, out_cap = 0, event_cap = 0;
+	uint64_t events_dropped = 0;                        /* trace events lost to a full buffer, not yet reported by vdl2gpu_read_events */
 	uint32_t lanes = 32, full_warps = 0xFFFFFFFFu;      /* channel slot mapping (see create_impl) */
 	int n_sms = 148;
 	uint32_t n_streams = 1, ch_per_stream = 0;          /* independent-streams mode: n_streams > 1, channels [s*C, (s+1)*C) on stream s */
@@ -959,6 +960,21 @@ extern "C" int vdl2gpu_read_events(vdl2gpu_ctx *c, vdl2gpu_event *out, uint32_t 
 	if(n > cap) n = cap;
 	if(n) CU(cudaMemcpy(out, (const vdl2gpu_event *)c->d_events + c->events_read, (size_t)n * sizeof(vdl2gpu_event), cudaMemcpyDeviceToHost));
 	c->events_read += n;
+	if(c->events_read == total) {
+		/* drained: the buffer is not a ring, so start it over (nothing is running: both streams were synchronised above).
+		 * Events the kernels could not store because it was full are counted and reported once the stored ones are out. */
+		if(ctl.n_events > c->event_cap) c->events_dropped += ctl.n_events - c->event_cap;
+		if(ctl.n_events) {
+			const uint32_t zero = 0;
+			CU(cudaMemcpy(reinterpret_cast<uint8_t *>(c->d_ctl) + offsetof(vdl2_queue_ctl, n_events), &zero, sizeof(zero), cudaMemcpyHostToDevice));
+			c->events_read = 0;
+		}
+	}
+	if(n == 0 && c->events_dropped) {
+		snprintf(g_last_error, sizeof(g_last_error), "trace buffer overflow: %llu events were not recorded (drain more often)", (unsigned long long)c->events_dropped);
+		c->events_dropped = 0;
+		return VDL2GPU_EOVERFLOW;
+	}
 	return (int)n;
 }
 

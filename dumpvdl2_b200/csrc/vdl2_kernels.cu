@@ -266,6 +266,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
  * pipe (measured: 6.6 ms instead of 5.1 ms per launch once the channels of a warp sit on different frequencies).
  * BLOCK = 32 keeps one warp per block and a single table copy; the launcher uses it when a 128-channel block would
  * straddle two streams in independent-streams mode. */
+/* NCO table look-up of the hot loops: byte offset of entry (phase >> 16) & 0xFF in this lane's copy of the table, formed
+ * as ((phase >> 9) & 0x7F80) | lane_bytes (NLUT = 8: 128 bytes per entry, the copy in bits 4..6) resp. (phase >> 12) & 0xFF0
+ * (single copy) - one shift and one three-input logic operation, the table's shared-memory address folded into the load.
+ * Written via indices the compiler spent a second logic operation and an address add on it. */
+template<int NLUT>
+__device__ __forceinline__ float4 k1_lut_entry(const float4 *s_lut, uint32_t phase, uint32_t lane_bytes) {
+	const uint32_t off = NLUT == 8 ? (((phase >> 9) & 0x7F80u) | lane_bytes) : ((phase >> 12) & 0xFF0u);
+	return *reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(s_lut) + off);
+}
+
 /* break-point table of vdl2_phase_fast: constant memory, copied to shared memory by the kernels that use it */
 __constant__ double c_atan_tab[VDL2_ATAN_TABLE_DOUBLES] = VDL2_ATAN_TABLE_INIT;
 
@@ -299,6 +309,7 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 	const float2 *samples = k1_stream_of(p, blockIdx.x * BLOCK);
 	for(uint32_t i = tid; i < 257 * NLUT; i += BLOCK) s_lut[i] = p.lut[i / NLUT];
 	const float4 *lut = s_lut + (NLUT > 1 ? (tid & (NLUT - 1)) : 0);       /* this lane's copy; entry i at lut[i * NLUT] */
+	const uint32_t lane_bytes = NLUT > 1 ? (tid & (NLUT - 1)) * 16u : 0u;
 	if(tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
 	if(PH && tid < VDL2_ATAN_TABLE_DOUBLES) s_atan[tid] = c_atan_tab[tid];
 	float *phase = nullptr;                                   /* this slot's column, row 0 = first sample of the chunk */
@@ -396,7 +407,7 @@ __global__ void __launch_bounds__(BLOCK) k1_mix_iir_decimate_packed(vdl2_k1_para
 						const int kl = k + LA, km = k + MA;
 						if(kl < OS) {
 							const uint32_t ph = phi + (uint32_t)kl * dphi;
-							E[kl] = lut[((ph >> 16) & 0xFFu) * NLUT];
+							E[kl] = k1_lut_entry<NLUT>(s_lut, ph, lane_bytes);
 							FR[kl] = (float)(ph & 0xFFFFu);
 							S[kl] = sp[kl];
 						}
@@ -487,6 +498,7 @@ __global__ void __launch_bounds__(K1L_BLOCK) k1_mix_iir_decimate_lanes(vdl2_k1_p
 	const float2 *samples = p.samples + (size_t)blockIdx.x * K1L_BLOCK;      /* this block's 128 columns */
 	for(uint32_t i = tid; i < 257 * NLUT; i += K1L_BLOCK) s_lut[i] = p.lut[i / NLUT];
 	const float4 *lut = s_lut + (tid & (NLUT - 1));
+	const uint32_t lane_bytes = (tid & (NLUT - 1)) * 16u;
 	if(tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
 	float xr1 = 0, xr2 = 0, xi1 = 0, xi2 = 0, yr1 = 0, yr2 = 0, yi1 = 0, yi2 = 0;
 	uint32_t phi = 0, dphi = 0;
@@ -551,7 +563,7 @@ __global__ void __launch_bounds__(K1L_BLOCK) k1_mix_iir_decimate_lanes(vdl2_k1_p
 					const int kl = k + LA, km = k + MA;
 					if(kl < OS) {
 						const uint32_t ph = phi + (uint32_t)kl * dphi;
-						E[kl] = lut[((ph >> 16) & 0xFFu) * NLUT];
+						E[kl] = k1_lut_entry<NLUT>(s_lut, ph, lane_bytes);
 						FR[kl] = (float)(ph & 0xFFFFu);
 						S[kl] = sp[kl * K1L_BLOCK];
 					}
@@ -646,7 +658,7 @@ __global__ void __launch_bounds__(256) k2a_phase_mag(const float2 *__restrict__ 
  * into this plane's history rows (the planes alternate between chunks; with n_dec < 160 the source range still lies inside
  * the previous plane, history rows included, so short chunks need no special case). */
 template<bool FAST>
-__global__ void __launch_bounds__(128, 9) k2a_phase_mag_warps(vdl2_k2a_params p) {      /* <= 56 registers: three blocks fit beside K1 and K2 */
+__global__ void __launch_bounds__(128, 8) k2a_phase_mag_warps(vdl2_k2a_params p) {      /* <= 64 registers: 32 warps per SM */
 	__shared__ double s_atan[VDL2_ATAN_TABLE_DOUBLES];
 	if(FAST) {
 		if(threadIdx.x < VDL2_ATAN_TABLE_DOUBLES) s_atan[threadIdx.x] = c_atan_tab[threadIdx.x];
@@ -670,23 +682,36 @@ __global__ void __launch_bounds__(128, 9) k2a_phase_mag_warps(vdl2_k2a_params p)
 	const float2 *dec = p.dec + slot;
 	float *ph = p.phase + (size_t)VDL2_SYNC_BUFLEN * s + slot, *mg = p.mag + slot;
 	uint32_t t = min(n_all, slice * per);
+	const bool want_mag = p.mag != nullptr;
+	/* four samples per step; the next four are requested before the current four are evaluated, so that the loads'
+	 * latency hides behind ~400 instructions of arithmetic (the kernel was long-scoreboard bound without it).  FAST: the
+	 * straight-line form of the fast atan2 lets the four FP64 chains of a step interleave. */
+	float2 nx[4];
+	if(t + 4 <= n_dec) {
+#pragma unroll
+		for(int k = 0; k < 4; k++) nx[k] = dec[(size_t)(t + k) * s];
+	}
 	for(; t + 4 <= n_dec; t += 4) {
 		float2 d[4];
 		float a[4], m[4];
 		int sp[4], sm[4];
 #pragma unroll
-		for(int k = 0; k < 4; k++) d[k] = dec[(size_t)(t + k) * s];
+		for(int k = 0; k < 4; k++) d[k] = nx[k];
+		if(t + 8 <= n_dec) {
+#pragma unroll
+			for(int k = 0; k < 4; k++) nx[k] = dec[(size_t)(t + 4 + k) * s];
+		}
 #pragma unroll
 		for(int k = 0; k < 4; k++) {
 			sm[k] = 1; m[k] = 0.f;
-			if(FAST) { a[k] = vdl2_phase_fast(d[k].x, d[k].y, s_atan, &sp[k]); if(p.mag != nullptr) m[k] = vdl2_mag_fast(d[k].x, d[k].y, &sm[k]); }
+			if(FAST) { a[k] = vdl2_phase_fast_nb(d[k].x, d[k].y, s_atan, &sp[k]); if(want_mag) m[k] = vdl2_mag_fast(d[k].x, d[k].y, &sm[k]); }
 			else { sp[k] = 1; a[k] = 0.f; }
 		}
 #pragma unroll
 		for(int k = 0; k < 4; k++) {
 			if(sp[k]) a[k] = vdl2_phase_of(d[k].x, d[k].y);
 			ph[(size_t)(t + k) * s] = a[k];
-			if(p.mag != nullptr) {
+			if(want_mag) {
 				if(sm[k]) m[k] = vdl2_mag_of(d[k].x, d[k].y);
 				mg[(size_t)(t + k) * s] = m[k];
 			}
@@ -817,12 +842,22 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 				for(int t = 0; t < VDL2_WALK_BLOCK; t++) pf.pw[t] = s_st[b][t][tid];
 				/* the four magnitudes the block's sync attempts use (src/demod.c:238) straight from the staged samples: the
 				 * Ziv-guarded square root, IEEE square root when it asks for it; no magnitude plane is read in this mode */
+				int mg_slow = 0;
 #pragma unroll
-				for(int j = 0; j < 4; j++) {
+				for(int j = 0; j < 4; j++) {                 /* four independent FP64 chains, no branch between them */
 					const float2 dj = s_sd[b][first + VDL2_SYNC_SKIP * j][tid];
 					int slow;
-					pf.mg[j] = vdl2_mag_fast(dj.x, dj.y, &slow);
-					if(slow) pf.mg[j] = vdl2_mag_of(dj.x, dj.y);
+					pf.mg[j] = vdl2_mag_fast_nb(dj.x, dj.y, &slow);
+					mg_slow |= slow << j;
+				}
+				if(mg_slow) {
+#pragma unroll
+					for(int j = 0; j < 4; j++) {
+						if((mg_slow >> j) & 1) {
+							const float2 dj = s_sd[b][first + VDL2_SYNC_SKIP * j][tid];
+							pf.mg[j] = vdl2_mag_of(dj.x, dj.y);
+						}
+					}
 				}
 				pf.first = first; pf.valid = 1;
 				vdl2_walk_block_ring<true>(v, ring, BLOCK, env, chan, dec_base + m, &s_sd[b][0][tid], &s_st[b][0][tid],

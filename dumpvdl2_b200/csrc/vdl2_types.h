@@ -3,7 +3,8 @@
  * Reference citations are file:line under /root/reference.
  *
  * HBM layout per context (one IQ stream, n_ch channels, n_chp = n_ch rounded up to 32):
- *   samples   float2[max_pairs]            K0 -> K1   converted stream (src/demod.c:339-365)
+ *   samples   float2[max_pairs]            K0 -> K1   converted stream {re, im} (src/demod.c:339-365); one stream per
+ *                                                     channel: float2[max_pairs][n_chp], time-major
  *   dec       float2[max_dec][n_chp]       K1 -> K2   decimated samples, TIME-MAJOR: a warp of 32 channels
  *                                                     reads/writes 256 contiguous bytes per time step
  *   phase     float[160+max_dec][n_chp]    K2a -> K2  atan2 of every decimated sample; the first 160 rows carry the

@@ -212,7 +212,9 @@ int vdl2gpu_get_tables(vdl2gpu_ctx *ctx, float levels[256], float sin_lut[257], 
 /* decimated samples of the most recent chunk (VDL2GPU_FLAG_KEEP_DEC): out[n_dec][n_channels][2] floats.
  * *n_dec receives the count; cap_floats is the capacity of out.  Synchronises. */
 int vdl2gpu_read_dec(vdl2gpu_ctx *ctx, float *out, size_t cap_floats, uint32_t *n_dec);
-/* drain trace events (VDL2GPU_FLAG_TRACE).  Synchronises.  Returns the number copied. */
+/* drain trace events (VDL2GPU_FLAG_TRACE).  Synchronises.  Returns the number copied (0: none left).  The device buffer
+ * holds 2^20 events and restarts whenever it has been drained; if it filled up in between, the stored events are
+ * delivered first and the following call returns VDL2GPU_EOVERFLOW once (the count of lost events in vdl2gpu_last_error). */
 int vdl2gpu_read_events(vdl2gpu_ctx *ctx, vdl2gpu_event *out, uint32_t cap);
 /* device time (ms) spent in each kernel for the chunks completed so far, measured with CUDA events on
  * the library's streams when timing was enabled with vdl2gpu_enable_timing(ctx, 1).

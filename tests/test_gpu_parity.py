@@ -87,6 +87,21 @@ def test_frames_match_oracle_and_reference(name, oracle_runs):
     assert st["msg_good"] == len(frames) and st["fcs_good"] == sum(f.fcs_ok for f in frames)
 
 
+def test_trace_events_can_be_drained_between_chunks(oracle_runs):
+    """the trace buffer restarts whenever it has been drained: events read chunk by chunk, concatenated, are the oracle's"""
+    c, o = oracle_runs("cfg2")
+    g = make_gpu(c, vd.FLAG_TRACE)
+    b = util.case_bytes(c)
+    got = []
+    for off in range(0, b.size, c["chunk"]):
+        g.submit(b[off:off + c["chunk"]])
+        got += g.read_events()
+    g.flush()
+    got += g.read_events()
+    assert g.read_events() == []
+    util.assert_events_equal(got, o.events(), "events drained per chunk")
+
+
 def test_golden_wav_sha256(oracle_runs):
     import hashlib
     c, _ = oracle_runs("wav")

@@ -64,6 +64,8 @@ static void worker(int id, uint64_t n) {
 			int ms = 0;
 			const float gm = vdl2_mag_fast(re, im, &ms);
 			const float wm = (float)sqrt((double)re * (double)re + (double)im * (double)im);
+			{ int ms2 = 0; const float gm2 = vdl2_mag_fast_nb(re, im, &ms2); uint32_t a, b; memcpy(&a, &gm, 4); memcpy(&b, &gm2, 4);
+			  if(ms2 != ms || (!ms && a != b)) { if(n_mag_bad++ < 20) printf("MAG NB MISMATCH re=%a im=%a nb=%a(%d) fast=%a(%d)\n", re, im, gm2, ms2, gm, ms); } }
 			if(ms) n_mag_slow++;
 			else { uint32_t a, b; memcpy(&a, &gm, 4); memcpy(&b, &wm, 4); if(a != b) { if(n_mag_bad++ < 20) printf("MAG MISMATCH re=%a im=%a got=%a want=%a\n", re, im, gm, wm); } }
 		}
