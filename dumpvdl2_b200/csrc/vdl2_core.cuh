@@ -19,6 +19,9 @@
 #include <string.h>
 #include "vdl2_types.h"
 
+/* branch layout hints: a sync decision, a noise-floor update or a lock are rare events of the walk's hot path */
+#define VDL2_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#define VDL2_LIKELY(x) __builtin_expect(!!(x), 1)
 #if defined(__CUDACC__)
 #define VDL2_HD __host__ __device__ __forceinline__
 #else
@@ -320,7 +323,7 @@ VDL2_HD int vdl2_preamble_metric(vdl2_chan &v, const float *ring, int rs, const 
 		p0 = vdl2_metric_core(ph, env.pr_phase, env.lr_X, env.lr_denom, &slope);
 	}
 	v.pherr0 = p0;
-	if(v.pherr1 < 4.f && p0 > v.pherr1) {
+	if(VDL2_UNLIKELY(v.pherr1 < 4.f && p0 > v.pherr1)) {
 		float vertex = vdl2_para_vertex((float)v.sclk, v.pherr2, v.pherr1, p0);
 		float neg = -roundf(vertex);
 		/* reachable metric triples give vertex in [-4.5,-1.5]; the guard only keeps the
@@ -449,7 +452,7 @@ VDL2_HD void vdl2_init_eval(vdl2_chan &v, const float *ring, int rs, const vdl2_
 		uint64_t dec_index, float mag, bool have_pre, float pre_p0, float pre_slope) {
 	const float one_minus_mag_lp = 1.0f - 0.9f, one_minus_nf_lp = 1.0f - 0.85f;
 	v.mag_lp = F_ADD(F_MUL(v.mag_lp, 0.9f), F_MUL(mag, one_minus_mag_lp));
-	if(++v.nfcnt == 1000) {
+	if(VDL2_UNLIKELY(++v.nfcnt == 1000)) {
 		v.nfcnt = 0;
 		v.mag_nf = F_ADD(F_ADD(F_MUL(0.85f, v.mag_nf), F_MUL(one_minus_nf_lp, fminf(v.mag_lp, v.mag_nf))), 0.0001f);
 	}
@@ -543,7 +546,7 @@ VDL2_HD void vdl2_walk_block(vdl2_chan &v, float *ring, int rs, const vdl2_k2_en
 					if(u <= first) vdl2_init_write(v, ring, rs, pw[VDL2_SYNC_SKIP * g + u]);
 				v.sclk = 0;
 				vdl2_init_eval(v, ring, rs, env, chan_idx, idx0 + (uint64_t)(VDL2_SYNC_SKIP * g + first), mg[g], true, p0[g], sl[g]);
-				if((v.state & VDL2_ST_LOCKED) || v.sclk != 0) {
+				if(VDL2_UNLIKELY((v.state & VDL2_ST_LOCKED) || v.sclk != 0)) {
 					/* locked on a preamble, or the preamble was vetoed by max_ppm (src/demod.c:190-192 leaves the
 					 * sample clock at the sync point): the per-sample path takes over for the rest of the block */
 					go = false;
@@ -649,11 +652,11 @@ VDL2_HD void vdl2_walk_block_ring(vdl2_chan &v, float *ring, int rs, const vdl2_
 	for(int t = 0; t < VDL2_WALK_BLOCK; t++) pw[t] = pf.pw[t];
 #pragma unroll
 	for(int j = 0; j < 4; j++) mg[j] = pf.mg[j];
-	if(!have_pw && fast) {
+	if(VDL2_UNLIKELY(!have_pw && fast)) {
 #pragma unroll
 		for(int t = 0; t < VDL2_WALK_BLOCK; t++) pw[t] = VDL2_LD(STAGED, phase + (ptrdiff_t)t * (ptrdiff_t)stride);
 	}
-	if(!have_mg && fast) {
+	if(VDL2_UNLIKELY(!have_mg && fast)) {
 #pragma unroll
 		for(int j = 0; j < 4; j++) {
 			const ptrdiff_t o = (ptrdiff_t)(first + VDL2_SYNC_SKIP * j) * (ptrdiff_t)stride;
@@ -709,7 +712,7 @@ VDL2_HD void vdl2_walk_block_ring(vdl2_chan &v, float *ring, int rs, const vdl2_
 				v.ring_pos = VDL2_RING_SLOT(VDL2_SYNC_SKIP * g + first);
 				v.sclk = 0;
 				vdl2_init_eval(v, ring, rs, env, chan_idx, idx0 + (uint64_t)(VDL2_SYNC_SKIP * g + first), mg[g], true, p0[g], sl[g]);
-				if((v.state & VDL2_ST_LOCKED) || v.sclk != 0) {
+				if(VDL2_UNLIKELY((v.state & VDL2_ST_LOCKED) || v.sclk != 0)) {
 					go = false;                      /* locked, or vetoed by max_ppm: the per-sample path takes over */
 					resume = VDL2_SYNC_SKIP * g + first + 1;
 				} else {

@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(128, 8) k2a_phase_mag_warps(vdl2_k2a_params p)
 		}
 #pragma unroll
 		for(int k = 0; k < 4; k++) {
-			if(sp[k]) a[k] = vdl2_phase_of(d[k].x, d[k].y);
+			if(VDL2_UNLIKELY(sp[k])) a[k] = vdl2_phase_of(d[k].x, d[k].y);
 			ph[(size_t)(t + k) * s] = a[k];
 			if(want_mag) {
 				if(sm[k]) m[k] = vdl2_mag_of(d[k].x, d[k].y);
@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(BLOCK) k2_sync_slice(vdl2_k2_params p) {
 					pf.mg[j] = vdl2_mag_fast_nb(dj.x, dj.y, &slow);
 					mg_slow |= slow << j;
 				}
-				if(mg_slow) {
+				if(VDL2_UNLIKELY(mg_slow)) {
 #pragma unroll
 					for(int j = 0; j < 4; j++) {
 						if((mg_slow >> j) & 1) {
