@@ -571,9 +571,11 @@ def main():
                                  "is `traffic`; the bound that binds K1 is `binding` (FP32 issue of one warp per SM sub-partition)",
                             binding=dict(bound="fp32-issue", achieved=fp32 / 1e12, peak=148 * 128 * sm_clock / 1e12, unit="T lane-ops/s",
                                          frac=fp32 / (148 * 128 * sm_clock),
-                                         note="24 individually rounded FP32 operations per channel-sample (12 packed FMUL2/FFMA2; contraction is not "
-                                              "allowed by the bit-exactness contract) against 148 SMs x 128 FP32 lanes x 1.965 GHz; a single warp "
-                                              "per sub-partition can reach ~0.72 of it (26.4 of 37 issue cycles per sample are FP32)"),
+                                         note="24 individually rounded FP32 operations per channel-sample (11 packed FMUL2/FFMA2 + 2 scalar; contraction is "
+                                              "not allowed by the bit-exactness contract) against 148 SMs x 128 FP32 lanes x 1.965 GHz.  One warp per "
+                                              "sub-partition with 27-28 of its 32 lanes holding a channel (16384 channels dealt over 592 warps) caps this at "
+                                              "0.86; a packed operation blocks the issuing warp for 2.25 cycles, so the instruction mix costs ~33 cycles per "
+                                              "sample per warp (36.7 measured) against 24 at the pipe's peak"),
                             stages=stages,
                             measured="CUDA events on the library's streams, kernels serialised (VDL2GPU_FLAG_NO_OVERLAP, kernel-by-kernel "
                                      "launches), same workload and process; value/e2e run the two-stage overlap with CUDA graph replay",
